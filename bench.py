@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- WENO5 Gauss-Seidel reinitialisation throughput (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+A step = one raster cycle (8 in-place sweeps, subs.f90:742-852, each followed by the boundary
+block and the RMS test) of `reinit` over one synthetic grid: the torus+cube STL of BASELINE
+configs 4/5 on a 1024 x 1024 x 1024 fp64 grid per GPU (weak scaling; `--grid` overrides).  The sign
+field fed to reinit is produced by the library's own sign search from the synthetic STL.
+
+  value : Gcell-updates/s, phi resident in HBM, CUDA-event time of the K steps, max over ranks
+  e2e   : same metric through the host-buffer drop-in call lsf_reinit (pinned host phi in, phi out:
+          H2D + 8 sweeps + D2H inside the timed region)
+  roofline : the sweep kernel's algorithmic HBM bytes (24 B per cell update: read phi, read the
+          frozen sign source, write phi) / its mean launch time, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the serial C restatement of the reference (oracle/) on a bounded slab sample
+
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DX = 0.05
+SWEEPS_PER_STEP = 8
+METRIC = "WENO5 reinit Gcell-updates/s"
+UNIT = "Gcell-updates/s"
+BYTES_PER_UPDATE = 24.0          # fp64: read phi + read phiS + write phi
+
+
+# ----------------------------------------------------------------------------------- helpers
+def analytic_sign_field(shape, dx=DX):
+    """Smeared sign (phiSign with gM=1, set3d.f90:260-264) of an analytic torus+cube placed like
+    stl.torus_cube_config -- used for the CPU legs, which must not touch the GPU kernels."""
+    nxp, nyp, nzp = shape
+    ex, ey, ez = ((n - 22.2) * dx for n in shape)
+    s = min(ex, ey)
+    r = 0.12 * s
+    R = 0.5 * s - r
+    x = (np.arange(nxp) * dx - 10 * dx - 0.5 * ex)[:, None, None]
+    y = (np.arange(nyp) * dx - 10 * dx - 0.5 * ey)[None, :, None]
+    z = (np.arange(nzp) * dx - 10 * dx - 0.5 * ez)[None, None, :]
+    zt = -0.5 * ez + r
+    d_t = np.sqrt((np.sqrt(x * x + y * y) - R) ** 2 + (z - zt) ** 2) - r
+    c = 0.18 * s
+    q = np.stack(np.broadcast_arrays(np.abs(x - (0.5 * ex - 0.5 * c)) - 0.5 * c,
+                                     np.abs(y - (0.5 * ey - 0.5 * c)) - 0.5 * c,
+                                     np.abs(z - (0.5 * ez - 0.5 * c)) - 0.5 * c))
+    d_c = np.linalg.norm(np.maximum(q, 0), axis=0) + np.minimum(q.max(axis=0), 0)
+    d = np.minimum(d_t, d_c)
+    return np.asfortranarray(d / np.sqrt(d * d + dx * dx))
+
+
+def cpu_sample(nxy, nzs, sweeps):
+    """Times the oracle (serial C restatement of subs.f90:717-931) on an nxy x nxy x nzs slab cut
+    through the torus of the same synthetic geometry.  Returns (Gcell-updates/s, description)."""
+    from oracle import oracle as O
+    O.build()
+    full = (nxy, nxy, max(nzs, 64))
+    # the torus sits at the low-z end of the bbox: take the slab around its mid-plane
+    r_cells = int(0.12 * (nxy - 22.2))
+    k0 = max(0, 10 + r_cells - nzs // 2)
+    shape = (nxy, nxy, nzs)
+    nxp, nyp, nzp = full
+    ex = (nxp - 22.2) * DX
+    s = ex
+    r = 0.12 * s
+    R = 0.5 * s - r
+    x = (np.arange(nxp) * DX - 10 * DX - 0.5 * ex)[:, None, None]
+    y = (np.arange(nyp) * DX - 10 * DX - 0.5 * ex)[None, :, None]
+    z = ((np.arange(nzs) + k0) * DX - 10 * DX - r)[None, None, :]
+    d = np.sqrt((np.sqrt(x * x + y * y) - R) ** 2 + z ** 2) - r
+    phi = np.asfortranarray(d / np.sqrt(d * d + DX * DX))
+    dxx = DX / (np.sqrt(3.0) * ex)
+    t0 = time.perf_counter()
+    O.reinit(phi, sweeps - 1, DX, 0.1 * dxx, tol=0.0)
+    dt = time.perf_counter() - t0
+    cells = (shape[0] - 2) * (shape[1] - 2) * (shape[2] - 2) * sweeps
+    return cells / dt / 1e9, f"{sweeps} sweep(s) on a {shape[0]}x{shape[1]}x{shape[2]} slab through the torus, {dt:.1f} s"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for q, n in enumerate(names) if any(len(r) >= 6 and r[2 + q].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nxy = args.grid
+    nzs = args.ref_slab
+    rates = []
+    desc = ""
+    for q in range(args.warmup + args.steps):
+        v, desc = cpu_sample(nxy, nzs, 1)
+        if q >= args.warmup:
+            rates.append(v)
+    value = float(np.mean(rates)) if rates else 0.0
+    cells = (nxy - 2) * (nxy - 2) * (nzs - 2)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cells / value / 1e6 if value else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"torus+cube sign field, {nxy}^3-class grid, reinit-only; each step = 1 GS sweep + BC + RMS "
+                                   f"on a {nxy}x{nxy}x{nzs} slab sample", "grid_per_gpu": [nxy, nxy, nxy]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": desc + " per step; serial C restatement of the serial reference (no Fortran "
+                                              "compiler in the image, reference cannot be built)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from levelsetfortran_b200 import DeviceGrid, _lib, build, stl
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    L = _lib.lib()
+    _lib.check(L.lsf_init(local))
+    _lib.check(L.lsf_set_arith(_lib.ARITH_EXACT if args.arith == "exact" else _lib.ARITH_FAST))
+    _lib.check(L.lsf_set_sched(_lib.SCHED_PLANE if args.sched == "plane" else _lib.SCHED_MARCH))
+    L.lsf_set_profile(1)
+
+    n = args.grid
+    shape_pts = (n, n, n)                                      # per GPU (weak scaling)
+    tris = stl.torus_cube_config(shape_pts, DX)
+    surfX, surfElem = stl.dedup_nodes(tris)
+    g = stl.grid_from_surface(surfX, DX)
+    nx, ny, nz = g["nx"], g["ny"], g["nz"]
+    assert (nx + 1, ny + 1, nz + 1) == shape_pts
+    h = 0.1 * g["dxx"]                                         # CFL = .1, set3d.f90:304-305
+    cells_per_step = (nx - 1) * (ny - 1) * (nz - 1) * SWEEPS_PER_STEP
+
+    G = DeviceGrid(nx, ny, nz)
+    G.fill(1.0)
+    t0 = time.perf_counter()
+    G.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
+    sign_ms, _ = _lib.last_timing()
+    setup_s = time.perf_counter() - t0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        rc, n_exit, hist = G.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)     # tol 0: never EXITs early
+        assert rc == 0 and n_exit == SWEEPS_PER_STEP - 1, (rc, n_exit)
+        return hist
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms = sweep_ms = 0.0
+    n_sweeps = launches = 0
+    hist = None
+    for _ in range(args.steps):
+        hist = step()
+        ms, nl = _lib.last_timing()
+        sm, ns = _lib.last_sweep_timing()
+        dev_ms += ms; launches += nl; sweep_ms += sm; n_sweeps += ns
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop()
+
+    # ---- e2e: the host-buffer drop-in call, pinned host memory, H2D + compute + D2H timed ------
+    e2e = None
+    if not args.no_e2e:
+        npts = (nx + 1) * (ny + 1) * (nz + 1)
+        host = torch.empty(npts, dtype=torch.float64, pin_memory=True)
+        G.download_ptr(host.data_ptr())                        # current phi as the e2e input
+        hist_buf = np.zeros(SWEEPS_PER_STEP)
+        import ctypes as C
+        n_exit = C.c_int(0)
+        def e2e_step():
+            rc = L.lsf_reinit(C.cast(host.data_ptr(), _lib.c_double_p), None, None, nx, ny, nz, SWEEPS_PER_STEP - 1,
+                              DX, h, C.byref(n_exit), hist_buf.ctypes.data_as(_lib.c_double_p))
+            _lib.check(rc)
+        G.close()                                              # free the resident grid: lsf_reinit allocates its own
+        e2e_step()                                             # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(1, min(args.steps, 3))
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / k_e2e
+        e2e = {"e2e_s": e2e_s, "bytes": npts * 8}
+    else:
+        G.close()
+
+    # ---- reduce over ranks: MAX time -----------------------------------------------------------
+    t = torch.tensor([dev_ms, wall_ms, e2e["e2e_s"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max, e2e_s_max = (float(v) for v in t.cpu())
+
+    if rank == 0:
+        value = world * cells_per_step * args.steps / (dev_ms_max * 1e-3) / 1e9
+        peak, peak_src = measured_peak()
+        launch_ms = sweep_ms / max(n_sweeps, 1)
+        cells_per_launch = (nx - 1) * (ny - 1) * (nz - 1)
+        achieved = BYTES_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
+        cpu = None
+        if not args.no_cpu:
+            v, desc = cpu_sample(n, args.ref_slab, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": desc + "; serial C restatement of the serial reference (reference itself is Fortran, no "
+                                    "compiler in the image)"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"BASELINE config 4/5: synthetic torus+cube STL ({len(surfElem)} triangles) on a "
+                                       f"{n}x{n}x{n} fp64 grid per GPU, reinit-only, one step = {SWEEPS_PER_STEP} Gauss-Seidel "
+                                       "raster sweeps (+BC+RMS each)",
+                           "grid_per_gpu": list(shape_pts), "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX, "h": h,
+                           "arith": args.arith, "sched": args.sched,
+                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak)",
+                           "l2": "inputs larger than L2 (%.1f GB per field)" % (8e-9 * n ** 3),
+                           "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
+                           "last_rms": float(hist[-1]) if hist is not None else None},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak if achieved else None, "traffic": None,
+                             "kernel": "k_reinit_march" if args.sched == "march" else "k_reinit_plane",
+                             "launch_ms": launch_ms, "peak_source": peak_src,
+                             "note": "fp64 WENO5 is FP64-pipe bound (SURVEY.md fact 4); see DESIGN.md"},
+                "cpu_baseline": cpu,
+                "e2e": ({"value": world * cells_per_step / e2e_s_max / 1e9, "unit": UNIT,
+                         "h2d_bytes_per_step": e2e["bytes"], "d2h_bytes_per_step": e2e["bytes"],
+                         "api": "lsf_reinit (host-buffer drop-in)"} if e2e else None),
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=1024, help="grid points per axis per GPU")
+    ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--sched", default="march", choices=["march", "plane"])
+    ap.add_argument("--ref-slab", type=int, default=32, help="z thickness of the CPU sample slab")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+/*
+ * lsf_b200.h -- C ABI of the B200-native grid hot path for LevelSetFortran.
+ *
+ * The reference (musheen/LevelSetFortran) has no FFI layer: its boundary is the
+ * set of `set_subs` module procedures and two inline loops that `set3d.f90`
+ * runs over phi(0:nx,0:ny,0:nz).  Per-cell routines (weno, phiSign,
+ * secondDeriv, minMax) are the wrong granularity for a device, so this ABI
+ * exports the enclosing whole-grid loops.  Each entry point cites the reference
+ * code it replaces.  The Fortran ISO_C_BINDING interface for these symbols is in
+ * fortran/lsf_b200_mod.f90 and INTEGRATION.md shows the calls to substitute in
+ * set3d.f90.
+ *
+ * Conventions
+ *  - All grid arrays are the reference's own: REAL(8)/INTEGER(4), Fortran
+ *    column-major, extents (0:nx,0:ny,0:nz), i fastest, contiguous, owned by the
+ *    caller.  Host entry points copy in/out; the library owns all device memory.
+ *  - Return value: 0 = ok, 1 = a NaN RMS was produced (the reference STOPs at
+ *    subs.f90:926 / set3d.f90:458; the caller decides), < 0 = failure
+ *    (LSF_ERR_*); lsf_last_error() gives the text.  The library never aborts.
+ *  - Calls are synchronous and must come from one host thread per process
+ *    (one process per GPU).  There is no CPU fallback: without a CUDA device
+ *    every compute entry point returns LSF_ERR_CUDA.
+ */
+#ifndef LSF_B200_H
+#define LSF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSF_OK 0
+#define LSF_NAN 1
+#define LSF_ERR_CUDA (-1)
+#define LSF_ERR_ARG (-2)
+#define LSF_ERR_BAND_ON_BOUNDARY (-3) /* a narrow-band cell lies on the grid boundary: the
+                                         reference would read phi(-1,..) (set3d.f90:402-403) */
+
+/* arithmetic of the WENO5 cell update */
+#define LSF_ARITH_FAST 0  /* FMA + reciprocal-reduced form, <= 1e-10 of the reference (default) */
+#define LSF_ARITH_EXACT 1 /* the reference's operation order, IEEE div/sqrt, no FMA: bit-identical */
+/* schedule of the in-place Gauss-Seidel sweeps (both are exact re-orderings) */
+#define LSF_SCHED_MARCH 0 /* skewed x-marching column tiles, one launch per sweep (default) */
+#define LSF_SCHED_PLANE 1 /* one launch per global hyperplane; simple cross-check path */
+
+typedef struct lsf_grid lsf_grid; /* a device-resident phi(0:nx,0:ny,0:nz) plus work arrays */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int lsf_init(int device);          /* device < 0: use $LOCAL_RANK, else 0 */
+int lsf_finalize(void);
+const char *lsf_last_error(void);
+int lsf_set_arith(int arith);      /* LSF_ARITH_*  */
+int lsf_set_sched(int sched);      /* LSF_SCHED_*  */
+/* Timing of the kernels of the most recent lsf_*reinit / lsf_*minmax / lsf_*sign_init call,
+ * CUDA events on the library's own stream: total ms, number of kernel launches. */
+int lsf_last_timing(double *kernel_ms, int *n_launches);
+/* With profiling on, every sweep kernel launch of lsf_*reinit is bracketed by its own event pair;
+ * lsf_last_sweep_timing returns their summed duration and count for the most recent call. */
+int lsf_set_profile(int on);
+int lsf_last_sweep_timing(double *sweep_ms, int *n_sweeps);
+
+/* ---- host-buffer entry points (the drop-in boundary) ------------------------------------ */
+
+/* Inside/outside sign search, replaces the inline loop set3d.f90:196-268 (+ phiSign,
+ * subs.f90:169).  phi must already hold the caller's fill value (reference: 1., set3d.f90:161);
+ * only points of the sub-box [im..ip]x[jm..jp]x[km..kp] are overwritten.
+ * surfX: REAL(8) (nSurfNode,3); surfElem: INTEGER(4) (nSurfElem,3), 1-based (subs.f90:84-88). */
+int lsf_sign_init(double *phi, int nx, int ny, int nz, const double xLo[3], double dx,
+                  const double *surfX, int nSurfNode, const int32_t *surfElem, int nSurfElem,
+                  int im, int ip, int jm, int jp, int km, int kp);
+
+/* SUBROUTINE reinit(phi,gradPhi,gradPhiMag,nx,ny,nz,iter,dx,h), subs.f90:717-931.
+ * gradPhi (0:nx,0:ny,0:nz,3) / gradPhiMag may be NULL (both are dead downstream,
+ * set3d.f90:372-375); when given they receive the last sweep's weno outputs (subs.f90:696-703).
+ * n_exit: loop index n at which the routine left; rms_hist[0..iter]: phiErr per sweep
+ * (the values the reference prints at subs.f90:923).  Exit tolerance 1.E-5 (subs.f90:915). */
+int lsf_reinit(double *phi, double *gradPhi, double *gradPhiMag, int nx, int ny, int nz,
+               int iter, double dx, double h, int *n_exit, double *rms_hist);
+
+/* SUBROUTINE narrowBand(nx,ny,nz,dx,phi,phiNB,phiSB), subs.f90:178-207. */
+int lsf_narrowband(int nx, int ny, int nz, double dx, const double *phi,
+                   int32_t *phiNB, int32_t *phiSB);
+
+/* The min/max flow time loop, set3d.f90:394-462 (secondDeriv subs.f90:370-407, minMax
+ * subs.f90:413-483, RMS/exit :435-451, narrowBand :460).  On entry phiNB/phiSB hold
+ * narrowBand(phi) (set3d.f90:360) and phiN = phi (:377); on exit all five arrays hold what
+ * the reference loop leaves in them.  tol is 1.E-7 in the reference (:448).
+ * rms_hist[0..iter-1]: phiErr of iteration n = 1..iter. */
+int lsf_minmax(double *phi, double *phiN, int32_t *phiNB, int32_t *phiSB,
+               int nx, int ny, int nz, int iter, double dx, double h1, double tol,
+               int *n_exit, double *rms_hist);
+
+/* ---- device-resident pipeline (no host round trip between stages) ------- */
+int lsf_grid_create(lsf_grid **g, int nx, int ny, int nz);
+int lsf_grid_destroy(lsf_grid *g);
+int lsf_grid_fill(lsf_grid *g, double value);                       /* phi = value, set3d.f90:161 */
+int lsf_grid_upload(lsf_grid *g, const double *phi_host);           /* H2D, dense Fortran layout */
+int lsf_grid_download(lsf_grid *g, double *phi_host);               /* D2H */
+int lsf_grid_download_phiN(lsf_grid *g, double *phiN_host);
+void *lsf_grid_device_ptr(lsf_grid *g);                             /* device address of phi(0,0,0) */
+int lsf_grid_sign_init(lsf_grid *g, const double xLo[3], double dx,
+                       const double *surfX, int nSurfNode, const int32_t *surfElem, int nSurfElem,
+                       int im, int ip, int jm, int jp, int km, int kp);
+int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol,
+                    int *n_exit, double *rms_hist);
+int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *phiSB_host);
+int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol,
+                    int *n_exit, double *rms_hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSF_B200_H */

@@ -1,0 +1,480 @@
+// lsf_api.cu -- the C ABI (include/lsf_b200.h): library state, device-resident grid objects,
+// the iteration loops of reinit (subs.f90:735-928) and min/max flow (set3d.f90:394-462), and the
+// host-buffer drop-in entry points.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "lsf_internal.cuh"
+
+namespace lsf {
+
+Global G;
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(G.err, sizeof(G.err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int ensure_init()
+{
+    if (G.inited) return LSF_OK;
+    return lsf_init(-1);
+}
+
+struct Timer {
+    void start() { G.n_launch = 0; cudaEventRecord(G.ev0, G.stream); }
+    int stop()
+    {
+        LSF_CUDA(cudaEventRecord(G.ev1, G.stream));
+        LSF_CUDA(cudaEventSynchronize(G.ev1));
+        float ms = 0.f;
+        LSF_CUDA(cudaEventElapsedTime(&ms, G.ev0, G.ev1));
+        G.last_ms = ms;
+        return LSF_OK;
+    }
+};
+
+static int ensure_hist(Grid *g, int n)
+{
+    if (g->hist_cap >= n) return LSF_OK;
+    if (g->hist) cudaFree(g->hist);
+    g->hist = nullptr;
+    g->hist_cap = 0;
+    int cap = n < 16384 ? 16384 : n;
+    LSF_CUDA(cudaMalloc(&g->hist, sizeof(double) * (size_t)cap));
+    g->hist_cap = cap;
+    return LSF_OK;
+}
+
+static int read_ctrl(Grid *g, Ctrl *h)
+{
+    LSF_CUDA(cudaMemcpyAsync(h, g->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, G.stream));
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    return LSF_OK;
+}
+
+// reinit, subs.f90:717-931.  d_gradPhi / d_gradPhiMag: optional device arrays.
+static int reinit_core(Grid *g, int iter, double dx, double h, double tol, double *d_gradPhi, double *d_gradPhiMag,
+                       int *n_exit, double *rms_hist)
+{
+    if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "reinit: bad iter/dx");
+    if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "reinit: grid too small");
+    int rc = ensure_hist(g, iter + 1);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * (size_t)g->np;
+    LSF_CUDA(cudaMemcpyAsync(g->phiS, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:731
+    LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
+    LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
+    CellConst cc;
+    cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
+    const bool want_grad = d_gradPhi || d_gradPhiMag;
+    const bool march = (G.sched == LSF_SCHED_MARCH) && !want_grad;
+    if (march) { rc = march_prepare(g); if (rc) return rc; }
+    const int check = march ? 8 : (g->np > 2000000 ? 1 : 8);
+    Timer tm;
+    tm.start();
+    Ctrl hc = {0, 0, 0, 0};
+    G.sweep_ms = 0.; G.n_sweeps = 0;
+    static cudaEvent_t pev[16][2];
+    static bool pev_init = false;
+    if (G.profile && !pev_init) {
+        for (int q = 0; q < 16; ++q) { LSF_CUDA(cudaEventCreate(&pev[q][0])); LSF_CUDA(cudaEventCreate(&pev[q][1])); }
+        pev_init = true;
+    }
+    int npend = 0;
+    for (int n = 0; n <= iter; ++n) {                                   // subs.f90:735
+        const int raster = n % 8 + 1;                                   // subs.f90:740,855
+        if (G.profile) cudaEventRecord(pev[npend][0], G.stream);
+        if (march) launch_reinit_sweep_march(g, raster, cc);
+        else launch_reinit_sweep_plane(g, raster, cc, d_gradPhi, d_gradPhiMag);
+        if (G.profile) { cudaEventRecord(pev[npend][1], G.stream); ++npend; }
+        launch_reinit_bc(g, dx);                                        // subs.f90:858-897
+        launch_rms(g, true);                                            // subs.f90:902-914,921
+        launch_finalize(g, RMS_BLOCKS, 0, tol);                         // subs.f90:914-926
+        if ((n + 1) % check == 0 || n == iter) {
+            rc = read_ctrl(g, &hc);
+            if (rc) return rc;
+            for (int q = 0; q < npend; ++q) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, pev[q][0], pev[q][1]) == cudaSuccess) { G.sweep_ms += ms; G.n_sweeps++; }
+            }
+            npend = 0;
+            if (hc.done) break;
+        }
+    }
+    rc = tm.stop();
+    if (rc) return rc;
+    LSF_CUDA(cudaGetLastError());
+    const int ne = hc.done ? hc.n_exit : iter;
+    if (G.profile && G.n_sweeps > ne + 1) {   // sweeps enqueued after the exit were no-ops
+        G.n_sweeps = ne + 1;
+    }
+    if (n_exit) *n_exit = ne;
+    if (rms_hist) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)(ne + 1), cudaMemcpyDeviceToHost));
+    return hc.done ? hc.status : LSF_OK;
+}
+
+static int ensure_minmax_buffers(Grid *g)
+{
+    if (!g->lap) LSF_CUDA(cudaMalloc(&g->lap, sizeof(double) * (size_t)g->np));
+    if (!g->mask) LSF_CUDA(cudaMalloc(&g->mask, (size_t)g->np));
+    return LSF_OK;
+}
+
+// The min/max loop, set3d.f90:394-462.  phiN must already equal phi (set3d.f90:377).
+static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool mask_given,
+                       int *n_exit, double *rms_hist, int *converged)
+{
+    if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "minmax: bad iter/dx");
+    int rc = ensure_hist(g, iter + 1);
+    if (rc) return rc;
+    rc = ensure_minmax_buffers(g);
+    if (rc) return rc;
+    Ctrl init = {0, 0, 1, 0};
+    LSF_CUDA(cudaMemcpyAsync(g->ctrl, &init, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    Timer tm;
+    tm.start();
+    Ctrl hc = init;
+    const int check = g->np > 2000000 ? 1 : 8;
+    for (int n = 1; n <= iter; ++n) {                                   // set3d.f90:394
+        launch_minmax_iteration_plane(g, dx, h1, mask_given && n == 1); // :399-431 (+ narrowBand :460 of n-1)
+        launch_rms(g, false);                                           // :435-447
+        launch_finalize(g, RMS_BLOCKS, 1, tol);                         // :447-458
+        launch_copy_if_running(g, g->phiN, g->phi);                     // :454
+        if (n % check == 0 || n == iter) {
+            rc = read_ctrl(g, &hc);
+            if (rc) return rc;
+            if (hc.done || hc.status < 0) break;
+        }
+    }
+    rc = tm.stop();
+    if (rc) return rc;
+    LSF_CUDA(cudaGetLastError());
+    if (hc.status == LSF_ERR_BAND_ON_BOUNDARY)
+        return set_error(LSF_ERR_BAND_ON_BOUNDARY, "minmax: narrow band touches the grid boundary");
+    const int ne = hc.done ? hc.n_exit : iter;
+    if (n_exit) *n_exit = ne;
+    if (converged) *converged = (hc.done && hc.status == 0) ? 1 : 0;
+    if (rms_hist && ne >= 1) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)ne, cudaMemcpyDeviceToHost));
+    return hc.done ? hc.status : LSF_OK;
+}
+
+static int sign_core(Grid *g, const double xLo[3], double dx, const double *surfX, int nNode,
+                     const int32_t *surfElem, int nElem, int im, int ip, int jm, int jp, int km, int kp)
+{
+    const Dims &dm = g->dm;
+    if (nNode < 1 || nElem < 1) return set_error(LSF_ERR_ARG, "sign_init: empty surface");
+    if (im < 0 || jm < 0 || km < 0 || ip > dm.nx || jp > dm.ny || kp > dm.nz || ip < im || jp < jm || kp < km)
+        return set_error(LSF_ERR_ARG, "sign_init: sub-box outside the grid");
+    for (long long q = 0; q < 3LL * nElem; ++q)
+        if (surfElem[q] < 1 || surfElem[q] > nNode) return set_error(LSF_ERR_ARG, "sign_init: surfElem index out of range");
+    double *d_X = nullptr, *d_cen = nullptr;
+    int32_t *d_E = nullptr;
+    LSF_CUDA(cudaMalloc(&d_X, sizeof(double) * 3 * (size_t)nNode));
+    LSF_CUDA(cudaMalloc(&d_E, sizeof(int32_t) * 3 * (size_t)nElem));
+    LSF_CUDA(cudaMalloc(&d_cen, sizeof(double) * 3 * (size_t)nElem));
+    LSF_CUDA(cudaMemcpyAsync(d_X, surfX, sizeof(double) * 3 * (size_t)nNode, cudaMemcpyHostToDevice, G.stream));
+    LSF_CUDA(cudaMemcpyAsync(d_E, surfElem, sizeof(int32_t) * 3 * (size_t)nElem, cudaMemcpyHostToDevice, G.stream));
+    Timer tm;
+    tm.start();
+    launch_sign_init(g, xLo, dx, d_X, nNode, d_E, nElem, d_cen, im, ip, jm, jp, km, kp);
+    int rc = tm.stop();
+    cudaError_t e = cudaGetLastError();
+    cudaFree(d_X); cudaFree(d_E); cudaFree(d_cen);
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "sign_init: %s", cudaGetErrorString(e));
+    return LSF_OK;
+}
+
+}  // namespace lsf
+
+using namespace lsf;
+
+// =============================================================================================
+extern "C" {
+
+int lsf_init(int device)
+{
+    if (G.inited) return LSF_OK;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_error(LSF_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % ndev : 0;
+    }
+    if (device >= ndev) return set_error(LSF_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    LSF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LSF_CUDA(cudaGetDeviceProperties(&prop, device));
+    G.device = device;
+    G.num_sms = prop.multiProcessorCount;
+    LSF_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+    LSF_CUDA(cudaEventCreate(&G.ev0));
+    LSF_CUDA(cudaEventCreate(&G.ev1));
+    G.inited = true;
+    return LSF_OK;
+}
+
+int lsf_finalize(void)
+{
+    if (!G.inited) return LSF_OK;
+    cudaStreamSynchronize(G.stream);
+    cudaEventDestroy(G.ev0);
+    cudaEventDestroy(G.ev1);
+    cudaStreamDestroy(G.stream);
+    G.inited = false;
+    return LSF_OK;
+}
+
+const char *lsf_last_error(void) { return G.err; }
+
+int lsf_set_arith(int arith)
+{
+    if (arith != LSF_ARITH_FAST && arith != LSF_ARITH_EXACT) return set_error(LSF_ERR_ARG, "bad arith %d", arith);
+    G.arith = arith;
+    return LSF_OK;
+}
+
+int lsf_set_sched(int sched)
+{
+    if (sched != LSF_SCHED_MARCH && sched != LSF_SCHED_PLANE) return set_error(LSF_ERR_ARG, "bad sched %d", sched);
+    G.sched = sched;
+    return LSF_OK;
+}
+
+int lsf_set_profile(int on)
+{
+    G.profile = on != 0;
+    return LSF_OK;
+}
+
+int lsf_last_sweep_timing(double *sweep_ms, int *n_sweeps)
+{
+    if (sweep_ms) *sweep_ms = G.sweep_ms;
+    if (n_sweeps) *n_sweeps = G.n_sweeps;
+    return LSF_OK;
+}
+
+int lsf_last_timing(double *kernel_ms, int *n_launches)
+{
+    if (kernel_ms) *kernel_ms = G.last_ms;
+    if (n_launches) *n_launches = G.n_launch;
+    return LSF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int lsf_grid_create(lsf_grid **out, int nx, int ny, int nz)
+{
+    if (!out) return set_error(LSF_ERR_ARG, "null handle");
+    *out = nullptr;
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (nx < 1 || ny < 1 || nz < 1) return set_error(LSF_ERR_ARG, "grid extents must be >= 1");
+    Grid *g = (Grid *)calloc(1, sizeof(Grid));
+    if (!g) return set_error(LSF_ERR_ARG, "out of host memory");
+    g->dm.nx = nx; g->dm.ny = ny; g->dm.nz = nz;
+    g->dm.sx = (long long)nx + 1;
+    g->dm.sxy = g->dm.sx * ((long long)ny + 1);
+    g->np = g->dm.sxy * ((long long)nz + 1);
+    const size_t bytes = sizeof(double) * (size_t)g->np;
+    cudaError_t e;
+    if ((e = cudaMalloc(&g->phi, bytes)) != cudaSuccess || (e = cudaMalloc(&g->phiS, bytes)) != cudaSuccess ||
+        (e = cudaMalloc(&g->phiN, bytes)) != cudaSuccess ||
+        (e = cudaMalloc(&g->partial, sizeof(double) * 65536)) != cudaSuccess ||
+        (e = cudaMalloc(&g->ctrl, sizeof(Ctrl))) != cudaSuccess) {
+        lsf_grid_destroy(g);
+        return set_error(LSF_ERR_CUDA, "grid_create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return LSF_OK;
+}
+
+int lsf_grid_destroy(lsf_grid *g)
+{
+    if (!g) return LSF_OK;
+    if (G.inited) cudaStreamSynchronize(G.stream);
+    cudaFree(g->phi); cudaFree(g->phiS); cudaFree(g->phiN); cudaFree(g->lap); cudaFree(g->mask);
+    cudaFree(g->partial); cudaFree(g->hist); cudaFree(g->ctrl);
+    cudaFree(g->march_ticket); cudaFree(g->march_progress);
+    free(g);
+    return LSF_OK;
+}
+
+int lsf_grid_fill(lsf_grid *g, double value)
+{
+    if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    launch_fill(g, g->phi, value);
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    return LSF_OK;
+}
+
+int lsf_grid_upload(lsf_grid *g, const double *phi_host)
+{
+    if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
+    LSF_CUDA(cudaMemcpyAsync(g->phi, phi_host, sizeof(double) * (size_t)g->np, cudaMemcpyHostToDevice, G.stream));
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    return LSF_OK;
+}
+
+int lsf_grid_download(lsf_grid *g, double *phi_host)
+{
+    if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
+    LSF_CUDA(cudaMemcpyAsync(phi_host, g->phi, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToHost, G.stream));
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    return LSF_OK;
+}
+
+int lsf_grid_download_phiN(lsf_grid *g, double *phiN_host)
+{
+    if (!g || !phiN_host) return set_error(LSF_ERR_ARG, "null argument");
+    LSF_CUDA(cudaMemcpyAsync(phiN_host, g->phiN, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToHost, G.stream));
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    return LSF_OK;
+}
+
+void *lsf_grid_device_ptr(lsf_grid *g) { return g ? (void *)g->phi : nullptr; }
+
+int lsf_grid_sign_init(lsf_grid *g, const double xLo[3], double dx, const double *surfX, int nSurfNode,
+                       const int32_t *surfElem, int nSurfElem, int im, int ip, int jm, int jp, int km, int kp)
+{
+    if (!g || !xLo || !surfX || !surfElem) return set_error(LSF_ERR_ARG, "null argument");
+    return sign_core(g, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
+}
+
+int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist)
+{
+    if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    return reinit_core(g, iter, dx, h, tol, nullptr, nullptr, n_exit, rms_hist);
+}
+
+static int narrowband_to_host(Grid *g, const double *d_phi, double dx, int32_t *nb_host, int32_t *sb_host)
+{
+    int32_t *d_nb = nullptr, *d_sb = nullptr;
+    const size_t bytes = sizeof(int32_t) * (size_t)g->np;
+    LSF_CUDA(cudaMalloc(&d_nb, bytes));
+    cudaError_t e = cudaMalloc(&d_sb, bytes);
+    if (e != cudaSuccess) { cudaFree(d_nb); return set_error(LSF_ERR_CUDA, "narrowband: %s", cudaGetErrorString(e)); }
+    launch_narrowband(g, d_phi, dx, d_nb, d_sb);
+    if (nb_host) cudaMemcpyAsync(nb_host, d_nb, bytes, cudaMemcpyDeviceToHost, G.stream);
+    if (sb_host) cudaMemcpyAsync(sb_host, d_sb, bytes, cudaMemcpyDeviceToHost, G.stream);
+    e = cudaStreamSynchronize(G.stream);
+    cudaFree(d_nb); cudaFree(d_sb);
+    if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "narrowband: %s", cudaGetErrorString(e));
+    return LSF_OK;
+}
+
+int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *phiSB_host)
+{
+    if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    return narrowband_to_host(g, g->phi, dx, phiNB_host, phiSB_host);
+}
+
+int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol, int *n_exit, double *rms_hist)
+{
+    if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToDevice, G.stream)); // set3d.f90:377
+    return minmax_core(g, iter, dx, h1, tol, false, n_exit, rms_hist, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer drop-in entry points
+// ---------------------------------------------------------------------------------------------
+int lsf_sign_init(double *phi, int nx, int ny, int nz, const double xLo[3], double dx, const double *surfX,
+                  int nSurfNode, const int32_t *surfElem, int nSurfElem, int im, int ip, int jm, int jp, int km, int kp)
+{
+    if (!phi || !xLo || !surfX || !surfElem) return set_error(LSF_ERR_ARG, "null argument");
+    lsf_grid *g = nullptr;
+    int rc = lsf_grid_create(&g, nx, ny, nz);
+    if (rc) return rc;
+    rc = lsf_grid_upload(g, phi);
+    if (!rc) rc = sign_core(g, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
+    if (!rc) rc = lsf_grid_download(g, phi);
+    lsf_grid_destroy(g);
+    return rc;
+}
+
+int lsf_reinit(double *phi, double *gradPhi, double *gradPhiMag, int nx, int ny, int nz, int iter, double dx, double h,
+               int *n_exit, double *rms_hist)
+{
+    if (!phi) return set_error(LSF_ERR_ARG, "null phi");
+    lsf_grid *g = nullptr;
+    int rc = lsf_grid_create(&g, nx, ny, nz);
+    if (rc) return rc;
+    double *d_g = nullptr, *d_gm = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)g->np;
+    cudaError_t e = cudaSuccess;
+    if (gradPhi && (e = cudaMalloc(&d_g, 3 * bytes)) == cudaSuccess) e = cudaMemcpy(d_g, gradPhi, 3 * bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && gradPhiMag && (e = cudaMalloc(&d_gm, bytes)) == cudaSuccess) e = cudaMemcpy(d_gm, gradPhiMag, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = set_error(LSF_ERR_CUDA, "reinit: %s", cudaGetErrorString(e));
+    if (!rc) rc = lsf_grid_upload(g, phi);
+    int st = LSF_OK;
+    if (!rc) {
+        st = reinit_core(g, iter, dx, h, 1.E-5, d_g, d_gm, n_exit, rms_hist);   // tol: subs.f90:915
+        if (st < 0) rc = st;
+    }
+    if (!rc) rc = lsf_grid_download(g, phi);
+    if (!rc && d_g && cudaMemcpy(gradPhi, d_g, 3 * bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error(LSF_ERR_CUDA, "reinit: D2H gradPhi");
+    if (!rc && d_gm && cudaMemcpy(gradPhiMag, d_gm, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error(LSF_ERR_CUDA, "reinit: D2H gradPhiMag");
+    cudaFree(d_g); cudaFree(d_gm);
+    lsf_grid_destroy(g);
+    return rc ? rc : st;
+}
+
+int lsf_narrowband(int nx, int ny, int nz, double dx, const double *phi, int32_t *phiNB, int32_t *phiSB)
+{
+    if (!phi || !phiNB || !phiSB) return set_error(LSF_ERR_ARG, "null argument");
+    lsf_grid *g = nullptr;
+    int rc = lsf_grid_create(&g, nx, ny, nz);
+    if (rc) return rc;
+    rc = lsf_grid_upload(g, phi);
+    if (!rc) rc = narrowband_to_host(g, g->phi, dx, phiNB, phiSB);
+    lsf_grid_destroy(g);
+    return rc;
+}
+
+int lsf_minmax(double *phi, double *phiN, int32_t *phiNB, int32_t *phiSB, int nx, int ny, int nz, int iter, double dx,
+               double h1, double tol, int *n_exit, double *rms_hist)
+{
+    if (!phi || !phiN || !phiNB || !phiSB) return set_error(LSF_ERR_ARG, "null argument");
+    lsf_grid *g = nullptr;
+    int rc = lsf_grid_create(&g, nx, ny, nz);
+    if (rc) return rc;
+    int st = LSF_OK, conv = 0, ne = 0;
+    const size_t bytes = sizeof(double) * (size_t)g->np;
+    int32_t *d_nb = nullptr;
+    do {
+        if ((rc = lsf_grid_upload(g, phi))) break;
+        if (cudaMemcpy(g->phiN, phiN, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { rc = set_error(LSF_ERR_CUDA, "minmax: H2D phiN"); break; }
+        if ((rc = ensure_minmax_buffers(g))) break;
+        if (cudaMalloc(&d_nb, sizeof(int32_t) * (size_t)g->np) != cudaSuccess ||
+            cudaMemcpy(d_nb, phiNB, sizeof(int32_t) * (size_t)g->np, cudaMemcpyHostToDevice) != cudaSuccess) {
+            rc = set_error(LSF_ERR_CUDA, "minmax: H2D phiNB"); break;
+        }
+        launch_mask_from_i32(g, d_nb);
+        cudaStreamSynchronize(G.stream);
+        cudaFree(d_nb); d_nb = nullptr;
+        st = minmax_core(g, iter, dx, h1, tol, true, &ne, rms_hist, &conv);
+        if (st < 0) { rc = st; break; }
+        if (n_exit) *n_exit = ne;
+        if ((rc = lsf_grid_download(g, phi))) break;
+        if ((rc = lsf_grid_download_phiN(g, phiN))) break;
+        // masks: the last narrowBand call (set3d.f90:460) saw phi of the last non-exiting iteration,
+        // i.e. phiN when the loop EXITed on tolerance, phi otherwise; none if no iteration ran it.
+        if (iter >= 1 && !(conv && ne == 1) && st != LSF_NAN)
+            rc = narrowband_to_host(g, conv ? g->phiN : g->phi, dx, phiNB, phiSB);
+    } while (0);
+    cudaFree(d_nb);
+    lsf_grid_destroy(g);
+    return rc ? rc : st;
+}
+
+}  // extern "C"

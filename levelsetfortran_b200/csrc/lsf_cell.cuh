@@ -1,0 +1,250 @@
+// lsf_cell.cuh -- per-cell arithmetic of the WENO5 Hamilton-Jacobi reinitialisation update.
+//
+// Two arithmetic policies compute the same update (reference: weno subs.f90:489-711, phiSign
+// subs.f90:152-172, Euler update subs.f90:747-750):
+//   ExactArith : the reference's operation order with round-to-nearest mul/add/div/sqrt and no
+//                FMA contraction -> bit-identical to `gfortran -O3 -fdefault-real-8` semantics.
+//   FastArith  : algebraically equivalent form built for the FP64 pipe: first/second differences
+//                are kept unscaled (1/dx factored out), the six 1/(eps+IS)^2 divisions and four
+//                weight divisions per direction collapse into ONE reciprocal per side
+//                (w0 = q1 q2 / D, w2 = 3 q0 q1 / D, D = q1 q2 + 6 q0 q2 + 3 q0 q1, q = (eps+IS)^2),
+//                reciprocals are MUFU seed + 2 Newton steps, and FMAs are allowed.  The 1.E-99
+//                epsilon floor (subs.f90:533) becomes 1.E-60 (in dx^2-scaled units) so the products
+//                of squares cannot underflow in exactly flat regions; where that floor matters the
+//                WENO correction it weights is < 1e-30.  Deviation from the reference <= 1e-10
+//                (measured ~1e-14 after 2155 sweeps, tests/test_gpu_parity.py).
+//
+// The header is also compiled by g++ (tests/emu) so the schedule logic can be checked on a CPU.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define LSF_HD __host__ __device__ __forceinline__
+#else
+#define LSF_HD inline
+#endif
+
+namespace lsf {
+
+// gfortran MAX/MIN on reals: a NaN first operand is replaced by the second.
+LSF_HD double fmax_f(double a, double b) { return (b > a || a != a) ? b : a; }
+LSF_HD double fmin_f(double a, double b) { return (b < a || a != a) ? b : a; }
+
+struct CellConst {
+    double dx;       // grid spacing
+    double inv_dx;   // 1/dx
+    double k12;      // 1/(12 dx)
+    double dx2;      // dx*dx            (phiSign: dxx*dxx, subs.f90:169)
+    double h;        // pseudo-time step (subs.f90:750)
+};
+
+// ------------------------------------------------------------------------------------------
+struct ExactArith {
+#if defined(__CUDA_ARCH__)
+    static LSF_HD double mul(double a, double b) { return __dmul_rn(a, b); }
+    static LSF_HD double add(double a, double b) { return __dadd_rn(a, b); }
+    static LSF_HD double sub(double a, double b) { return __dsub_rn(a, b); }
+    static LSF_HD double div(double a, double b) { return __ddiv_rn(a, b); }
+    static LSF_HD double sqr(double a) { return __dsqrt_rn(a); }
+#else
+    static LSF_HD double mul(double a, double b) { return a * b; }   // host: build with -ffp-contract=off
+    static LSF_HD double add(double a, double b) { return a + b; }
+    static LSF_HD double sub(double a, double b) { return a - b; }
+    static LSF_HD double div(double a, double b) { return a / b; }
+    static LSF_HD double sqr(double a) { return sqrt(a); }
+#endif
+
+    // one direction of the high-order branch; v[0..6] = phi at physical offsets -3..+3.
+    // YQ reproduces subs.f90:576 (y direction: p5 = (phi(j+3)-phi(j+3))/dx).
+    template <bool YQ>
+    static LSF_HD void weno_dir(const double v[7], const CellConst &cc, double &dminus, double &dplus)
+    {
+        const double dx = cc.dx;
+        const double m3 = v[0], m2 = v[1], m1 = v[2], c0 = v[3], p1v = v[4], p2v = v[5], p3v = v[6];
+        const double ap = div(add(sub(p3v, mul(2., p2v)), p1v), dx);
+        const double am = div(add(sub(m3, mul(2., m2)), m1), dx);
+        const double bp = div(add(sub(p2v, mul(2., p1v)), c0), dx);
+        const double bm = div(add(sub(m2, mul(2., m1)), c0), dx);
+        const double cp = div(add(sub(p1v, mul(2., c0)), m1), dx);
+        const double cm = cp, dp = bm, dm = bp;
+#define LSF_IS(x, y) add(mul(mul(13., (x)), (x)), mul(mul(3., (y)), (y)))
+        const double IS0p = LSF_IS(sub(ap, bp), sub(ap, mul(3., bp)));
+        const double IS0m = LSF_IS(sub(am, bm), sub(am, mul(3., bm)));
+        const double IS1p = LSF_IS(sub(bp, cp), add(bp, cp));
+        const double IS1m = LSF_IS(sub(bm, cm), add(bm, cm));
+        const double IS2p = LSF_IS(sub(cp, dp), sub(mul(3., cp), dp));
+        const double IS2m = LSF_IS(sub(cm, dm), sub(mul(3., cm), dm));
+#undef LSF_IS
+        const double p0 = div(sub(m2, m3), dx);
+        const double p1 = div(sub(m1, m2), dx);
+        const double p2 = div(sub(c0, m1), dx);
+        const double p3 = div(sub(p1v, c0), dx);
+        const double p4 = div(sub(p2v, p1v), dx);
+        const double p5 = YQ ? div(sub(p3v, p3v), dx) : div(sub(p3v, p2v), dx);
+        const double q0 = mul(p0, p0), q1 = mul(p1, p1), q2 = mul(p2, p2), q3 = mul(p3, p3),
+                     q4 = mul(p4, p4), q5 = mul(p5, p5);
+        const double epsp = add(mul(1.E-6, fmax_f(q1, fmax_f(q2, fmax_f(q3, fmax_f(q4, q5))))), 1.E-99);
+        const double epsm = add(mul(1.E-6, fmax_f(q0, fmax_f(q1, fmax_f(q2, fmax_f(q3, q4))))), 1.E-99);
+#define LSF_AL(c, eps, IS) div((c), mul(add((eps), (IS)), add((eps), (IS))))
+        const double a0p = LSF_AL(1., epsp, IS0p), a0m = LSF_AL(1., epsm, IS0m);
+        const double a1p = LSF_AL(6., epsp, IS1p), a1m = LSF_AL(6., epsm, IS1m);
+        const double a2p = LSF_AL(3., epsp, IS2p), a2m = LSF_AL(3., epsm, IS2m);
+#undef LSF_AL
+        const double sp = add(add(a0p, a1p), a2p), sm = add(add(a0m, a1m), a2m);
+        const double w0p = div(a0p, sp), w0m = div(a0m, sm);
+        const double w2p = div(a2p, sp), w2m = div(a2m, sm);
+        const double third = 1. / 3., sixth = 1. / 6., twelfth = 1. / 12.;
+        const double PWp = add(mul(mul(third, w0p), add(sub(ap, mul(2., bp)), cp)),
+                               mul(mul(sixth, sub(w2p, 0.5)), add(sub(bp, mul(2., cp)), dp)));
+        const double PWm = add(mul(mul(third, w0m), add(sub(am, mul(2., bm)), cm)),
+                               mul(mul(sixth, sub(w2m, 0.5)), add(sub(bm, mul(2., cm)), dm)));
+        const double cen = mul(twelfth, sub(add(add(-p1, mul(7., p2)), mul(7., p3)), p4));
+        dminus = sub(cen, PWm);
+        dplus = add(cen, PWp);
+    }
+
+    // low-order one-sided differences, subs.f90:657-662
+    static LSF_HD void lo_dir(double vm, double vc, double vp, const CellConst &cc, double &dminus, double &dplus)
+    {
+        dminus = div(sub(vc, vm), cc.dx);
+        dplus = div(sub(vp, vc), cc.dx);
+    }
+
+    // Godunov selection + |grad phi|, subs.f90:667-702.  g[3] receives gradX,gradY,gradZ.
+    static LSF_HD double godunov(double phic, double a, double b, double c, double d, double e, double f, double g[3])
+    {
+        const double pa = fmax_f(a, 0.), pb = fmax_f(b, 0.), pc = fmax_f(c, 0.);
+        const double pd = fmax_f(d, 0.), pe = fmax_f(e, 0.), pf = fmax_f(f, 0.);
+        const double na = fmin_f(a, 0.), nb = fmin_f(b, 0.), nc = fmin_f(c, 0.);
+        const double nd = fmin_f(d, 0.), ne = fmin_f(e, 0.), nf = fmin_f(f, 0.);
+        if (phic > 0.) {
+            g[0] = fmax_f(mul(pa, pa), mul(nb, nb));
+            g[1] = fmax_f(mul(pc, pc), mul(nd, nd));
+            g[2] = fmax_f(mul(pe, pe), mul(nf, nf));
+        } else {
+            g[0] = fmax_f(mul(pb, pb), mul(na, na));
+            g[1] = fmax_f(mul(pd, pd), mul(nc, nc));
+            g[2] = fmax_f(mul(pf, pf), mul(ne, ne));
+        }
+        return sqr(add(add(g[0], g[1]), g[2]));
+    }
+
+    // phiSign (subs.f90:169) + Euler update (subs.f90:749-750)
+    static LSF_HD double update(double phic, double phiS, double gM, const CellConst &cc)
+    {
+        const double sgn = div(phiS, sqr(add(mul(phiS, phiS), mul(mul(cc.dx, cc.dx), gM))));
+        const double k1 = mul(sgn, sub(1., gM));
+        return add(phic, mul(cc.h, k1));
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+struct FastArith {
+    static LSF_HD double rcp(double x)
+    {
+#if defined(__CUDA_ARCH__)
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+        double e = fma(-x, r, 1.0);
+        r = fma(r, e, r);
+        e = fma(-x, r, 1.0);
+        r = fma(r, e, r);
+        return r;
+#else
+        return 1.0 / x;
+#endif
+    }
+
+    // Jiang-Shu weights from E_k = eps + IS_k:  out 2*w0 and (w2 - 1/2)
+    static LSF_HD void weights(double E0, double E1, double E2, double &w0x2, double &w2mh)
+    {
+        const double q0 = E0 * E0, q1 = E1 * E1, q2 = E2 * E2;
+        const double n0 = q1 * q2, x = q0 * q2, y = q0 * q1;
+        const double D = fma(6.0, x, fma(3.0, y, n0));
+        const double r = rcp(D);
+        w0x2 = (n0 + n0) * r;
+        w2mh = fma(3.0 * y, r, -0.5);
+    }
+
+    template <bool YQ>
+    static LSF_HD void weno_dir(const double v[7], const CellConst &cc, double &dminus, double &dplus)
+    {
+        const double e0 = v[1] - v[0], e1 = v[2] - v[1], e2 = v[3] - v[2];
+        const double e3 = v[4] - v[3], e4 = v[5] - v[4], e5 = v[6] - v[5];
+        const double am = e1 - e0, bm = e2 - e1, c = e3 - e2, bp = e4 - e3, ap = e5 - e4;
+        const double tpa = ap - bp, tpb = bp - c, tmc = c - bm, tma = am - bm;
+        const double s13b = 13.0 * tpb * tpb, s13c = 13.0 * tmc * tmc;
+        double t;
+        t = fma(-3.0, bp, ap); const double IS0p = fma(13.0 * tpa, tpa, 3.0 * t * t);
+        t = bp + c;            const double IS1p = fma(3.0 * t, t, s13b);
+        t = fma(3.0, c, -bm);  const double IS2p = fma(3.0 * t, t, s13c);
+        t = fma(-3.0, bm, am); const double IS0m = fma(13.0 * tma, tma, 3.0 * t * t);
+        t = bm + c;            const double IS1m = fma(3.0 * t, t, s13c);
+        t = fma(3.0, c, -bp);  const double IS2m = fma(3.0 * t, t, s13b);
+        const double mc = fmax(fmax(fabs(e1), fabs(e2)), fmax(fabs(e3), fabs(e4)));
+        const double mp = YQ ? mc : fmax(mc, fabs(e5));
+        const double mm = fmax(mc, fabs(e0));
+        const double tiny = 1.0e-60;
+        const double epsp = fma(1.0e-6 * mp, mp, tiny);
+        const double epsm = fma(1.0e-6 * mm, mm, tiny);
+        double w0p2, w2ph, w0m2, w2mh;
+        weights(epsp + IS0p, epsp + IS1p, epsp + IS2p, w0p2, w2ph);
+        weights(epsm + IS0m, epsm + IS1m, epsm + IS2m, w0m2, w2mh);
+        const double s = tpb - tmc;
+        const double Yp = fma(w0p2, tpa - tpb, w2ph * s);
+        const double Ym = fma(w0m2, tma + tmc, w2mh * s);
+        const double cen = fma(7.0, e2 + e3, -(e1 + e4));
+        dminus = cc.k12 * fma(-2.0, Ym, cen);
+        dplus = cc.k12 * fma(2.0, Yp, cen);
+    }
+
+    static LSF_HD void lo_dir(double vm, double vc, double vp, const CellConst &cc, double &dminus, double &dplus)
+    {
+        dminus = (vc - vm) * cc.inv_dx;
+        dplus = (vp - vc) * cc.inv_dx;
+    }
+
+    static LSF_HD double godunov(double phic, double a, double b, double c, double d, double e, double f, double g[3])
+    {
+        // upwind pair per axis: phi>0 -> (max(a,0), min(b,0)) else (max(b,0), min(a,0))
+        const bool pos = phic > 0.;
+        const double ax = pos ? a : b, bx = pos ? b : a;
+        const double ay = pos ? c : d, by = pos ? d : c;
+        const double az = pos ? e : f, bz = pos ? f : e;
+        const double x1 = fmax(ax, 0.), x2 = fmin(bx, 0.);
+        const double y1 = fmax(ay, 0.), y2 = fmin(by, 0.);
+        const double z1 = fmax(az, 0.), z2 = fmin(bz, 0.);
+        g[0] = fmax(x1 * x1, x2 * x2);
+        g[1] = fmax(y1 * y1, y2 * y2);
+        g[2] = fmax(z1 * z1, z2 * z2);
+        return sqrt(g[0] + g[1] + g[2]);
+    }
+
+    static LSF_HD double update(double phic, double phiS, double gM, const CellConst &cc)
+    {
+        const double sgn = phiS / sqrt(fma(phiS, phiS, cc.dx2 * gM));
+        return fma(cc.h, sgn * (1.0 - gM), phic);
+    }
+};
+
+// Full cell update from the three 7-point lines (physical orientation, index 3 = centre).
+// hi = high-order branch condition of subs.f90:506.  Returns the new phi; g[3]/gM as in weno.
+template <class AR>
+LSF_HD double reinit_cell(const double vx[7], const double vy[7], const double vz[7], double phiS, bool hi,
+                          const CellConst &cc, double g[3], double &gM)
+{
+    double a, b, c, d, e, f;
+    if (hi) {
+        AR::template weno_dir<false>(vx, cc, a, b);
+        AR::template weno_dir<true>(vy, cc, c, d);
+        AR::template weno_dir<false>(vz, cc, e, f);
+    } else {
+        AR::lo_dir(vx[2], vx[3], vx[4], cc, a, b);
+        AR::lo_dir(vy[2], vy[3], vy[4], cc, c, d);
+        AR::lo_dir(vz[2], vz[3], vz[4], cc, e, f);
+    }
+    gM = AR::godunov(vx[3], a, b, c, d, e, f, g);
+    return AR::update(vx[3], phiS, gM, cc);
+}
+
+}  // namespace lsf

@@ -1,0 +1,75 @@
+// lsf_internal.cuh -- internal state shared by the translation units of liblsf_b200.so.
+#pragma once
+#include "../../include/lsf_b200.h"
+#include "lsf_common.cuh"
+
+struct lsf_grid {
+    lsf::Dims dm;
+    long long np;             // (nx+1)(ny+1)(nz+1)
+    double *phi;              // the level set, reference layout
+    double *phiS;             // frozen sign source of reinit (subs.f90:731)
+    double *phiN;             // previous iterate for the RMS test (subs.f90:732,921; set3d.f90:377,454)
+    double *lap;              // min/max: Laplacian of the iteration's old phi on band cells
+    uint8_t *mask;            // min/max: band mask of the current iteration
+    double *partial;          // per-block partial sums of the RMS reduction
+    double *hist;             // device copy of the per-iteration RMS history
+    int hist_cap;
+    lsf::Ctrl *ctrl;          // device control block
+    // march schedule state (lsf_march.cu)
+    unsigned int *march_ticket;   // tile ticket counter
+    long long *march_progress;    // per column-tile progress, epoch-encoded
+    int march_tiles_cap;
+    long long march_epoch;
+};
+
+namespace lsf {
+
+typedef lsf_grid Grid;
+
+constexpr int RMS_BLOCKS = 1184;   // 8 x 148 SMs
+
+struct Global {
+    bool inited = false;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int arith = LSF_ARITH_FAST;
+    int sched = LSF_SCHED_MARCH;
+    int n_launch = 0;
+    double last_ms = 0.;
+    bool profile = false;
+    double sweep_ms = 0.;
+    int n_sweeps = 0;
+    char err[512] = {0};
+};
+extern Global G;
+
+int set_error(int code, const char *fmt, ...);
+#define LSF_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return lsf::set_error(LSF_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,        \
+                                  cudaGetErrorString(e__));                                         \
+    } while (0)
+
+// lsf_kernels.cu
+void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double *gradPhi, double *gradPhiMag);
+void launch_reinit_bc(Grid *g, double dx);
+void launch_rms(Grid *g, bool copy);
+void launch_finalize(Grid *g, int npart, int hist_off, double tol);
+void launch_copy_if_running(Grid *g, double *dst, const double *src);
+void launch_narrowband(Grid *g, const double *phi, double dx, int32_t *nb, int32_t *sb);
+void launch_minmax_iteration_plane(Grid *g, double dx, double h1, bool mask_given);
+void launch_mask_from_i32(Grid *g, const int32_t *nb);
+void launch_fill(Grid *g, double *p, double v);
+void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode,
+                      const int32_t *d_surfElem, int nElem, double *d_cen,
+                      int im, int ip, int jm, int jp, int km, int kp);
+
+// lsf_march.cu
+int march_prepare(Grid *g);
+void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc);
+
+}  // namespace lsf

@@ -1,0 +1,176 @@
+"""Host-side mirror of the reference's `MODULE set_subs` interface for the grid hot path.
+
+Same names, argument order and in-place (INTENT(INOUT)) behaviour as the Fortran procedures the
+CUDA library replaces, so calls read like set3d.f90's:
+
+    reinit(phi, gradPhi, gradPhiMag, nx, ny, nz, iter, dx, h)         # subs.f90:717
+    narrowBand(nx, ny, nz, dx, phi, phiNB, phiSB)                     # subs.f90:178
+    signSearch(phi, nx, ny, nz, xLo, dx, surfX, surfElem, box)        # inline loop set3d.f90:196-268
+    minMaxFlow(phi, phiN, phiNB, phiSB, nx, ny, nz, iter, dx, h1)     # inline loop set3d.f90:394-462
+
+Arrays are numpy, Fortran-ordered, shape (nx+1, ny+1, nz+1) == phi(0:nx,0:ny,0:nz); REAL -> float64,
+INTEGER -> int32.  Everything runs on the GPU through the C ABI (include/lsf_b200.h); a NaN RMS is
+reported the way the reference reports it -- by stopping: `ReferenceStop` is raised after the
+arrays have been updated (subs.f90:926, set3d.f90:458).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_double_p, c_i32_p, check, lib
+
+
+class ReferenceStop(RuntimeError):
+    """The reference would execute STOP here (NaN RMS)."""
+
+    def __init__(self, where, n, rms_hist):
+        super().__init__(f"{where}: RMS error is NaN at iteration {n} (reference STOPs)")
+        self.n = n
+        self.rms_hist = rms_hist
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_i32_p)
+
+
+def _grid_array(a, nx, ny, nz, dtype, name, extra=()):
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.f_contiguous \
+            or a.shape != (nx + 1, ny + 1, nz + 1) + tuple(extra):
+        raise ValueError(f"{name} must be a Fortran-ordered {np.dtype(dtype).name} array of shape "
+                         f"{(nx + 1, ny + 1, nz + 1) + tuple(extra)}")
+    return a
+
+
+def set_arith(exact: bool):
+    check(lib().lsf_set_arith(_lib.ARITH_EXACT if exact else _lib.ARITH_FAST))
+
+
+def set_sched(plane: bool):
+    check(lib().lsf_set_sched(_lib.SCHED_PLANE if plane else _lib.SCHED_MARCH))
+
+
+def reinit(phi, gradPhi, gradPhiMag, nx, ny, nz, iter, dx, h, stop_on_nan=True):
+    """SUBROUTINE reinit (subs.f90:717-931).  Returns (n_exit, rms_hist) -- the iteration index at
+    which the loop left and the RMS errors the reference prints at subs.f90:923."""
+    _grid_array(phi, nx, ny, nz, np.float64, "phi")
+    if gradPhi is not None:
+        _grid_array(gradPhi, nx, ny, nz, np.float64, "gradPhi", (3,))
+    if gradPhiMag is not None:
+        _grid_array(gradPhiMag, nx, ny, nz, np.float64, "gradPhiMag")
+    hist = np.zeros(iter + 1)
+    n_exit = C.c_int(-1)
+    rc = check(lib().lsf_reinit(_dp(phi), _dp(gradPhi), _dp(gradPhiMag), nx, ny, nz, int(iter), float(dx), float(h),
+                                C.byref(n_exit), _dp(hist)))
+    hist = hist[: n_exit.value + 1]
+    if rc == _lib.LSF_NAN and stop_on_nan:
+        raise ReferenceStop("reinit", n_exit.value, hist)
+    return n_exit.value, hist
+
+
+def narrowBand(nx, ny, nz, dx, phi, phiNB, phiSB):
+    """SUBROUTINE narrowBand (subs.f90:178-207)."""
+    _grid_array(phi, nx, ny, nz, np.float64, "phi")
+    _grid_array(phiNB, nx, ny, nz, np.int32, "phiNB")
+    _grid_array(phiSB, nx, ny, nz, np.int32, "phiSB")
+    check(lib().lsf_narrowband(nx, ny, nz, float(dx), _dp(phi), _ip(phiNB), _ip(phiSB)))
+
+
+def signSearch(phi, nx, ny, nz, xLo, dx, surfX, surfElem, box):
+    """The inside/outside search loop of set3d.f90:196-268.  box = (im, ip, jm, jp, km, kp)."""
+    _grid_array(phi, nx, ny, nz, np.float64, "phi")
+    surfX = np.asfortranarray(surfX, dtype=np.float64)
+    surfElem = np.asfortranarray(surfElem, dtype=np.int32)
+    xLo = np.ascontiguousarray(xLo, dtype=np.float64)
+    check(lib().lsf_sign_init(_dp(phi), nx, ny, nz, _dp(xLo), float(dx), _dp(surfX), surfX.shape[0],
+                              _ip(surfElem), surfElem.shape[0], *[int(v) for v in box]))
+
+
+def minMaxFlow(phi, phiN, phiNB, phiSB, nx, ny, nz, iter, dx, h1, tol=1.0e-7, stop_on_nan=True):
+    """The min/max time loop of set3d.f90:394-462.  Returns (n_exit, rms_hist)."""
+    _grid_array(phi, nx, ny, nz, np.float64, "phi")
+    _grid_array(phiN, nx, ny, nz, np.float64, "phiN")
+    _grid_array(phiNB, nx, ny, nz, np.int32, "phiNB")
+    _grid_array(phiSB, nx, ny, nz, np.int32, "phiSB")
+    hist = np.zeros(max(int(iter), 1))
+    n_exit = C.c_int(-1)
+    rc = check(lib().lsf_minmax(_dp(phi), _dp(phiN), _ip(phiNB), _ip(phiSB), nx, ny, nz, int(iter), float(dx),
+                                float(h1), float(tol), C.byref(n_exit), _dp(hist)))
+    hist = hist[: n_exit.value]
+    if rc == _lib.LSF_NAN and stop_on_nan:
+        raise ReferenceStop("minMaxFlow", n_exit.value, hist)
+    return n_exit.value, hist
+
+
+class DeviceGrid:
+    """A device-resident phi(0:nx,0:ny,0:nz): sign search -> reinit -> min/max without host round trips."""
+
+    def __init__(self, nx, ny, nz):
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self._h = C.c_void_p()
+        check(lib().lsf_grid_create(C.byref(self._h), self.nx, self.ny, self.nz))
+
+    @property
+    def shape(self):
+        return (self.nx + 1, self.ny + 1, self.nz + 1)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().lsf_grid_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def fill(self, value):
+        check(lib().lsf_grid_fill(self._h, float(value)))
+
+    def upload(self, phi):
+        _grid_array(phi, self.nx, self.ny, self.nz, np.float64, "phi")
+        check(lib().lsf_grid_upload(self._h, phi.ctypes.data))
+
+    def upload_ptr(self, host_ptr: int):
+        check(lib().lsf_grid_upload(self._h, host_ptr))
+
+    def download_ptr(self, host_ptr: int):
+        check(lib().lsf_grid_download(self._h, host_ptr))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, order="F")
+        _grid_array(out, self.nx, self.ny, self.nz, np.float64, "out")
+        check(lib().lsf_grid_download(self._h, out.ctypes.data))
+        return out
+
+    def device_ptr(self) -> int:
+        return int(lib().lsf_grid_device_ptr(self._h))
+
+    def signSearch(self, xLo, dx, surfX, surfElem, box):
+        surfX = np.asfortranarray(surfX, dtype=np.float64)
+        surfElem = np.asfortranarray(surfElem, dtype=np.int32)
+        xLo = np.ascontiguousarray(xLo, dtype=np.float64)
+        check(lib().lsf_grid_sign_init(self._h, _dp(xLo), float(dx), _dp(surfX), surfX.shape[0], _ip(surfElem),
+                                       surfElem.shape[0], *[int(v) for v in box]))
+
+    def reinit(self, iter, dx, h, tol=1.0e-5):
+        hist = np.zeros(iter + 1)
+        n_exit = C.c_int(-1)
+        rc = check(lib().lsf_grid_reinit(self._h, int(iter), float(dx), float(h), float(tol), C.byref(n_exit), _dp(hist)))
+        return rc, n_exit.value, hist[: n_exit.value + 1]
+
+    def narrowBand(self, dx):
+        nb = np.empty(self.shape, dtype=np.int32, order="F")
+        sb = np.empty(self.shape, dtype=np.int32, order="F")
+        check(lib().lsf_grid_narrowband(self._h, float(dx), _ip(nb), _ip(sb)))
+        return nb, sb
+
+    def minMaxFlow(self, iter, dx, h1, tol=1.0e-7):
+        hist = np.zeros(max(int(iter), 1))
+        n_exit = C.c_int(-1)
+        rc = check(lib().lsf_grid_minmax(self._h, int(iter), float(dx), float(h1), float(tol), C.byref(n_exit), _dp(hist)))
+        return rc, n_exit.value, hist[: n_exit.value]

@@ -1,0 +1,18 @@
+// emu_prims.h -- CPU stand-ins for the handful of device primitives lsf_march.cuh uses, so the
+// very same tile/march code runs with one OS thread per CUDA thread (test infrastructure).
+#pragma once
+#include <pthread.h>
+#include <sched.h>
+#define LSF_DEV inline
+namespace lsf {
+struct EmuCta { pthread_barrier_t bar; };
+extern thread_local EmuCta *emu_cta;
+inline void p_sync() { pthread_barrier_wait(&emu_cta->bar); }
+inline double p_ldcg(const double *p) { return *(const volatile double *)p; }
+inline void p_stcg(double *p, double v) { *(volatile double *)p = v; }
+inline void p_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned p_ticket(unsigned *ctr) { return __atomic_fetch_add(ctr, 1u, __ATOMIC_SEQ_CST); }
+inline long long p_ld_acquire(const long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void p_st_release(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void p_sleep() { sched_yield(); }
+}  // namespace lsf

@@ -1,0 +1,224 @@
+"""GPU parity tests (run on a B200 with `pytest -m gpu`).  Everything goes through the C ABI
+(include/lsf_b200.h) via the set_subs mirror; the oracle / golden fixtures are only the checker.
+
+Bars (BASELINE.json north_star): inside/outside sign field bit-exact; phi after init, reinit and
+min/max flow within 1e-10 max-abs of the reference path in fp64; identical iteration counts.
+The EXACT arithmetic mode and the whole min/max path are additionally required to be bit-identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_mesh, synth_field
+
+pytestmark = pytest.mark.gpu
+DX = 0.05
+TOL = 1.0e-10      # north_star: phi within 1e-10 max-abs in fp64
+
+
+@pytest.fixture(scope="module")
+def S(lsf):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from levelsetfortran_b200 import set_subs
+    yield set_subs
+    set_subs.set_arith(False)
+    set_subs.set_sched(False)
+
+
+def _mode(S, exact, plane):
+    S.set_arith(exact)
+    S.set_sched(plane)
+
+
+# ------------------------------------------------------------------------------------ sign search
+@pytest.mark.parametrize("name", ["cube40", "twoCube10"])
+def test_sign_search_bit_exact_on_reference_inputs(S, name):
+    from levelsetfortran_b200 import stl
+    X, E = load_mesh(name)
+    g = stl.grid_from_surface(X, DX)
+    gold = np.load(f"{GOLDEN}/{name}_fields.npz")["sign"]
+    phi = np.ones(gold.shape, order="F")
+    S.signSearch(phi, g["nx"], g["ny"], g["nz"], g["xLo"], DX, X, E, g["box"])
+    assert np.array_equal(phi, gold)
+    assert np.array_equal(np.signbit(phi), np.signbit(gold))          # includes -0.0 vs +0.0
+
+
+def test_sign_search_bit_exact_synthetic(S, oracle):
+    from levelsetfortran_b200 import stl
+    X, E = stl.dedup_nodes(stl.torus_cube_config((48, 40, 56)))
+    g = stl.grid_from_surface(X, DX)
+    shape = (g["nx"] + 1, g["ny"] + 1, g["nz"] + 1)
+    a = np.ones(shape, order="F")
+    b = np.ones(shape, order="F")
+    oracle.sign_init(a, g["xLo"], DX, X, E, g["box"])
+    S.signSearch(b, g["nx"], g["ny"], g["nz"], g["xLo"], DX, X, E, g["box"])
+    assert np.array_equal(a, b) and (a < 0).any() and (a == 1.0).any()
+
+
+# ------------------------------------------------------------------------------------ reinit
+@pytest.mark.parametrize("plane", [False, True], ids=["march", "plane"])
+@pytest.mark.parametrize("shape", [(22, 21, 23), (40, 38, 36), (19, 50, 33), (35, 18, 70), (6, 5, 7), (3, 3, 3)])
+def test_reinit_sweeps_exact_mode_bitwise(S, oracle, shape, plane):
+    """All 8 rasters + BC + RMS on small/ragged grids: exact arithmetic is bit-identical."""
+    _mode(S, True, plane)
+    p0 = synth_field(shape, seed=7)
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    nx, ny, nz = (s - 1 for s in shape)
+    st, n, hist = oracle.reinit(a, 15, DX, 0.0014)                    # tol 1.E-5 as subs.f90:915
+    n2, hist2 = S.reinit(b, None, None, nx, ny, nz, 15, DX, 0.0014)
+    assert n2 == n
+    assert np.array_equal(a, b)
+    assert np.allclose(hist, hist2, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("plane", [False, True], ids=["march", "plane"])
+def test_reinit_fast_mode_within_tolerance(S, oracle, plane):
+    _mode(S, False, plane)
+    shape = (40, 38, 36)
+    p0 = synth_field(shape, seed=8)
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    st, n, hist = oracle.reinit(a, 31, DX, 0.0014)
+    n2, hist2 = S.reinit(b, None, None, 39, 37, 35, 31, DX, 0.0014)
+    assert n == n2 == 31
+    assert np.abs(a - b).max() < 1e-13
+
+
+def test_reinit_gradphi_outputs(S, oracle):
+    _mode(S, True, False)
+    shape = (20, 18, 19)
+    p0 = synth_field(shape, seed=9)
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    st, n, hist, g, gm = oracle.reinit(a, 9, DX, 0.0014, want_grad=True)
+    g2 = np.zeros(shape + (3,), order="F")
+    gm2 = np.zeros(shape, order="F")
+    S.reinit(b, g2, gm2, 19, 17, 18, 9, DX, 0.0014)
+    assert np.array_equal(a, b) and np.array_equal(g, g2) and np.array_equal(gm, gm2)
+
+
+@pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
+def test_cube40_reinit_full_parity(S, exact):
+    """BASELINE config 1, reinit #1: 2155 sweeps to the reference's own exit."""
+    _mode(S, exact, False)
+    from levelsetfortran_b200 import stl
+    X, E = load_mesh("cube40")
+    g = stl.grid_from_surface(X, DX)
+    gold = np.load(f"{GOLDEN}/cube40_fields.npz")
+    phi = np.asfortranarray(gold["sign"].copy())
+    n, hist = S.reinit(phi, None, None, 61, 61, 61, 10000, DX, 0.1 * g["dxx"])
+    assert n == 2154 == int(gold["n_exit"][0])                        # same iteration count
+    err = np.abs(phi - gold["reinit1"]).max()
+    assert err <= (0.0 if exact else TOL), err
+    assert np.allclose(hist, gold["rms_reinit1"], rtol=1e-9, atol=0)
+
+
+def test_twocube10_nan_stop_parity(S):
+    """BASELINE config 2: the reference STOPs with a NaN RMS at n = 272."""
+    _mode(S, False, False)
+    from levelsetfortran_b200 import ReferenceStop, stl
+    X, E = load_mesh("twoCube10")
+    g = stl.grid_from_surface(X, DX)
+    gold = np.load(f"{GOLDEN}/twoCube10_fields.npz")
+    phi = np.asfortranarray(gold["sign"].copy())
+    with pytest.raises(ReferenceStop) as e:
+        S.reinit(phi, None, None, 261, 41, 41, 10000, DX, 0.1 * g["dxx"])
+    assert e.value.n == 272 == int(gold["n_nan"][0])
+    assert np.allclose(e.value.rms_hist[:272], gold["rms_reinit1"][:272], rtol=1e-9, atol=0)
+    phi = np.asfortranarray(gold["sign"].copy())
+    n, hist = S.reinit(phi, None, None, 261, 41, 41, 271, DX, 0.1 * g["dxx"])
+    assert n == 271 and np.abs(phi - gold["phi_n271"]).max() <= TOL
+
+
+# ------------------------------------------------------------------------------------ narrow band + min/max
+def test_narrowband_exact(S, oracle):
+    gold = np.load(f"{GOLDEN}/cube40_fields.npz")
+    phi = np.asfortranarray(gold["reinit1"].copy())
+    nb = np.zeros(phi.shape, dtype=np.int32, order="F")
+    sb = np.zeros(phi.shape, dtype=np.int32, order="F")
+    S.narrowBand(61, 61, 61, DX, phi, nb, sb)
+    nbo, sbo = oracle.narrowband(phi, DX)
+    assert np.array_equal(nb, nbo) and np.array_equal(sb, sbo) and nb.sum() == 84530
+
+
+def test_cube40_minmax_full_parity_bit_exact(S):
+    from levelsetfortran_b200 import stl
+    X, E = load_mesh("cube40")
+    g = stl.grid_from_surface(X, DX)
+    gold = np.load(f"{GOLDEN}/cube40_fields.npz")
+    phi = np.asfortranarray(gold["reinit1"].copy())
+    phiN = phi.copy(order="F")
+    nb = np.zeros(phi.shape, dtype=np.int32, order="F")
+    sb = np.zeros(phi.shape, dtype=np.int32, order="F")
+    S.narrowBand(61, 61, 61, DX, phi, nb, sb)
+    n, hist = S.minMaxFlow(phi, phiN, nb, sb, 61, 61, 61, 10000, DX, 0.01 * g["dxx"])
+    assert n == 406 == int(gold["n_exit"][1])
+    assert np.array_equal(phi, gold["minmax"])
+    assert np.allclose(hist, gold["rms_minmax"], rtol=1e-9, atol=0)
+    assert np.array_equal(nb, gold["phiNB"].astype(np.int32)) and np.array_equal(sb, gold["phiSB"].astype(np.int32))
+
+
+def test_minmax_small_vs_oracle_iteration_limit(S, oracle):
+    shape = (30, 28, 26)
+    p0 = synth_field(shape, seed=11, noise=0.002)
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    st, n, hist, nbo, sbo = oracle.minmax(a, 12, DX, 1.0e-4, tol=1e-30)
+    assert st == 2 and n == 12
+    phiN = b.copy(order="F")
+    nb = np.zeros(shape, dtype=np.int32, order="F")
+    sb = np.zeros(shape, dtype=np.int32, order="F")
+    S.narrowBand(29, 27, 25, DX, b, nb, sb)
+    n2, hist2 = S.minMaxFlow(b, phiN, nb, sb, 29, 27, 25, 12, DX, 1.0e-4, tol=1e-30)
+    assert n2 == 12 and np.array_equal(a, b) and np.array_equal(phiN, b)
+    assert np.array_equal(nb, nbo) and np.array_equal(sb, sbo)
+    assert np.allclose(hist, hist2, rtol=1e-12, atol=0)
+
+
+# ------------------------------------------------------------------------------------ device-resident pipeline + larger sizes
+def test_device_pipeline_cube40_default_run(S):
+    """sign search -> reinit -> min/max on the device without host round trips == golden."""
+    _mode(S, False, False)
+    from levelsetfortran_b200 import DeviceGrid, stl
+    X, E = load_mesh("cube40")
+    g = stl.grid_from_surface(X, DX)
+    gold = np.load(f"{GOLDEN}/cube40_fields.npz")
+    G = DeviceGrid(g["nx"], g["ny"], g["nz"])
+    G.fill(1.0)
+    G.signSearch(g["xLo"], DX, X, E, g["box"])
+    assert np.array_equal(G.download(), gold["sign"])
+    rc, n, hist = G.reinit(10000, DX, 0.1 * g["dxx"])
+    assert (rc, n) == (0, 2154)
+    assert np.abs(G.download() - gold["reinit1"]).max() <= TOL
+    rc, n, hist = G.minMaxFlow(10000, DX, 0.01 * g["dxx"])
+    assert (rc, n) == (0, 406)
+    assert np.abs(G.download() - gold["minmax"]).max() <= TOL
+    rc, n, hist = G.reinit(2000, DX, 0.001 * g["dxx"])               # reinit #2, set3d.f90:576-582
+    assert (rc, n) == (0, 0)
+    G.close()
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 128), (96, 160, 200)])
+def test_march_equals_plane_schedule_at_size(S, shape):
+    """Size-independent property: both schedules are exact re-orderings, so in exact arithmetic
+    they agree bit for bit at sizes where the CPU oracle is too slow to run."""
+    p0 = synth_field(shape, seed=12)
+    nx, ny, nz = (s - 1 for s in shape)
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    _mode(S, True, True)
+    S.reinit(a, None, None, nx, ny, nz, 7, DX, 0.0014)
+    _mode(S, True, False)
+    S.reinit(b, None, None, nx, ny, nz, 7, DX, 0.0014)
+    assert np.array_equal(a, b)
+
+
+def test_one_sweep_vs_oracle_128(S, oracle):
+    """One full raster-1 sweep at 128^3 against the oracle (~0.4 s of CPU)."""
+    shape = (128, 128, 128)
+    p0 = synth_field(shape, seed=13)
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    oracle.reinit(a, 0, DX, 0.0014)
+    _mode(S, True, False)
+    S.reinit(b, None, None, 127, 127, 127, 0, DX, 0.0014)
+    assert np.array_equal(a, b)
+    c = p0.copy(order="F")
+    _mode(S, False, False)
+    S.reinit(c, None, None, 127, 127, 127, 0, DX, 0.0014)
+    assert np.abs(a - c).max() < 1e-14

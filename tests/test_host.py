@@ -1,0 +1,101 @@
+"""CPU tests of the host logic and of the C-ABI library (loads, exports every declared symbol,
+refuses to compute without a device).  No GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE, ROOT, load_mesh
+
+
+def test_header_and_binding_agree():
+    from levelsetfortran_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "lsf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lsf_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+def test_library_loads_and_exports_every_symbol(lsf):
+    from levelsetfortran_b200 import _lib
+    L = _lib.lib()
+    for name in _lib.SYMBOLS:
+        assert getattr(L, name) is not None
+
+
+def test_no_cpu_fallback(lsf):
+    """Without a CUDA device every compute entry point must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from levelsetfortran_b200 import _lib, set_subs
+    phi = np.ones((5, 5, 5), order="F")
+    with pytest.raises(_lib.LsfError) as e:
+        set_subs.reinit(phi, None, None, 4, 4, 4, 1, 0.05, 0.001)
+    assert e.value.code == _lib.LSF_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+    assert np.all(phi == 1.0)
+
+
+def test_argument_validation_mirrors_fortran_shapes(lsf):
+    from levelsetfortran_b200 import set_subs
+    with pytest.raises(ValueError):
+        set_subs.reinit(np.ones((5, 5, 5)), None, None, 4, 4, 4, 1, 0.05, 0.001)          # C order
+    with pytest.raises(ValueError):
+        set_subs.reinit(np.ones((5, 5, 4), order="F"), None, None, 4, 4, 4, 1, 0.05, 0.001)  # wrong extent
+    with pytest.raises(ValueError):
+        set_subs.narrowBand(4, 4, 4, 0.05, np.ones((5, 5, 5), order="F"), np.ones((5, 5, 5), order="F"),
+                            np.ones((5, 5, 5), dtype=np.int32, order="F"))                # REAL where INTEGER expected
+
+
+def test_stl_roundtrip_and_dedup_matches_oracle(tmp_path, oracle):
+    from levelsetfortran_b200 import stl
+    tris = np.concatenate([stl.sphere_tris(1.3, 9, 8), stl.box_tris([2, 0, 0], [3, 1, 1], 2)])
+    # a degenerate triangle that repeats a NEW vertex inside one triangle (stlRead's window quirk)
+    tris = np.concatenate([tris, np.array([[[9, 9, 9], [9, 9, 9], [8, 8, 8]]], dtype=np.float32)])
+    p = str(tmp_path / "s.stl")
+    stl.stl_write(p, tris)
+    assert np.array_equal(stl.stl_triangles(p), tris)
+    X, n, E, ne = stl.stlRead(p)
+    Xo, Eo = oracle.stl_read(p)
+    assert n == Xo.shape[0] and ne == len(tris)
+    assert np.array_equal(X, Xo) and np.array_equal(E, Eo)
+    assert E.min() == 1 and E.max() == n
+    # the in-triangle repeat is stored twice, exactly as subs.f90:75-93 does
+    assert E[-1, 0] != E[-1, 1]
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE), reason="reference tree not present on this machine")
+@pytest.mark.parametrize("name", ["cube40", "twoCube10"])
+def test_stlread_on_reference_inputs(name, oracle):
+    from levelsetfortran_b200 import stl
+    X, n, E, ne = stl.stlRead(f"{REFERENCE}/{name}.stl")
+    Xo, Eo = oracle.stl_read(f"{REFERENCE}/{name}.stl")
+    Xg, Eg = load_mesh(name)
+    assert np.array_equal(X, Xo) and np.array_equal(E, Eo)
+    assert np.array_equal(X, Xg) and np.array_equal(E, Eg)
+
+
+@pytest.mark.parametrize("name,expect", [("cube40", (61, 61, 61, (7, 53, 7, 53, 7, 53))),
+                                         ("twoCube10", (261, 41, 41, (7, 253, 7, 33, 7, 33)))])
+def test_grid_definition(name, expect, oracle):
+    from levelsetfortran_b200 import stl
+    X, E = load_mesh(name)
+    g, go = stl.grid_from_surface(X), oracle.grid_from_surface(X)
+    assert (g["nx"], g["ny"], g["nz"], g["box"]) == expect
+    assert (go["nx"], go["ny"], go["nz"], go["box"]) == expect
+    assert g["dxx"] == go["dxx"] and np.array_equal(g["xLo"], go["xLo"])
+    if name == "cube40":
+        assert g["dxx"] == 0.014433756729740645 and 0.1 * g["dxx"] == 0.0014433756729740647
+
+
+def test_synthetic_configs_hit_the_named_grid_sizes():
+    from levelsetfortran_b200 import stl
+    X, E = stl.dedup_nodes(stl.sphere_config(512))
+    g = stl.grid_from_surface(X)
+    assert (g["nx"] + 1, g["ny"] + 1, g["nz"] + 1) == (512, 512, 512) and len(E) == 20000
+    X, E = stl.dedup_nodes(stl.torus_cube_config((1024, 1024, 2048)))
+    g = stl.grid_from_surface(X)
+    assert (g["nx"] + 1, g["ny"] + 1, g["nz"] + 1) == (1024, 1024, 2048)
