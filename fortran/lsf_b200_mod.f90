@@ -1,0 +1,233 @@
+!*************************************************************************************!
+! lsf_b200_mod.f90 -- ISO_C_BINDING interface to liblsf_b200.so (include/lsf_b200.h)
+!
+! Drop-in replacements for the grid hot path of musheen/LevelSetFortran:
+!
+!   reference                                            this module
+!   ---------------------------------------------------  ------------------------------
+!   inline sign-search loop       set3d.f90:196-268      CALL signSearch_b200(...)
+!   CALL reinit(...)              subs.f90:717-931       CALL reinit_b200(...)      (same argument list)
+!   CALL narrowBand(...)          subs.f90:178-207       CALL narrowBand_b200(...)  (same argument list)
+!   inline min/max DO n loop      set3d.f90:394-462      CALL minMaxFlow_b200(...)
+!
+! Build (the reference is compiled with -fdefault-real-8, Makefile:4, so REAL == REAL(c_double)
+! and the default INTEGER == INTEGER(c_int); the module states the kinds explicitly so it is
+! correct with or without that flag as long as the caller's arrays are 8-byte reals):
+!
+!   gfortran -O3 -fdefault-real-8 -c fortran/lsf_b200_mod.f90 subs.f90 set3d.f90
+!   gfortran -o set3d.exec lsf_b200_mod.o subs.o set3d.o -L<repo>/levelsetfortran_b200 -llsf_b200 \
+!            -Wl,-rpath,<repo>/levelsetfortran_b200
+!
+! NOTE: no Fortran compiler exists in the image this library was developed in; this file is kept
+! small and conservative (F2003 only) and has been reviewed but not compiled there.  The same C
+! symbols are exercised by the ctypes mirror levelsetfortran_b200/set_subs.py in the test-suite.
+!*************************************************************************************!
+MODULE lsf_b200
+
+USE, INTRINSIC :: ISO_C_BINDING
+IMPLICIT NONE
+PRIVATE
+
+PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched
+PUBLIC :: signSearch_b200, reinit_b200, narrowBand_b200, minMaxFlow_b200
+PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT
+
+INTEGER(c_int), PARAMETER :: LSF_OK = 0, LSF_NAN = 1
+INTEGER(c_int), PARAMETER :: LSF_ARITH_FAST = 0, LSF_ARITH_EXACT = 1
+
+INTERFACE
+
+   FUNCTION lsf_init(device) BIND(C, NAME='lsf_init') RESULT(rc)
+      IMPORT :: c_int
+      INTEGER(c_int), VALUE :: device
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_init
+
+   FUNCTION lsf_finalize() BIND(C, NAME='lsf_finalize') RESULT(rc)
+      IMPORT :: c_int
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_finalize
+
+   FUNCTION lsf_set_arith(arith) BIND(C, NAME='lsf_set_arith') RESULT(rc)
+      IMPORT :: c_int
+      INTEGER(c_int), VALUE :: arith
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_set_arith
+
+   FUNCTION lsf_set_sched(sched) BIND(C, NAME='lsf_set_sched') RESULT(rc)
+      IMPORT :: c_int
+      INTEGER(c_int), VALUE :: sched
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_set_sched
+
+   FUNCTION lsf_last_error() BIND(C, NAME='lsf_last_error') RESULT(msg)
+      IMPORT :: c_ptr
+      TYPE(c_ptr) :: msg
+   END FUNCTION lsf_last_error
+
+   FUNCTION c_lsf_sign_init(phi,nx,ny,nz,xLo,dx,surfX,nSurfNode,surfElem,nSurfElem, &
+                            im,ip,jm,jp,km,kp) BIND(C, NAME='lsf_sign_init') RESULT(rc)
+      IMPORT :: c_int, c_double, c_int32_t
+      REAL(c_double) :: phi(*)
+      INTEGER(c_int), VALUE :: nx,ny,nz
+      REAL(c_double), INTENT(IN) :: xLo(3)
+      REAL(c_double), VALUE :: dx
+      REAL(c_double), INTENT(IN) :: surfX(*)
+      INTEGER(c_int), VALUE :: nSurfNode
+      INTEGER(c_int32_t), INTENT(IN) :: surfElem(*)
+      INTEGER(c_int), VALUE :: nSurfElem,im,ip,jm,jp,km,kp
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_sign_init
+
+   FUNCTION c_lsf_reinit(phi,gradPhi,gradPhiMag,nx,ny,nz,iter,dx,h,n_exit,rms_hist) &
+                         BIND(C, NAME='lsf_reinit') RESULT(rc)
+      IMPORT :: c_int, c_double
+      REAL(c_double) :: phi(*), gradPhi(*), gradPhiMag(*)
+      INTEGER(c_int), VALUE :: nx,ny,nz,iter
+      REAL(c_double), VALUE :: dx,h
+      INTEGER(c_int) :: n_exit
+      REAL(c_double) :: rms_hist(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_reinit
+
+   FUNCTION c_lsf_narrowband(nx,ny,nz,dx,phi,phiNB,phiSB) BIND(C, NAME='lsf_narrowband') RESULT(rc)
+      IMPORT :: c_int, c_double, c_int32_t
+      INTEGER(c_int), VALUE :: nx,ny,nz
+      REAL(c_double), VALUE :: dx
+      REAL(c_double), INTENT(IN) :: phi(*)
+      INTEGER(c_int32_t) :: phiNB(*), phiSB(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_narrowband
+
+   FUNCTION c_lsf_minmax(phi,phiN,phiNB,phiSB,nx,ny,nz,iter,dx,h1,tol,n_exit,rms_hist) &
+                         BIND(C, NAME='lsf_minmax') RESULT(rc)
+      IMPORT :: c_int, c_double, c_int32_t
+      REAL(c_double) :: phi(*), phiN(*)
+      INTEGER(c_int32_t) :: phiNB(*), phiSB(*)
+      INTEGER(c_int), VALUE :: nx,ny,nz,iter
+      REAL(c_double), VALUE :: dx,h1,tol
+      INTEGER(c_int) :: n_exit
+      REAL(c_double) :: rms_hist(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_minmax
+
+END INTERFACE
+
+CONTAINS
+
+!*************************************************************************************!
+! library failure (rc < 0): print the library's message and stop, like the reference's
+! other fatal paths (set3d.f90:79-80)
+!*************************************************************************************!
+SUBROUTINE lsf_fail(where, rc)
+   CHARACTER(LEN=*), INTENT(IN) :: where
+   INTEGER(c_int), INTENT(IN) :: rc
+   TYPE(c_ptr) :: p
+   CHARACTER(KIND=c_char), POINTER :: s(:)
+   INTEGER :: q
+   p = lsf_last_error()
+   PRINT*, " liblsf_b200 failure in ", where, " code ", rc
+   IF (C_ASSOCIATED(p)) THEN
+      CALL C_F_POINTER(p, s, (/512/))
+      DO q = 1,512
+         IF (s(q) == C_NULL_CHAR) EXIT
+         WRITE(*,'(A)',ADVANCE='NO') s(q)
+      END DO
+      PRINT*,
+   END IF
+   STOP 2
+END SUBROUTINE lsf_fail
+
+!*************************************************************************************!
+! Inside/outside sign search: replaces the loop nest set3d.f90:196-268 (centroids,
+! nearest-centroid search, triple product, phiSign with gM = 1).  phi keeps its fill
+! value (1., set3d.f90:161) outside the sub-box im..ip, jm..jp, km..kp.
+!*************************************************************************************!
+SUBROUTINE signSearch_b200(phi,nx,ny,nz,xLo,dx,surfX,nSurfNode,surfElem,nSurfElem,im,ip,jm,jp,km,kp)
+   INTEGER, INTENT(IN) :: nx,ny,nz,im,ip,jm,jp,km,kp
+   INTEGER(c_int32_t), INTENT(IN) :: nSurfNode,nSurfElem
+   REAL(c_double), INTENT(IN) :: xLo(3),dx
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phi
+   REAL(c_double), DIMENSION(nSurfNode,3), INTENT(IN) :: surfX
+   INTEGER(c_int32_t), DIMENSION(nSurfElem,3), INTENT(IN) :: surfElem
+   INTEGER(c_int) :: rc
+   rc = c_lsf_sign_init(phi,INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),xLo,dx,surfX,INT(nSurfNode,c_int), &
+                        surfElem,INT(nSurfElem,c_int),INT(im,c_int),INT(ip,c_int),INT(jm,c_int), &
+                        INT(jp,c_int),INT(km,c_int),INT(kp,c_int))
+   IF (rc < 0) CALL lsf_fail("signSearch_b200", rc)
+END SUBROUTINE signSearch_b200
+
+!*************************************************************************************!
+! SUBROUTINE reinit(phi,gradPhi,gradPhiMag,nx,ny,nz,iter,dx,h), subs.f90:717-931.
+! Same argument list; prints the reference's per-iteration lines (subs.f90:916,923)
+! from the returned RMS history and STOPs on a NaN RMS like subs.f90:926.
+!*************************************************************************************!
+SUBROUTINE reinit_b200(phi,gradPhi,gradPhiMag,nx,ny,nz,iter,dx,h)
+   INTEGER, INTENT(IN) :: nx,ny,nz,iter
+   REAL(c_double), INTENT(IN) :: dx,h
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phi,gradPhiMag
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz,3), INTENT(INOUT) :: gradPhi
+   REAL(c_double), ALLOCATABLE :: hist(:)
+   INTEGER(c_int) :: rc, n_exit
+   INTEGER :: n
+   ALLOCATE(hist(0:iter))
+   rc = c_lsf_reinit(phi,gradPhi,gradPhiMag,INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),INT(iter,c_int), &
+                     dx,h,n_exit,hist)
+   IF (rc < 0) CALL lsf_fail("reinit_b200", rc)
+   DO n = 0,n_exit
+      IF (n == n_exit .AND. rc == LSF_OK .AND. hist(n) < 1.E-5) THEN
+         PRINT*, " Distance function time integration has reached steady state "
+      ELSE
+         PRINT*, " Iteration: ",n," ", " RMS Error: ",hist(n)
+      END IF
+   END DO
+   DEALLOCATE(hist)
+   IF (rc == LSF_NAN) STOP
+   PRINT*,
+END SUBROUTINE reinit_b200
+
+!*************************************************************************************!
+! SUBROUTINE narrowBand(nx,ny,nz,dx,phi,phiNB,phiSB), subs.f90:178-207
+!*************************************************************************************!
+SUBROUTINE narrowBand_b200(nx,ny,nz,dx,phi,phiNB,phiSB)
+   INTEGER, INTENT(IN) :: nx,ny,nz
+   REAL(c_double), INTENT(IN) :: dx
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(IN) :: phi
+   INTEGER(c_int32_t), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phiNB,phiSB
+   INTEGER(c_int) :: rc
+   rc = c_lsf_narrowband(INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),dx,phi,phiNB,phiSB)
+   IF (rc < 0) CALL lsf_fail("narrowBand_b200", rc)
+END SUBROUTINE narrowBand_b200
+
+!*************************************************************************************!
+! The min/max flow time loop, set3d.f90:394-462 (DO n = 1,iter ... END DO), including the
+! per-iteration narrowBand (:460), the RMS / steady-state EXIT (:435-451) and the NaN STOP
+! (:458).  tol = 1.E-7 in the reference.  On return phi, phiN, phiNB, phiSB hold what the
+! reference loop leaves in them; nDone = the loop index at which it left.
+!*************************************************************************************!
+SUBROUTINE minMaxFlow_b200(phi,phiN,phiNB,phiSB,nx,ny,nz,iter,dx,h1,tol,nDone)
+   INTEGER, INTENT(IN) :: nx,ny,nz,iter
+   REAL(c_double), INTENT(IN) :: dx,h1,tol
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phi,phiN
+   INTEGER(c_int32_t), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phiNB,phiSB
+   INTEGER, INTENT(OUT) :: nDone
+   REAL(c_double), ALLOCATABLE :: hist(:)
+   INTEGER(c_int) :: rc, n_exit
+   INTEGER :: n
+   ALLOCATE(hist(MAX(iter,1)))
+   rc = c_lsf_minmax(phi,phiN,phiNB,phiSB,INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),INT(iter,c_int), &
+                     dx,h1,tol,n_exit,hist)
+   IF (rc < 0) CALL lsf_fail("minMaxFlow_b200", rc)
+   nDone = n_exit
+   DO n = 1,n_exit
+      IF (n == n_exit .AND. rc == LSF_OK .AND. hist(n) < tol) THEN
+         PRINT*, " Min/max time integration has reached steady state "
+      ELSE
+         PRINT*, " Iteration: ",n," ", " RMS Error: ",hist(n)
+      END IF
+   END DO
+   DEALLOCATE(hist)
+   IF (rc == LSF_NAN) STOP
+END SUBROUTINE minMaxFlow_b200
+
+END MODULE lsf_b200

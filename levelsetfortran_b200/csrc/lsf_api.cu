@@ -220,6 +220,9 @@ int lsf_init(int device)
     LSF_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
     LSF_CUDA(cudaEventCreate(&G.ev0));
     LSF_CUDA(cudaEventCreate(&G.ev1));
+    // environment overrides for hosts that cannot easily call the setters (e.g. a Fortran driver)
+    if (const char *a = getenv("LSF_ARITH")) G.arith = (strcmp(a, "exact") == 0) ? LSF_ARITH_EXACT : LSF_ARITH_FAST;
+    if (const char *s = getenv("LSF_SCHED")) G.sched = (strcmp(s, "plane") == 0) ? LSF_SCHED_PLANE : LSF_SCHED_MARCH;
     G.inited = true;
     return LSF_OK;
 }
