@@ -68,12 +68,12 @@ static int reinit_core(Grid *g, int iter, double dx, double h, double tol, doubl
     if (rc) return rc;
     const size_t bytes = sizeof(double) * (size_t)g->np;
     LSF_CUDA(cudaMemcpyAsync(g->phiS, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:731
-    LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
     LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
     CellConst cc;
     cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
     const bool want_grad = d_gradPhi || d_gradPhiMag;
     const bool march = (G.sched == LSF_SCHED_MARCH) && !want_grad;
+    if (!march) LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
     if (march) { rc = march_prepare(g); if (rc) return rc; }
     const int check = march ? 8 : (g->np > 2000000 ? 1 : 8);
     Timer tm;
@@ -93,9 +93,16 @@ static int reinit_core(Grid *g, int iter, double dx, double h, double tol, doubl
         if (march) launch_reinit_sweep_march(g, raster, cc);
         else launch_reinit_sweep_plane(g, raster, cc, d_gradPhi, d_gradPhiMag);
         if (G.profile) { cudaEventRecord(pev[npend][1], G.stream); ++npend; }
-        launch_reinit_bc(g, dx);                                        // subs.f90:858-897
-        launch_rms(g, true);                                            // subs.f90:902-914,921
-        launch_finalize(g, RMS_BLOCKS, 0, tol);                         // subs.f90:914-926
+        if (march) {
+            // RMS fused: interior sums come from the sweep (one per column tile), boundary sums from the
+            // BC kernel; phiN (subs.f90:732,921) is never materialised on this path
+            launch_reinit_bc_rms(g, dx, march_ntiles(g));               // subs.f90:858-897 + boundary part of :902-914
+            launch_finalize(g, march_ntiles(g) + BC_BLOCKS, 0, tol);    // subs.f90:914-926
+        } else {
+            launch_reinit_bc(g, dx);                                    // subs.f90:858-897
+            launch_rms(g, true);                                        // subs.f90:902-914,921
+            launch_finalize(g, RMS_BLOCKS, 0, tol);                     // subs.f90:914-926
+        }
         if ((n + 1) % check == 0 || n == iter) {
             rc = read_ctrl(g, &hc);
             if (rc) return rc;
@@ -292,7 +299,7 @@ int lsf_grid_create(lsf_grid **out, int nx, int ny, int nz)
     cudaError_t e;
     if ((e = cudaMalloc(&g->phi, bytes)) != cudaSuccess || (e = cudaMalloc(&g->phiS, bytes)) != cudaSuccess ||
         (e = cudaMalloc(&g->phiN, bytes)) != cudaSuccess ||
-        (e = cudaMalloc(&g->partial, sizeof(double) * 65536)) != cudaSuccess ||
+        (e = cudaMalloc(&g->partial, sizeof(double) * PARTIAL_CAP)) != cudaSuccess ||
         (e = cudaMalloc(&g->ctrl, sizeof(Ctrl))) != cudaSuccess) {
         lsf_grid_destroy(g);
         return set_error(LSF_ERR_CUDA, "grid_create: %s", cudaGetErrorString(e));

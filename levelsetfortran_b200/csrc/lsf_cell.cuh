@@ -140,6 +140,28 @@ struct ExactArith {
 
 // ------------------------------------------------------------------------------------------
 struct FastArith {
+    // ---- select-style helpers that stay off the FP64 pipe ---------------------------------------
+    // (a double fmax/fmin costs a DSETP on the FP64 pipe plus ~6 integer instructions of NaN
+    // fix-up; here the operands are known to be sign-definite, so integer compares on the bit
+    // patterns are exact.  NaN inputs are not canonicalised: a NaN still ends in a NaN RMS.)
+#if defined(__CUDA_ARCH__)
+    static LSF_HD double pos_part(double x) { return __double2hiint(x) < 0 ? 0.0 : x; }          // max(x, 0)
+    static LSF_HD double neg_part(double x) { return __double2hiint(x) < 0 ? x : 0.0; }          // min(x, 0), -0 for x = 0
+    static LSF_HD double dabs(double x) { return __longlong_as_double(__double_as_longlong(x) & 0x7fffffffffffffffLL); }
+    static LSF_HD double max_nn(double a, double b)                                              // a, b >= 0
+    {
+        const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+        return __longlong_as_double(ia > ib ? ia : ib);
+    }
+    static LSF_HD double rsq(double x) { return rsqrt(x); }
+#else
+    static LSF_HD double pos_part(double x) { return x > 0. ? x : 0.0; }
+    static LSF_HD double neg_part(double x) { return x < 0. ? x : 0.0; }
+    static LSF_HD double dabs(double x) { return fabs(x); }
+    static LSF_HD double max_nn(double a, double b) { return a > b ? a : b; }
+    static LSF_HD double rsq(double x) { return 1.0 / sqrt(x); }
+#endif
+
     static LSF_HD double rcp(double x)
     {
 #if defined(__CUDA_ARCH__)
@@ -159,11 +181,11 @@ struct FastArith {
     static LSF_HD void weights(double E0, double E1, double E2, double &w0x2, double &w2mh)
     {
         const double q0 = E0 * E0, q1 = E1 * E1, q2 = E2 * E2;
-        const double n0 = q1 * q2, x = q0 * q2, y = q0 * q1;
-        const double D = fma(6.0, x, fma(3.0, y, n0));
+        const double n0 = q1 * q2, x = q0 * q2, y3 = 3.0 * (q0 * q1);
+        const double D = fma(6.0, x, y3 + n0);
         const double r = rcp(D);
         w0x2 = (n0 + n0) * r;
-        w2mh = fma(3.0 * y, r, -0.5);
+        w2mh = fma(y3, r, -0.5);
     }
 
     template <bool YQ>
@@ -173,23 +195,24 @@ struct FastArith {
         const double e3 = v[4] - v[3], e4 = v[5] - v[4], e5 = v[6] - v[5];
         const double am = e1 - e0, bm = e2 - e1, c = e3 - e2, bp = e4 - e3, ap = e5 - e4;
         const double tpa = ap - bp, tpb = bp - c, tmc = c - bm, tma = am - bm;
-        const double s13b = 13.0 * tpb * tpb, s13c = 13.0 * tmc * tmc;
-        double t;
-        t = fma(-3.0, bp, ap); const double IS0p = fma(13.0 * tpa, tpa, 3.0 * t * t);
-        t = bp + c;            const double IS1p = fma(3.0 * t, t, s13b);
-        t = fma(3.0, c, -bm);  const double IS2p = fma(3.0 * t, t, s13c);
-        t = fma(-3.0, bm, am); const double IS0m = fma(13.0 * tma, tma, 3.0 * t * t);
-        t = bm + c;            const double IS1m = fma(3.0 * t, t, s13c);
-        t = fma(3.0, c, -bp);  const double IS2m = fma(3.0 * t, t, s13b);
-        const double mc = fmax(fmax(fabs(e1), fabs(e2)), fmax(fabs(e3), fabs(e4)));
-        const double mp = YQ ? mc : fmax(mc, fabs(e5));
-        const double mm = fmax(mc, fabs(e0));
+        const double mc = max_nn(max_nn(dabs(e1), dabs(e2)), max_nn(dabs(e3), dabs(e4)));
+        const double mp = YQ ? mc : max_nn(mc, dabs(e5));
+        const double mm = max_nn(mc, dabs(e0));
         const double tiny = 1.0e-60;
         const double epsp = fma(1.0e-6 * mp, mp, tiny);
         const double epsm = fma(1.0e-6 * mm, mm, tiny);
+        const double s13b = (13.0 * tpb) * tpb, s13c = (13.0 * tmc) * tmc;
+        double t;
+        // E_k = eps + IS_k, the eps folded into the FMA chains
+        t = fma(-3.0, bp, ap); const double E0p = fma(13.0 * tpa, tpa, fma(3.0 * t, t, epsp));
+        t = bp + c;            const double E1p = fma(3.0 * t, t, s13b + epsp);
+        t = fma(3.0, c, -bm);  const double E2p = fma(3.0 * t, t, s13c + epsp);
+        t = fma(-3.0, bm, am); const double E0m = fma(13.0 * tma, tma, fma(3.0 * t, t, epsm));
+        t = bm + c;            const double E1m = fma(3.0 * t, t, s13c + epsm);
+        t = fma(3.0, c, -bp);  const double E2m = fma(3.0 * t, t, s13b + epsm);
         double w0p2, w2ph, w0m2, w2mh;
-        weights(epsp + IS0p, epsp + IS1p, epsp + IS2p, w0p2, w2ph);
-        weights(epsm + IS0m, epsm + IS1m, epsm + IS2m, w0m2, w2mh);
+        weights(E0p, E1p, E2p, w0p2, w2ph);
+        weights(E0m, E1m, E2m, w0m2, w2mh);
         const double s = tpb - tmc;
         const double Yp = fma(w0p2, tpa - tpb, w2ph * s);
         const double Ym = fma(w0m2, tma + tmc, w2mh * s);
@@ -211,18 +234,19 @@ struct FastArith {
         const double ax = pos ? a : b, bx = pos ? b : a;
         const double ay = pos ? c : d, by = pos ? d : c;
         const double az = pos ? e : f, bz = pos ? f : e;
-        const double x1 = fmax(ax, 0.), x2 = fmin(bx, 0.);
-        const double y1 = fmax(ay, 0.), y2 = fmin(by, 0.);
-        const double z1 = fmax(az, 0.), z2 = fmin(bz, 0.);
-        g[0] = fmax(x1 * x1, x2 * x2);
-        g[1] = fmax(y1 * y1, y2 * y2);
-        g[2] = fmax(z1 * z1, z2 * z2);
+        const double x1 = pos_part(ax), x2 = neg_part(bx);
+        const double y1 = pos_part(ay), y2 = neg_part(by);
+        const double z1 = pos_part(az), z2 = neg_part(bz);
+        g[0] = max_nn(x1 * x1, x2 * x2);
+        g[1] = max_nn(y1 * y1, y2 * y2);
+        g[2] = max_nn(z1 * z1, z2 * z2);
         return sqrt(g[0] + g[1] + g[2]);
     }
 
     static LSF_HD double update(double phic, double phiS, double gM, const CellConst &cc)
     {
-        const double sgn = phiS / sqrt(fma(phiS, phiS, cc.dx2 * gM));
+        // phiS / sqrt(phiS^2 + dx^2 gM): 0 * rsqrt(0) = NaN reproduces the reference's 0/0 (subs.f90:169)
+        const double sgn = phiS * rsq(fma(phiS, phiS, cc.dx2 * gM));
         return fma(cc.h, sgn * (1.0 - gM), phic);
     }
 };

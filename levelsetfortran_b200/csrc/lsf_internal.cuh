@@ -27,6 +27,8 @@ namespace lsf {
 typedef lsf_grid Grid;
 
 constexpr int RMS_BLOCKS = 1184;   // 8 x 148 SMs
+constexpr int BC_BLOCKS = 592;     // 4 x 148 SMs
+constexpr int PARTIAL_CAP = 65536 + RMS_BLOCKS;
 
 struct Global {
     bool inited = false;
@@ -57,6 +59,7 @@ int set_error(int code, const char *fmt, ...);
 // lsf_kernels.cu
 void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double *gradPhi, double *gradPhiMag);
 void launch_reinit_bc(Grid *g, double dx);
+void launch_reinit_bc_rms(Grid *g, double dx, int partial_off);
 void launch_rms(Grid *g, bool copy);
 void launch_finalize(Grid *g, int npart, int hist_off, double tol);
 void launch_copy_if_running(Grid *g, double *dst, const double *src);
@@ -70,6 +73,7 @@ void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_s
 
 // lsf_march.cu
 int march_prepare(Grid *g);
+int march_ntiles(const Grid *g);
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc);
 
 }  // namespace lsf

@@ -110,6 +110,53 @@ void launch_reinit_bc(Grid *g, double dx)
     G.n_launch++;
 }
 
+// K3+K4 fused: the same closed form, every boundary point visited exactly once (k faces whole,
+// j faces without the k faces' points, i faces without both), and the boundary part of the RMS sum
+// (subs.f90:902-914) accumulated on the fly: the sweep never writes boundary points, so the value
+// found in phi IS phiN there.  Together with the per-tile sums of the sweep kernel this makes the
+// separate RMS pass and the phiN array unnecessary in reinit.  Per-block partials, fixed order.
+__global__ void __launch_bounds__(256)
+k_reinit_bc_rms(double *__restrict__ phi, Dims dm, double dx, double *__restrict__ partial,
+                const Ctrl *__restrict__ ctrl)
+{
+    if (ctrl->done) return;
+    __shared__ double sh[256];
+    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzm = dm.nz - 1, nym = dm.ny - 1;
+    const long long fk = nxp * nyp, fj = nxp * nzm, fi = nym * nzm;
+    const long long tot = 2 * (fk + fj + fi);
+    double acc = 0.;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < tot; t0 += (long long)gridDim.x * blockDim.x) {
+        long long t = t0;
+        int i, j, k;
+        if (t < 2 * fk) { k = (t >= fk) ? dm.nz : 0; t %= fk; i = (int)(t % nxp); j = (int)(t / nxp); }
+        else if ((t -= 2 * fk) < 2 * fj) { j = (t >= fj) ? dm.ny : 0; t %= fj; i = (int)(t % nxp); k = 1 + (int)(t / nxp); }
+        else { t -= 2 * fj; i = (t >= fi) ? dm.nx : 0; t %= fi; j = 1 + (int)(t % nym); k = 1 + (int)(t / nym); }
+        const int B = (i == 0 || i == dm.nx) + (j == 0 || j == dm.ny) + (k == 0 || k == dm.nz);
+        const int H = (i == dm.nx) + (j == dm.ny) + (k == dm.nz);
+        const int m = min(1 + H, B);
+        const int ci = min(max(i, 1), dm.nx - 1), cj = min(max(j, 1), dm.ny - 1), ck = min(max(k, 1), dm.nz - 1);
+        double v = phi[ci + dm.sx * cj + dm.sxy * ck];
+        for (int r = 0; r < m; ++r) v = __dadd_rn(v, dx);
+        const long long q = i + dm.sx * j + dm.sxy * k;
+        const double d = __dsub_rn(v, phi[q]);
+        acc = __dadd_rn(acc, __dmul_rn(d, d));
+        phi[q] = v;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+void launch_reinit_bc_rms(Grid *g, double dx, int partial_off)
+{
+    k_reinit_bc_rms<<<BC_BLOCKS, 256, 0, G.stream>>>(g->phi, g->dm, dx, g->partial + partial_off, g->ctrl);
+    G.n_launch++;
+}
+
 // =====================================================================================
 // K4: RMS of (phi - phiN) over ALL points (subs.f90:902-914, set3d.f90:435-447) as per-block
 // partial sums in a fixed order (deterministic run to run), optionally fused with phiN = phi

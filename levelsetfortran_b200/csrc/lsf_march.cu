@@ -1,4 +1,5 @@
 // lsf_march.cu -- GPU launch of the skewed x-marching column-tile sweep (lsf_march.cuh).
+#include <stdlib.h>
 #include <vector>
 
 #include "lsf_internal.cuh"
@@ -6,13 +7,41 @@
 
 namespace lsf {
 
-template <class AR>
-__global__ void __launch_bounds__(M_THREADS, 2)
+#ifndef LSF_TB
+#define LSF_TB 16
+#endif
+#ifndef LSF_TC
+#define LSF_TC 16
+#endif
+#ifndef LSF_OCC
+#define LSF_OCC 2      // resident CTAs per SM (register budget 65536 / (OCC * THREADS))
+#endif
+typedef MarchCfg<LSF_TB, LSF_TC> CFG;
+
+template <class AR, bool FA, bool FB, bool FC>
+__global__ void __launch_bounds__(CFG::THREADS, LSF_OCC)
 k_reinit_march(const MarchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    MarchSmem &sm = *reinterpret_cast<MarchSmem *>(smem_raw);
-    march_cta<AR>(p, sm, threadIdx.x);
+    MarchSmem<CFG> &sm = *reinterpret_cast<MarchSmem<CFG> *>(smem_raw);
+    march_cta<AR, FA, FB, FC, CFG>(p, sm, threadIdx.x);
+}
+
+typedef void (*MarchKernel)(const MarchParams);
+
+template <class AR>
+static MarchKernel march_kernel(int fa, int fb, int fc)
+{
+    switch ((fa ? 1 : 0) | (fb ? 2 : 0) | (fc ? 4 : 0)) {
+    case 0: return k_reinit_march<AR, false, false, false>;
+    case 1: return k_reinit_march<AR, true, false, false>;
+    case 2: return k_reinit_march<AR, false, true, false>;
+    case 3: return k_reinit_march<AR, true, true, false>;
+    case 4: return k_reinit_march<AR, false, false, true>;
+    case 5: return k_reinit_march<AR, true, false, true>;
+    case 6: return k_reinit_march<AR, false, true, true>;
+    default: return k_reinit_march<AR, true, true, true>;
+    }
 }
 
 struct MarchHost {
@@ -21,10 +50,15 @@ struct MarchHost {
 };
 static MarchHost MH;   // order table of the most recent grid shape
 
+int march_ntiles(const Grid *g)
+{
+    return ((g->dm.ny - 1 + CFG::TB - 1) / CFG::TB) * ((g->dm.nz - 1 + CFG::TC - 1) / CFG::TC);
+}
+
 int march_prepare(Grid *g)
 {
     MarchParams p;
-    march_orient(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, 1);
+    march_orient<CFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, 1);
     if (p.ntiles > 65536) return set_error(LSF_ERR_ARG, "march: more than 65536 column tiles");
     if (!g->march_ticket) LSF_CUDA(cudaMalloc(&g->march_ticket, sizeof(unsigned)));
     if (g->march_tiles_cap < p.ntiles) {
@@ -46,8 +80,10 @@ int march_prepare(Grid *g)
     }
     static bool attr_done = false;
     if (!attr_done) {
-        LSF_CUDA(cudaFuncSetAttribute(k_reinit_march<FastArith>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)));
-        LSF_CUDA(cudaFuncSetAttribute(k_reinit_march<ExactArith>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)));
+        for (int o = 0; o < 8; ++o) {
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+        }
         attr_done = true;
     }
     return LSF_OK;
@@ -56,15 +92,40 @@ int march_prepare(Grid *g)
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
 {
     MarchParams p;
-    march_orient(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, raster);
+    march_orient<CFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, raster);
     p.phi = g->phi; p.phiS = g->phiS; p.cc = cc;
     p.partial = g->partial; p.ticket = g->march_ticket; p.order = MH.d_order;
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
+    p.dbg = nullptr;
+#if defined(LSF_EXP_TIMING)
+    {   // experiment: dump per-tile timing of this sweep to $LSF_TIMING_DUMP after the launch (synchronous)
+        static long long *d_dbg = nullptr; static int cap = 0;
+        if (cap < p.ntiles) { cudaFree(d_dbg); cudaMalloc(&d_dbg, sizeof(long long) * 6 * p.ntiles); cap = p.ntiles; }
+        p.dbg = d_dbg;
+    }
+#endif
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
-    const int ncta = p.ntiles < 2 * G.num_sms ? p.ntiles : 2 * G.num_sms;
-    if (G.arith == LSF_ARITH_EXACT) k_reinit_march<ExactArith><<<ncta, M_THREADS, sizeof(MarchSmem), G.stream>>>(p);
-    else k_reinit_march<FastArith><<<ncta, M_THREADS, sizeof(MarchSmem), G.stream>>>(p);
+    const int ncta = p.ntiles < LSF_OCC * G.num_sms ? p.ntiles : LSF_OCC * G.num_sms;
+    MarchKernel kern = (G.arith == LSF_ARITH_EXACT) ? march_kernel<ExactArith>(p.fa, p.fb, p.fc)
+                                                    : march_kernel<FastArith>(p.fa, p.fb, p.fc);
+    kern<<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(p);
     G.n_launch++;
+#if defined(LSF_EXP_TIMING)
+    if (const char *path = getenv("LSF_TIMING_DUMP")) {
+        cudaStreamSynchronize(G.stream);
+        std::vector<long long> h(6 * (size_t)p.ntiles);
+        cudaMemcpy(h.data(), p.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        FILE *f = fopen(path, "w");
+        if (f) {
+            fprintf(f, "# raster %d ntb %d ntc %d : tile J K start_ns end_ns wait_cycles total_cycles smid cta\n", raster, p.ntb, p.ntc);
+            long long t0 = h[0];
+            for (int q = 0; q < p.ntiles; ++q) if (h[6 * q] < t0) t0 = h[6 * q];
+            for (int q = 0; q < p.ntiles; ++q)
+                fprintf(f, "%d %d %lld %lld %lld %lld %lld %lld\n", q % p.ntb, q / p.ntb, h[6 * q] - t0, h[6 * q + 1] - t0, h[6 * q + 2], h[6 * q + 3], h[6 * q + 4], h[6 * q + 5]);
+            fclose(f);
+        }
+    }
+#endif
 }
 
 }  // namespace lsf

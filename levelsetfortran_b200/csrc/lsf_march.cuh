@@ -8,20 +8,26 @@
 //   * thread (tb,tc) owns the whole x-row (b0+tb, c0+tc) and marches along a (the contiguous
 //     axis), skewed by one cell per unit of tb+tc: at step t it updates a = 1 + t - (tb+tc+3).
 //     All TB*TC threads are busy every step (except the ~TB+TC ramp steps at both ends);
-//   * the row's own +-3 window lives in registers (3 new values behind, 3 old ahead);
-//   * y/z neighbours are exchanged through a ring of NSLOT hyperplane slots in shared memory:
+//   * ALL 19 stencil values come from a ring of hyperplane slots in shared memory:
 //     slot(h) holds, for every row of the tile and its 3-wide halo, the cell whose step index
 //     is h -- the OLD value until its owner reaches step h, the NEW one afterwards.  A thread
-//     at step t therefore reads slots t-3..t-1 (new) and t+1..t+3 (old): exactly what the
-//     reference's in-place loop sees.  One __syncthreads per step;
+//     at step t therefore reads slots t-3..t-1 (new) and t+1..t+3 (old) of its x/y/z neighbour
+//     rows: exactly what the reference's in-place loop sees.  One __syncthreads per step.
+//     The ring is stored position-major with the 8 slots written twice (S[pos][h&7] and
+//     S[pos][(h&7)+8]), so the 7-slot window t-3..t+3 is contiguous and every one of the 19 loads
+//     is  base(thread) + ((t-3)&7) + compile-time constant: no per-load address arithmetic;
+//   * the sweep orientation (which axes run backwards) is a template parameter, so the mapping of
+//     oriented stencil offsets to the physical -3..+3 stencil is resolved at compile time;
 //   * halo rows on the -b/-c side are the neighbouring tiles' NEW values, read from global
-//     memory (L2) behind a per-tile progress flag: the same cell is LAG=TB steps later in the
+//     memory (L2) behind a per-tile progress flag: the same cell is LAG=TB (TC) steps later in the
 //     neighbour's frame, so a tile simply runs >= LAG+CHUNK steps behind its two predecessors.
 //     +b/+c halo rows are OLD values, read 4 steps ahead; the successor tile cannot have
 //     overwritten them because it runs behind this tile by the same rule;
 //   * tiles are handed out through an atomic ticket in an order that is topological for
 //     (J-1,K) -> (J,K) <- (J,K-1), so a waiting CTA's predecessors are always running: no
-//     deadlock, no grid-wide barrier, one launch per sweep.
+//     deadlock, no grid-wide barrier, one launch per sweep;
+//   * the sum over the tile of (new-old)^2 -- the interior part of the RMS exit test,
+//     subs.f90:902-914 -- is accumulated on the fly (one partial per tile, fixed order).
 //
 // The file is written against a tiny set of primitives (sync, cache-global load/store, fence,
 // acquire/release flag access) so that tests/emu can compile the very same code for the CPU,
@@ -49,23 +55,44 @@ LSF_DEV void p_st_release(long long *p, long long v)
 {
     asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-LSF_DEV void p_sleep() { __nanosleep(40); }
+// polling load: relaxed (LDG.STRONG.GPU only).  ld.acquire would add an L1 invalidate (CCTL.IVALL) to
+// EVERY poll, which floods the LSU/MIO pipe the shared-memory loads go through; instead one acquire
+// fence is executed after the poll loop has seen the value it waits for.
+LSF_DEV long long p_ld_relaxed(const long long *p)
+{
+    long long v;
+    asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+LSF_DEV void p_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+LSF_DEV void p_sleep() { __nanosleep(100); }
 }  // namespace lsf
 #endif
 
 namespace lsf {
 
-constexpr int M_TB = 16, M_TC = 16;          // tile cross-section (oriented b x c)
-constexpr int M_THREADS = M_TB * M_TC;
 constexpr int M_H = 3;                       // stencil half-width
-constexpr int M_SW = M_TB + 2 * M_H;         // 22
-constexpr int M_SH = M_TC + 2 * M_H;         // 22
-constexpr int M_NSLOT = 8;
+constexpr int M_NSLOT = 8;                   // hyperplane slots in the ring (each stored twice)
+constexpr int M_SLOTW = 2 * M_NSLOT + 1;     // doubles per position: 16 + 1 pad (bank spread)
 constexpr int M_CHUNK = 8;                   // publish / wait granularity in steps
 constexpr int M_LOOK = 4;                    // old values are deposited this many steps ahead
-constexpr int M_NHALO = 2 * M_H * (M_TB + M_TC);   // 192 halo rows
 constexpr long long M_FIN = 1LL << 30;       // "tile finished" progress value
 constexpr long long M_BIAS = 1000;
+
+// Tile geometry.  TB x TC rows per CTA (oriented b x c), one thread per row.
+template <int TB_, int TC_>
+struct MarchCfg {
+    static constexpr int TB = TB_, TC = TC_;
+    static constexpr int THREADS = TB * TC;
+    static constexpr int SW = TB + 2 * M_H, SH = TC + 2 * M_H;
+    // pitch of one c-row of positions, in doubles; for TB = 8 a warp spans 4 c-rows and the pitch
+    // is padded to 8 (mod 16) doubles so that the two rows of a half-warp hit disjoint banks
+    static constexpr int RP = (TB >= 16) ? SW * M_SLOTW : ((SW * M_SLOTW + 15) / 16) * 16 + 8;
+    static constexpr int NHALO = 2 * M_H * (TB + TC);               // halo rows
+    static constexpr int HR = (NHALO + THREADS - 1) / THREADS;      // halo rows fed per thread
+    static constexpr int SMEM_DOUBLES = SH * RP;
+};
+typedef MarchCfg<16, 16> MarchCfgDefault;
 
 struct MarchParams {
     double *phi;
@@ -83,15 +110,18 @@ struct MarchParams {
     long long *progress;           // per tile (J + ntb*K)
     long long epoch;               // progress values are epoch*2^32 + step + BIAS
     const Ctrl *ctrl;
+    long long *dbg;                // timing experiments only (LSF_EXP_TIMING): 6 words per tile
 };
 
+template <class CFG>
 struct MarchSmem {
-    double S[M_NSLOT][M_SH][M_SW];
-    double red[M_THREADS];
+    double S[CFG::SMEM_DOUBLES];
+    double red[CFG::THREADS];
     int tile;
 };
 
 // Host helper shared with the emulator: fill the orientation-dependent fields.
+template <class CFG>
 inline void march_orient(MarchParams &p, int nx, int ny, int nz, long long sx, long long sxy, int raster)
 {
     int d[3];
@@ -106,10 +136,10 @@ inline void march_orient(MarchParams &p, int nx, int ny, int nz, long long sx, l
     p.lo_a = p.fa ? 5 : 4; p.hi_a = p.fa ? nx - 4 : nx - 5;
     p.lo_b = p.fb ? 5 : 4; p.hi_b = p.fb ? ny - 4 : ny - 5;
     p.lo_c = p.fc ? 5 : 4; p.hi_c = p.fc ? nz - 4 : nz - 5;
-    p.ntb = (ny - 1 + M_TB - 1) / M_TB;
-    p.ntc = (nz - 1 + M_TC - 1) / M_TC;
+    p.ntb = (ny - 1 + CFG::TB - 1) / CFG::TB;
+    p.ntc = (nz - 1 + CFG::TC - 1) / CFG::TC;
     p.ntiles = p.ntb * p.ntc;
-    p.tend = (nx - 1) - 1 + (M_TB - 1) + (M_TC - 1) + M_H;
+    p.tend = (nx - 1) - 1 + (CFG::TB - 1) + (CFG::TC - 1) + M_H;
 }
 
 // ticket order: anti-diagonals of the tile grid (J+K ascending): topological, and all tiles of
@@ -125,11 +155,13 @@ inline void march_fill_order(int ntb, int ntc, int *order)
         }
 }
 
-template <class AR>
-LSF_DEV void march_tile(const MarchParams &p, MarchSmem &sm, const int tid, const int J, const int K)
+template <class AR, bool FA, bool FB, bool FC, class CFG>
+LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K)
 {
-    const int tb = tid % M_TB, tc = tid / M_TB;
-    const int b = 1 + J * M_TB + tb, c = 1 + K * M_TC + tc;
+    constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP;
+    constexpr int W = M_SLOTW;
+    const int tb = tid % TB, tc = tid / TB;
+    const int b = 1 + J * TB + tb, c = 1 + K * TC + tc;
     const bool rowValid = (b <= p.ny) && (c <= p.nz);
     const bool compValid = (b <= p.ny - 1) && (c <= p.nz - 1);
     const bool hiBC = (b >= p.lo_b) && (b <= p.hi_b) && (c >= p.lo_c) && (c <= p.hi_c);
@@ -137,22 +169,37 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem &sm, const int tid, cons
     const long long rowoff = p.off0 + (long long)b * p.sb + (long long)c * p.sc;
     double *rowp = p.phi + (rowValid ? rowoff : 0);
     const double *rowS = p.phiS + (rowValid ? rowoff : 0);
+    double *const Sown = sm.S + (tc + M_H) * RP + (tb + M_H) * W;
 
-    // halo duty: thread q < 192 feeds one halo row
-    bool hvalid = false, hlow = false;
-    int htb = 0, htc = 0, hsig = 0;
-    const double *hrow = p.phi;
-    if (tid < M_NHALO) {
-        const int side = tid / (M_H * M_TB), r = tid % (M_H * M_TB);
-        const int m = r / M_TB + 1, idx = r % M_TB;
-        if (side == 0) { htb = -m; htc = idx; hlow = true; }
-        else if (side == 1) { htb = M_TB - 1 + m; htc = idx; }
-        else if (side == 2) { htb = idx; htc = -m; hlow = true; }
-        else { htb = idx; htc = M_TC - 1 + m; }
-        const int hb = 1 + J * M_TB + htb, hc = 1 + K * M_TC + htc;
-        hvalid = (hb >= 0) && (hb <= p.ny) && (hc >= 0) && (hc <= p.nz);
-        hsig = htb + htc + M_H;
-        if (hvalid) hrow = p.phi + p.off0 + (long long)hb * p.sb + (long long)hc * p.sc;
+    // halo duty: thread q feeds halo rows q, q+THREADS, ... (< NHALO)
+    bool hvalid[CFG::HR], hlow[CFG::HR];
+    int hsig[CFG::HR];
+    const double *hrow[CFG::HR];
+    double *hS[CFG::HR];
+#pragma unroll
+    for (int r = 0; r < CFG::HR; ++r) {
+        const int q = tid + r * THREADS;
+        hvalid[r] = false; hlow[r] = false; hsig[r] = 0; hrow[r] = p.phi; hS[r] = sm.S;
+        if (q < CFG::NHALO) {
+            int htb, htc;
+            if (q < 2 * M_H * TC) {                     // -b / +b sides: 3 rows x TC each
+                const int side = q / (M_H * TC), rr = q % (M_H * TC);
+                const int m = rr / TC + 1, idx = rr % TC;
+                htc = idx;
+                if (side == 0) { htb = -m; hlow[r] = true; } else htb = TB - 1 + m;
+            } else {                                    // -c / +c sides: 3 rows x TB each
+                const int q2 = q - 2 * M_H * TC;
+                const int side = q2 / (M_H * TB), rr = q2 % (M_H * TB);
+                const int m = rr / TB + 1, idx = rr % TB;
+                htb = idx;
+                if (side == 0) { htc = -m; hlow[r] = true; } else htc = TC - 1 + m;
+            }
+            const int hb = 1 + J * TB + htb, hc = 1 + K * TC + htc;
+            hvalid[r] = (hb >= 0) && (hb <= p.ny) && (hc >= 0) && (hc <= p.nz);
+            hsig[r] = htb + htc + M_H;
+            hS[r] = sm.S + (htc + M_H) * RP + (htb + M_H) * W;
+            if (hvalid[r]) hrow[r] = p.phi + p.off0 + (long long)hb * p.sb + (long long)hc * p.sc;
+        }
     }
 
     const long long ebase = p.epoch << 32;
@@ -160,87 +207,121 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem &sm, const int tid, cons
     const long long *predC = (K > 0) ? p.progress + (J + p.ntb * (K - 1)) : nullptr;
     long long *mine = p.progress + (J + p.ntb * K);
 
-    double w0 = 0., w1 = 0., w2 = 0., w3 = 0., w4 = 0., w5 = 0., w6 = 0.;
     double acc = 0.;
+#if defined(LSF_EXP_TIMING)
+    long long dbg_wait = 0, dbg_t0 = 0, dbg_c0 = 0;
+    if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); dbg_c0 = clock64(); }
+#endif
+    // running pointers: cell a of the own row (phi, phiS) and cell ah of each halo row, advanced by
+    // one cell per step (a = 1 + t - sig)
+    constexpr long long SA = FA ? -1 : 1;
+    double *pOut = rowp + (long long)(1 - M_LOOK - sig) * SA;
+    const double *pSgn = rowS + (long long)(1 - M_LOOK - sig) * SA;
+    const double *hp[CFG::HR];
+#pragma unroll
+    for (int r = 0; r < CFG::HR; ++r)
+        hp[r] = hrow[r] + (long long)(1 - M_LOOK + (hlow[r] ? 0 : M_LOOK) - hsig[r]) * SA;
 
-    for (int t = -M_LOOK; t <= p.tend; ++t) {
+    for (int t = -M_LOOK; t <= p.tend; ++t, pOut += SA, pSgn += SA) {
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
         if (t >= 0 && (t % M_CHUNK) == 0) {
-            const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + M_TB);
-            const long long need_c = ebase + M_BIAS + (t + M_CHUNK - 1 + M_TC);
-            if (tid == 0 && predB) { while (p_ld_acquire(predB) < need_b) p_sleep(); }
-            if (tid == 32 && predC) { while (p_ld_acquire(predC) < need_c) p_sleep(); }
+            const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + TB);
+            const long long need_c = ebase + M_BIAS + (t + M_CHUNK - 1 + TC);
+#if defined(LSF_EXP_TIMING)
+            long long tw0 = 0;
+            if (tid == 0) tw0 = clock64();
+#endif
+            if (tid == 0 && predB) { while (p_ld_relaxed(predB) < need_b) p_sleep(); p_fence_acquire(); }
+            if (tid == 32 % THREADS && predC) { while (p_ld_relaxed(predC) < need_c) p_sleep(); p_fence_acquire(); }
             p_sync();
+#if defined(LSF_EXP_TIMING)
+            if (tid == 0) dbg_wait += clock64() - tw0;
+#endif
         }
         const int a = 1 + t - sig;
         // ---- (1) issue the global loads of this step --------------------------------------
         const int a4 = a + M_LOOK;
         const bool ldLook = rowValid && (a4 >= 0) && (a4 <= p.nx);
         double la = 0.;
-        if (ldLook) la = p_ldcg(rowp + a4 * p.sa);
+        if (ldLook) la = p_ldcg(pOut + M_LOOK * SA);
         const bool active = compValid && (a >= 1) && (a <= p.nx - 1);
         double ps = 0.;
-        if (active) ps = p_ldcg(rowS + a * p.sa);
-        bool hdep = false;
-        double hv = 0.;
-        int hh = 0;
-        if (hvalid) {
-            hh = hlow ? t : t + M_LOOK;
-            const int ah = 1 + hh - hsig;
-            if (hh >= 0 && ah >= 0 && ah <= p.nx) { hv = p_ldcg(hrow + ah * p.sa); hdep = true; }
+        if (active) ps = p_ldcg(pSgn);
+        bool hdep[CFG::HR];
+        double hv[CFG::HR];
+        int hh[CFG::HR];
+#pragma unroll
+        for (int r = 0; r < CFG::HR; ++r) {
+            hdep[r] = false; hv[r] = 0.; hh[r] = 0;
+            if (hvalid[r]) {
+                hh[r] = hlow[r] ? t : t + M_LOOK;
+                const int ah = 1 + hh[r] - hsig[r];
+                if (hh[r] >= 0 && ah >= 0 && ah <= p.nx) { hv[r] = p_ldcg(hp[r]); hdep[r] = true; }
+            }
+            hp[r] += SA;
         }
         // ---- (2) cell update ----------------------------------------------------------------
-        double pn = w3;
+        double pn = 0.;
         if (active) {
-            double vy[7], vz[7], vx[7];
-            const int sy = tc + M_H, sx = tb + M_H;
+            const double *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
+            double vx[7], vy[7], vz[7];
 #pragma unroll
             for (int m = -3; m <= 3; ++m) {
-                if (m == 0) continue;
-                const int sl = (t + m) & (M_NSLOT - 1);
-                const double yv = sm.S[sl][sy][sx + m];
-                const double zv = sm.S[sl][sy + m][sx];
-                vy[p.fb ? 3 - m : 3 + m] = yv;
-                vz[p.fc ? 3 - m : 3 + m] = zv;
+                vx[FA ? 3 - m : 3 + m] = Wn[3 + m];
+                if (m != 0) {
+                    vy[FB ? 3 - m : 3 + m] = Wn[m * W + 3 + m];
+                    vz[FC ? 3 - m : 3 + m] = Wn[m * RP + 3 + m];
+                }
             }
-            vy[3] = w3; vz[3] = w3;
-            if (p.fa) { vx[0] = w6; vx[1] = w5; vx[2] = w4; vx[3] = w3; vx[4] = w2; vx[5] = w1; vx[6] = w0; }
-            else      { vx[0] = w0; vx[1] = w1; vx[2] = w2; vx[3] = w3; vx[4] = w4; vx[5] = w5; vx[6] = w6; }
+            vy[3] = vx[3]; vz[3] = vx[3];
             const bool hi = hiBC && (a >= p.lo_a) && (a <= p.hi_a);
             double g[3], gM;
             pn = reinit_cell<AR>(vx, vy, vz, ps, hi, p.cc, g, gM);
-            const double df = pn - w3;
+            const double df = pn - vx[3];
             acc += df * df;
-            p_stcg(rowp + a * p.sa, pn);
+            p_stcg(pOut, pn);
         }
-        // ---- (3) deposits into the slot ring ------------------------------------------------
-        if (active) sm.S[t & (M_NSLOT - 1)][tc + M_H][tb + M_H] = pn;
-        if (ldLook) sm.S[(t + M_LOOK) & (M_NSLOT - 1)][tc + M_H][tb + M_H] = la;
-        if (hdep) sm.S[hh & (M_NSLOT - 1)][htc + M_H][htb + M_H] = hv;
-        // ---- (4) slide the register window --------------------------------------------------
-        w0 = w1; w1 = w2; w2 = pn; w3 = w4; w4 = w5; w5 = w6; w6 = la;
-        // ---- (5) publish progress every CHUNK steps -----------------------------------------
+        // ---- (3) deposits into the slot ring (each value to slot h&7 and its double) ----------
+        if (active) { double *d = Sown + (t & (M_NSLOT - 1)); d[0] = pn; d[M_NSLOT] = pn; }
+        if (ldLook) { double *d = Sown + ((t + M_LOOK) & (M_NSLOT - 1)); d[0] = la; d[M_NSLOT] = la; }
+#pragma unroll
+        for (int r = 0; r < CFG::HR; ++r)
+            if (hdep[r]) { double *d = hS[r] + (hh[r] & (M_NSLOT - 1)); d[0] = hv[r]; d[M_NSLOT] = hv[r]; }
+        // ---- (4) publish progress every CHUNK steps -----------------------------------------
+        // (all threads' stores -> CTA barrier -> one thread's gpu-scope release: cumulative, so the
+        // whole tile's stores of this chunk are visible to whoever acquires the flag)
         const bool pub = (t >= 0) && ((t % M_CHUNK) == M_CHUNK - 1);
-        if (pub) p_fence();
+#if defined(LSF_EXP_NOSYNC)          // timing experiment only (results are wrong): no CTA barrier per step
+        __syncwarp();
+#else
         p_sync();
-        if (pub && tid == 0) p_st_release(mine, ebase + M_BIAS + t);
+#endif
+        if (pub && tid == 0) { p_fence(); p_st_release(mine, ebase + M_BIAS + t); }
     }
     // ---- tile done: final publish + deterministic block reduction of the RMS partial --------
-    p_fence();
     sm.red[tid] = acc;
     p_sync();
-    if (tid == 0) p_st_release(mine, ebase + M_BIAS + M_FIN);
-    for (int wdt = M_THREADS / 2; wdt > 0; wdt >>= 1) {
+    if (tid == 0) { p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN); }
+    for (int wdt = THREADS / 2; wdt > 0; wdt >>= 1) {
         if (tid < wdt) sm.red[tid] = sm.red[tid] + sm.red[tid + wdt];
         p_sync();
     }
     if (tid == 0) p.partial[J + p.ntb * K] = sm.red[0];
+#if defined(LSF_EXP_TIMING)
+    if (tid == 0 && p.dbg) {
+        long long t1; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *d = p.dbg + 6 * (long long)(J + p.ntb * K);
+        d[0] = dbg_t0; d[1] = t1; d[2] = dbg_wait; d[3] = clock64() - dbg_c0; d[4] = smid; d[5] = blockIdx.x;
+    }
+#endif
     p_sync();
 }
 
 // Persistent CTA: take tickets until the tile list is exhausted.
-template <class AR>
-LSF_DEV void march_cta(const MarchParams &p, MarchSmem &sm, const int tid)
+template <class AR, bool FA, bool FB, bool FC, class CFG>
+LSF_DEV void march_cta(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
 {
     if (p.ctrl->done) return;
     for (;;) {
@@ -250,7 +331,24 @@ LSF_DEV void march_cta(const MarchParams &p, MarchSmem &sm, const int tid)
         p_sync();
         if (tk >= p.ntiles) break;
         const int jk = p.order[tk];
-        march_tile<AR>(p, sm, tid, jk & 0xffff, jk >> 16);
+        march_tile<AR, FA, FB, FC, CFG>(p, sm, tid, jk & 0xffff, jk >> 16);
+    }
+}
+
+// Run-time orientation -> compile-time orientation.
+template <class AR, class CFG>
+LSF_DEV void march_cta_any(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
+{
+    const int o = (p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0);
+    switch (o) {
+    case 0: march_cta<AR, false, false, false, CFG>(p, sm, tid); break;
+    case 1: march_cta<AR, true, false, false, CFG>(p, sm, tid); break;
+    case 2: march_cta<AR, false, true, false, CFG>(p, sm, tid); break;
+    case 3: march_cta<AR, true, true, false, CFG>(p, sm, tid); break;
+    case 4: march_cta<AR, false, false, true, CFG>(p, sm, tid); break;
+    case 5: march_cta<AR, true, false, true, CFG>(p, sm, tid); break;
+    case 6: march_cta<AR, false, true, true, CFG>(p, sm, tid); break;
+    default: march_cta<AR, true, true, true, CFG>(p, sm, tid); break;
     }
 }
 

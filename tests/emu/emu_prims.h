@@ -13,6 +13,8 @@ inline void p_stcg(double *p, double v) { *(volatile double *)p = v; }
 inline void p_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned p_ticket(unsigned *ctr) { return __atomic_fetch_add(ctr, 1u, __ATOMIC_SEQ_CST); }
 inline long long p_ld_acquire(const long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline long long p_ld_relaxed(const long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void p_fence_acquire() { __atomic_thread_fence(__ATOMIC_ACQ_REL); }
 inline void p_st_release(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void p_sleep() { sched_yield(); }
 }  // namespace lsf

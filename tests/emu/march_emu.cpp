@@ -12,14 +12,17 @@
 namespace lsf { thread_local EmuCta *emu_cta = nullptr; }
 using namespace lsf;
 
-struct ThreadArg { const MarchParams *p; MarchSmem *sm; EmuCta *cta; int tid; int arith; };
+typedef MarchCfgDefault CFG;
+typedef MarchSmem<CFG> Smem;
+constexpr int M_THREADS = CFG::THREADS;
+struct ThreadArg { const MarchParams *p; Smem *sm; EmuCta *cta; int tid; int arith; };
 
 static void *thread_main(void *v)
 {
     ThreadArg *a = (ThreadArg *)v;
     emu_cta = a->cta;
-    if (a->arith == 1) march_cta<ExactArith>(*a->p, *a->sm, a->tid);
-    else march_cta<FastArith>(*a->p, *a->sm, a->tid);
+    if (a->arith == 1) march_cta_any<ExactArith, CFG>(*a->p, *a->sm, a->tid);
+    else march_cta_any<FastArith, CFG>(*a->p, *a->sm, a->tid);
     return nullptr;
 }
 
@@ -31,7 +34,7 @@ extern "C" double emu_march_sweep(double *phi, const double *phiS, int nx, int n
     MarchParams p;
     memset(&p, 0, sizeof(p));
     const long long sx = nx + 1, sxy = sx * (ny + 1);
-    march_orient(p, nx, ny, nz, sx, sxy, raster);
+    march_orient<CFG>(p, nx, ny, nz, sx, sxy, raster);
     p.phi = phi; p.phiS = phiS;
     p.cc.dx = dx; p.cc.inv_dx = 1. / dx; p.cc.k12 = 1. / (12. * dx); p.cc.dx2 = dx * dx; p.cc.h = h;
     std::vector<double> partial(p.ntiles, 0.);
@@ -43,7 +46,7 @@ extern "C" double emu_march_sweep(double *phi, const double *phiS, int nx, int n
     p.partial = partial.data(); p.order = order.data(); p.progress = progress.data();
     p.ticket = &ticket; p.ctrl = &ctrl; p.epoch = 1;
     if (ncta > p.ntiles) ncta = p.ntiles;
-    std::vector<MarchSmem> sm(ncta);
+    std::vector<Smem> sm(ncta);
     std::vector<EmuCta> ctas(ncta);
     std::vector<ThreadArg> args((size_t)ncta * M_THREADS);
     std::vector<pthread_t> th((size_t)ncta * M_THREADS);
