@@ -38,6 +38,8 @@ SWEEPS_PER_STEP = 8
 METRIC = "WENO5 reinit Gcell-updates/s"
 UNIT = "Gcell-updates/s"
 BYTES_PER_UPDATE = 24.0          # fp64: read phi + read phiS + write phi
+FP64_PER_UPDATE = 307            # FP64-pipe warp instructions per cell update of the FAST sweep kernel (ncu source page)
+FP64_PIPE_PEAK = 148 * 64 * 1.965e9   # lane-ops/s
 
 
 # ----------------------------------------------------------------------------------- helpers
@@ -181,7 +183,7 @@ def run_gpu(args):
         build.build()
     L = _lib.lib()
     _lib.check(L.lsf_init(local))
-    _lib.check(L.lsf_set_arith(_lib.ARITH_EXACT if args.arith == "exact" else _lib.ARITH_FAST))
+    _lib.check(L.lsf_set_arith({"exact": _lib.ARITH_EXACT, "fast": _lib.ARITH_FAST, "auto": _lib.ARITH_AUTO}[args.arith]))
     _lib.check(L.lsf_set_sched(_lib.SCHED_PLANE if args.sched == "plane" else _lib.SCHED_MARCH))
     L.lsf_set_profile(1)
 
@@ -230,6 +232,21 @@ def run_gpu(args):
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop()
+
+    # ---- companion measurements on the same resident grid (not part of `value`): min/max flow ----
+    mm = None
+    if args.minmax_iters > 0:
+        rc, n_mm, hist_mm = G.minMaxFlow(3, DX, 0.01 * g["dxx"], tol=0.0)          # warm-up
+        barrier()
+        rc, n_mm, hist_mm = G.minMaxFlow(args.minmax_iters, DX, 0.01 * g["dxx"], tol=0.0)
+        mm_ms, mm_launches = _lib.last_timing()
+        npts_all = (nx + 1) * (ny + 1) * (nz + 1)
+        mm_rate = npts_all * n_mm / (mm_ms * 1e-3) / 1e9
+        mm = {"metric": "min/max flow Gpoint-iterations/s (all grid points per iteration)", "value": mm_rate,
+              "iterations": n_mm, "ms_per_iteration": mm_ms / max(n_mm, 1), "launches": mm_launches,
+              "roofline": {"bound": "hbm", "bytes_per_point": 16.0, "achieved": 16.0 * mm_rate,
+                           "peak": measured_peak()[0], "unit": "GB/s", "frac": 16.0 * mm_rate / measured_peak()[0]},
+              "last_rms": float(hist_mm[-1]) if len(hist_mm) else None}
 
     # ---- e2e: the host-buffer drop-in call, pinned host memory, H2D + compute + D2H timed ------
     e2e = None
@@ -282,7 +299,7 @@ def run_gpu(args):
                                        f"{n}x{n}x{n} fp64 grid per GPU, reinit-only, one step = {SWEEPS_PER_STEP} Gauss-Seidel "
                                        "raster sweeps (+BC+RMS each)",
                            "grid_per_gpu": list(shape_pts), "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX, "h": h,
-                           "arith": args.arith, "sched": args.sched,
+                           "arith": args.arith, "arith_used": "exact" if L.lsf_last_arith() == _lib.ARITH_EXACT else "fast", "sched": args.sched,
                            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak)",
                            "l2": "inputs larger than L2 (%.1f GB per field)" % (8e-9 * n ** 3),
                            "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
@@ -291,11 +308,19 @@ def run_gpu(args):
                              "frac": achieved / peak if achieved else None, "traffic": None,
                              "kernel": "k_reinit_march" if args.sched == "march" else "k_reinit_plane",
                              "launch_ms": launch_ms, "peak_source": peak_src,
+                             "fp64_pipe_frac": (FP64_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3)) / FP64_PIPE_PEAK if launch_ms > 0 else None,
+                             "fp64_pipe_note": "second roof: %d FP64-pipe instructions per cell update (SASS) vs %.1f T lane-ops/s "
+                                               "(148 SM x 64 lanes x 1.965 GHz; micro-benchmarked 18.4 T, profiles/r1_fp64_pipe_ubench.txt)"
+                                               % (FP64_PER_UPDATE, FP64_PIPE_PEAK / 1e12),
                              "note": "fp64 WENO5 is FP64-pipe bound (SURVEY.md fact 4); see DESIGN.md"},
                 "cpu_baseline": cpu,
                 "e2e": ({"value": world * cells_per_step / e2e_s_max / 1e9, "unit": UNIT,
                          "h2d_bytes_per_step": e2e["bytes"], "d2h_bytes_per_step": e2e["bytes"],
                          "api": "lsf_reinit (host-buffer drop-in)"} if e2e else None),
+                "minmax_flow": mm,
+                "sign_search": {"ms": sign_ms, "points": int(np.prod([g["box"][1] - g["box"][0] + 1, g["box"][3] - g["box"][2] + 1,
+                                                                      g["box"][5] - g["box"][4] + 1])),
+                                "triangles": int(len(surfElem))},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -309,9 +334,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=1024, help="grid points per axis per GPU")
-    ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--arith", default="auto", choices=["auto", "fast", "exact"])
     ap.add_argument("--sched", default="march", choices=["march", "plane"])
     ap.add_argument("--ref-slab", type=int, default=32, help="z thickness of the CPU sample slab")
+    ap.add_argument("--minmax-iters", type=int, default=16, help="min/max iterations of the companion measurement (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -30,10 +30,10 @@ PRIVATE
 
 PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched
 PUBLIC :: signSearch_b200, reinit_b200, narrowBand_b200, minMaxFlow_b200
-PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT
+PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT, LSF_ARITH_AUTO
 
 INTEGER(c_int), PARAMETER :: LSF_OK = 0, LSF_NAN = 1
-INTEGER(c_int), PARAMETER :: LSF_ARITH_FAST = 0, LSF_ARITH_EXACT = 1
+INTEGER(c_int), PARAMETER :: LSF_ARITH_FAST = 0, LSF_ARITH_EXACT = 1, LSF_ARITH_AUTO = 2
 
 INTERFACE
 

@@ -38,8 +38,11 @@ extern "C" {
                                          reference would read phi(-1,..) (set3d.f90:402-403) */
 
 /* arithmetic of the WENO5 cell update */
-#define LSF_ARITH_FAST 0  /* FMA + reciprocal-reduced form, <= 1e-10 of the reference (default) */
+#define LSF_ARITH_FAST 0  /* FMA + reciprocal-reduced form; <= 1e-10 of the reference on well-conditioned data */
 #define LSF_ARITH_EXACT 1 /* the reference's operation order, IEEE div/sqrt, no FMA: bit-identical */
+#define LSF_ARITH_AUTO 2  /* (default) FAST with an on-the-fly conditioning guard; if any cell update is
+                             ill-conditioned (flat extremum of phi next to the interface -- where the reference
+                             itself produces its 0/0 NaN, subs.f90:169) the call restarts in EXACT */
 /* schedule of the in-place Gauss-Seidel sweeps (both are exact re-orderings) */
 #define LSF_SCHED_MARCH 0 /* skewed x-marching column tiles, one launch per sweep (default) */
 #define LSF_SCHED_PLANE 1 /* one launch per global hyperplane; simple cross-check path */
@@ -51,6 +54,7 @@ int lsf_init(int device);          /* device < 0: use $LOCAL_RANK, else 0 */
 int lsf_finalize(void);
 const char *lsf_last_error(void);
 int lsf_set_arith(int arith);      /* LSF_ARITH_*  */
+int lsf_last_arith(void);          /* arithmetic the most recent lsf_*reinit call finished in (FAST or EXACT) */
 int lsf_set_sched(int sched);      /* LSF_SCHED_*  */
 /* Timing of the kernels of the most recent lsf_*reinit / lsf_*minmax / lsf_*sign_init call,
  * CUDA events on the library's own stream: total ms, number of kernel launches. */

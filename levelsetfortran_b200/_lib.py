@@ -18,7 +18,7 @@ c_int_p = C.POINTER(C.c_int)
 
 LSF_OK, LSF_NAN = 0, 1
 LSF_ERR_CUDA, LSF_ERR_ARG, LSF_ERR_BAND_ON_BOUNDARY = -1, -2, -3
-ARITH_FAST, ARITH_EXACT = 0, 1
+ARITH_FAST, ARITH_EXACT, ARITH_AUTO = 0, 1, 2
 SCHED_MARCH, SCHED_PLANE = 0, 1
 
 # every symbol include/lsf_b200.h declares: name -> (restype, argtypes)
@@ -28,6 +28,7 @@ SYMBOLS = {
     "lsf_finalize": (_I, []),
     "lsf_last_error": (C.c_char_p, []),
     "lsf_set_arith": (_I, [_I]),
+    "lsf_last_arith": (_I, []),
     "lsf_set_sched": (_I, [_I]),
     "lsf_last_timing": (_I, [c_double_p, c_int_p]),
     "lsf_set_profile": (_I, [_I]),

@@ -59,27 +59,22 @@ static int read_ctrl(Grid *g, Ctrl *h)
 }
 
 // reinit, subs.f90:717-931.  d_gradPhi / d_gradPhiMag: optional device arrays.
-static int reinit_core(Grid *g, int iter, double dx, double h, double tol, double *d_gradPhi, double *d_gradPhiMag,
-                       int *n_exit, double *rms_hist)
+// One attempt in the arithmetic G.arith_run.  *guard_hit is set when a FAST attempt met an ill-conditioned
+// cell update (then phi is NOT valid and the caller restarts from phiS in EXACT).
+static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, double *d_gradPhi, double *d_gradPhiMag,
+                          int *n_exit, double *rms_hist, bool watch_guard, bool *guard_hit)
 {
-    if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "reinit: bad iter/dx");
-    if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "reinit: grid too small");
-    int rc = ensure_hist(g, iter + 1);
-    if (rc) return rc;
     const size_t bytes = sizeof(double) * (size_t)g->np;
-    LSF_CUDA(cudaMemcpyAsync(g->phiS, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:731
     LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
     CellConst cc;
     cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
     const bool want_grad = d_gradPhi || d_gradPhiMag;
     const bool march = (G.sched == LSF_SCHED_MARCH) && !want_grad;
-    if (!march) LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
+    int rc;
     if (march) { rc = march_prepare(g); if (rc) return rc; }
+    else LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
     const int check = march ? 8 : (g->np > 2000000 ? 1 : 8);
-    Timer tm;
-    tm.start();
-    Ctrl hc = {0, 0, 0, 0};
-    G.sweep_ms = 0.; G.n_sweeps = 0;
+    Ctrl hc = {0, 0, 0, 0, 0};
     static cudaEvent_t pev[16][2];
     static bool pev_init = false;
     if (G.profile && !pev_init) {
@@ -87,6 +82,7 @@ static int reinit_core(Grid *g, int iter, double dx, double h, double tol, doubl
         pev_init = true;
     }
     int npend = 0;
+    *guard_hit = false;
     for (int n = 0; n <= iter; ++n) {                                   // subs.f90:735
         const int raster = n % 8 + 1;                                   // subs.f90:740,855
         if (G.profile) cudaEventRecord(pev[npend][0], G.stream);
@@ -111,43 +107,61 @@ static int reinit_core(Grid *g, int iter, double dx, double h, double tol, doubl
                 if (cudaEventElapsedTime(&ms, pev[q][0], pev[q][1]) == cudaSuccess) { G.sweep_ms += ms; G.n_sweeps++; }
             }
             npend = 0;
+            if (watch_guard && hc.guard) { *guard_hit = true; return LSF_OK; }
             if (hc.done) break;
         }
     }
-    rc = tm.stop();
-    if (rc) return rc;
     LSF_CUDA(cudaGetLastError());
     const int ne = hc.done ? hc.n_exit : iter;
-    if (G.profile && G.n_sweeps > ne + 1) {   // sweeps enqueued after the exit were no-ops
-        G.n_sweeps = ne + 1;
-    }
+    if (G.profile && G.n_sweeps > ne + 1) G.n_sweeps = ne + 1;   // sweeps enqueued after the exit were no-ops
     if (n_exit) *n_exit = ne;
     if (rms_hist) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)(ne + 1), cudaMemcpyDeviceToHost));
     return hc.done ? hc.status : LSF_OK;
 }
 
-static int ensure_minmax_buffers(Grid *g)
+static int reinit_core(Grid *g, int iter, double dx, double h, double tol, double *d_gradPhi, double *d_gradPhiMag,
+                       int *n_exit, double *rms_hist)
 {
-    if (!g->lap) LSF_CUDA(cudaMalloc(&g->lap, sizeof(double) * (size_t)g->np));
+    if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "reinit: bad iter/dx");
+    if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "reinit: grid too small");
+    int rc = ensure_hist(g, iter + 1);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * (size_t)g->np;
+    LSF_CUDA(cudaMemcpyAsync(g->phiS, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:731
+    Timer tm;
+    tm.start();
+    G.sweep_ms = 0.; G.n_sweeps = 0;
+    G.arith_run = (G.arith == LSF_ARITH_EXACT) ? LSF_ARITH_EXACT : LSF_ARITH_FAST;
+    bool guard_hit = false;
+    int st = reinit_attempt(g, iter, dx, h, tol, d_gradPhi, d_gradPhiMag, n_exit, rms_hist, G.arith == LSF_ARITH_AUTO, &guard_hit);
+    if (st >= 0 && guard_hit) {
+        // LSF_ARITH_AUTO: an ill-conditioned update was met -> the FAST result cannot be trusted to 1e-10;
+        // start over from the frozen input (phiS still holds it) in the reference's exact arithmetic
+        LSF_CUDA(cudaMemcpyAsync(g->phi, g->phiS, bytes, cudaMemcpyDeviceToDevice, G.stream));
+        G.arith_run = LSF_ARITH_EXACT;
+        G.sweep_ms = 0.; G.n_sweeps = 0;
+        st = reinit_attempt(g, iter, dx, h, tol, d_gradPhi, d_gradPhiMag, n_exit, rms_hist, false, &guard_hit);
+    }
+    G.arith_last = G.arith_run;
+    rc = tm.stop();
+    if (rc) return rc;
+    return st;
+}
+
+static int ensure_minmax_buffers(Grid *g, bool want_lap)
+{
+    if (want_lap && !g->lap) LSF_CUDA(cudaMalloc(&g->lap, sizeof(double) * (size_t)g->np));
     if (!g->mask) LSF_CUDA(cudaMalloc(&g->mask, (size_t)g->np));
     return LSF_OK;
 }
 
 // The min/max loop, set3d.f90:394-462.  phiN must already equal phi (set3d.f90:377).
-static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool mask_given,
-                       int *n_exit, double *rms_hist, int *converged)
+// Plane schedule (cross-check): Jacobi Laplacian kernel + one launch per hyperplane, in place.
+static int minmax_core_plane(Grid *g, int iter, double dx, double h1, double tol, bool mask_given, Ctrl *hc_out)
 {
-    if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "minmax: bad iter/dx");
-    int rc = ensure_hist(g, iter + 1);
+    int rc = ensure_minmax_buffers(g, true);
     if (rc) return rc;
-    rc = ensure_minmax_buffers(g);
-    if (rc) return rc;
-    Ctrl init = {0, 0, 1, 0};
-    LSF_CUDA(cudaMemcpyAsync(g->ctrl, &init, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
-    LSF_CUDA(cudaStreamSynchronize(G.stream));
-    Timer tm;
-    tm.start();
-    Ctrl hc = init;
+    Ctrl hc = {0, 0, 1, 0, 0};
     const int check = g->np > 2000000 ? 1 : 8;
     for (int n = 1; n <= iter; ++n) {                                   // set3d.f90:394
         launch_minmax_iteration_plane(g, dx, h1, mask_given && n == 1); // :399-431 (+ narrowBand :460 of n-1)
@@ -160,14 +174,74 @@ static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool
             if (hc.done || hc.status < 0) break;
         }
     }
+    *hc_out = hc;
+    // on a tolerance EXIT the reference leaves phiN at the previous iterate; the guarded copy above did not
+    // run for the exiting iteration (done was already set), so phiN is right in every case
+    return LSF_OK;
+}
+
+// March schedule (production): one fused kernel per iteration, ping-pong between the phi and phiN buffers
+// (iteration n reads the buffer holding phi_{n-1} and writes phi_n into the other), so phiN = phi
+// (set3d.f90:454) is free and the RMS is the sum of the kernel's per-tile partials.
+static int minmax_core_march(Grid *g, int iter, double dx, double h1, double tol, bool mask_given, Ctrl *hc_out)
+{
+    int rc = mm_march_prepare(g);
+    if (rc) return rc;
+    Ctrl hc = {0, 0, 1, 0, 0};
+    if (iter >= 1) {
+        launch_mm_check_boundary(g, mask_given ? g->mask : nullptr, dx, !mask_given || iter >= 2);
+        rc = read_ctrl(g, &hc);
+        if (rc) return rc;
+        if (hc.status < 0) { *hc_out = hc; return LSF_OK; }
+    }
+    const int ntiles = march_ntiles(g);
+    double *buf[2] = {g->phi, g->phiN};                                 // buf[0] = phi_0, buf[1] = copy of it
+    for (int n = 1; n <= iter; ++n) {                                   // set3d.f90:394
+        const double *A = buf[(n - 1) & 1];
+        double *B = buf[n & 1];
+        launch_minmax_iteration_march(g, A, B, (mask_given && n == 1) ? g->mask : nullptr, dx, h1);   // :399-431
+        launch_finalize(g, ntiles, 1, tol);                             // :435-458
+        if (n % 8 == 0 || n == iter) {
+            rc = read_ctrl(g, &hc);
+            if (rc) return rc;
+            if (hc.done) break;
+        }
+    }
+    const int ne = hc.done ? hc.n_exit : iter;
+    // phi_ne lives in buf[ne & 1], phi_{ne-1} in the other buffer
+    g->phi = buf[ne & 1];
+    g->phiN = buf[(ne & 1) ^ 1];
+    *hc_out = hc;
+    return LSF_OK;
+}
+
+static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool mask_given,
+                       int *n_exit, double *rms_hist, int *converged)
+{
+    if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "minmax: bad iter/dx");
+    if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "minmax: grid too small");
+    int rc = ensure_hist(g, iter + 1);
+    if (rc) return rc;
+    Ctrl init = {0, 0, 1, 0, 0};
+    LSF_CUDA(cudaMemcpyAsync(g->ctrl, &init, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    Timer tm;
+    tm.start();
+    Ctrl hc = init;
+    if (G.sched == LSF_SCHED_MARCH) rc = minmax_core_march(g, iter, dx, h1, tol, mask_given, &hc);
+    else rc = minmax_core_plane(g, iter, dx, h1, tol, mask_given, &hc);
+    if (rc) return rc;
     rc = tm.stop();
     if (rc) return rc;
     LSF_CUDA(cudaGetLastError());
     if (hc.status == LSF_ERR_BAND_ON_BOUNDARY)
         return set_error(LSF_ERR_BAND_ON_BOUNDARY, "minmax: narrow band touches the grid boundary");
     const int ne = hc.done ? hc.n_exit : iter;
+    const bool conv = hc.done && hc.status == 0;
+    if (!conv && ne >= 1)      // the reference executed phiN = phi (set3d.f90:454) in the last iteration it ran
+        LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToDevice, G.stream));
     if (n_exit) *n_exit = ne;
-    if (converged) *converged = (hc.done && hc.status == 0) ? 1 : 0;
+    if (converged) *converged = conv ? 1 : 0;
     if (rms_hist && ne >= 1) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)ne, cudaMemcpyDeviceToHost));
     return hc.done ? hc.status : LSF_OK;
 }
@@ -228,7 +302,8 @@ int lsf_init(int device)
     LSF_CUDA(cudaEventCreate(&G.ev0));
     LSF_CUDA(cudaEventCreate(&G.ev1));
     // environment overrides for hosts that cannot easily call the setters (e.g. a Fortran driver)
-    if (const char *a = getenv("LSF_ARITH")) G.arith = (strcmp(a, "exact") == 0) ? LSF_ARITH_EXACT : LSF_ARITH_FAST;
+    if (const char *a = getenv("LSF_ARITH"))
+        G.arith = (strcmp(a, "exact") == 0) ? LSF_ARITH_EXACT : (strcmp(a, "fast") == 0) ? LSF_ARITH_FAST : LSF_ARITH_AUTO;
     if (const char *s = getenv("LSF_SCHED")) G.sched = (strcmp(s, "plane") == 0) ? LSF_SCHED_PLANE : LSF_SCHED_MARCH;
     G.inited = true;
     return LSF_OK;
@@ -249,10 +324,13 @@ const char *lsf_last_error(void) { return G.err; }
 
 int lsf_set_arith(int arith)
 {
-    if (arith != LSF_ARITH_FAST && arith != LSF_ARITH_EXACT) return set_error(LSF_ERR_ARG, "bad arith %d", arith);
+    if (arith != LSF_ARITH_FAST && arith != LSF_ARITH_EXACT && arith != LSF_ARITH_AUTO)
+        return set_error(LSF_ERR_ARG, "bad arith %d", arith);
     G.arith = arith;
     return LSF_OK;
 }
+
+int lsf_last_arith(void) { return G.arith_last; }
 
 int lsf_set_sched(int sched)
 {
@@ -464,7 +542,7 @@ int lsf_minmax(double *phi, double *phiN, int32_t *phiNB, int32_t *phiSB, int nx
     do {
         if ((rc = lsf_grid_upload(g, phi))) break;
         if (cudaMemcpy(g->phiN, phiN, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { rc = set_error(LSF_ERR_CUDA, "minmax: H2D phiN"); break; }
-        if ((rc = ensure_minmax_buffers(g))) break;
+        if ((rc = ensure_minmax_buffers(g, false))) break;
         if (cudaMalloc(&d_nb, sizeof(int32_t) * (size_t)g->np) != cudaSuccess ||
             cudaMemcpy(d_nb, phiNB, sizeof(int32_t) * (size_t)g->np, cudaMemcpyHostToDevice) != cudaSuccess) {
             rc = set_error(LSF_ERR_CUDA, "minmax: H2D phiNB"); break;

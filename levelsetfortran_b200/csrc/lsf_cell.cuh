@@ -130,8 +130,9 @@ struct ExactArith {
     }
 
     // phiSign (subs.f90:169) + Euler update (subs.f90:749-750)
-    static LSF_HD double update(double phic, double phiS, double gM, const CellConst &cc)
+    static LSF_HD double update(double phic, double phiS, double gM, const CellConst &cc, bool &sens)
     {
+        sens = false;
         const double sgn = div(phiS, sqr(add(mul(phiS, phiS), mul(mul(cc.dx, cc.dx), gM))));
         const double k1 = mul(sgn, sub(1., gM));
         return add(phic, mul(cc.h, k1));
@@ -243,11 +244,24 @@ struct FastArith {
         return sqrt(g[0] + g[1] + g[2]);
     }
 
-    static LSF_HD double update(double phic, double phiS, double gM, const CellConst &cc)
+    // `sens` flags an ill-conditioned update: d(sgn (1-gM))/d(gM) contains  k1 * dx^2 / (2 D)  with
+    // D = phiS^2 + dx^2 gM, which blows up where the sign source AND the Godunov gradient vanish (a flat
+    // extremum of phi next to the interface, e.g. an under-resolved gap).  There, 1e-13 differences between
+    // this arithmetic and the reference's are amplified beyond the 1e-10 contract -- and the reference's own
+    // 0/0 NaN (subs.f90:169, phiS == 0 and gM == 0 exactly) hinges on the last bit of gM.  LSF_ARITH_AUTO
+    // reruns the call in EXACT arithmetic when any cell raises the flag.
+    static LSF_HD double update(double phic, double phiS, double gM, const CellConst &cc, bool &sens)
     {
         // phiS / sqrt(phiS^2 + dx^2 gM): 0 * rsqrt(0) = NaN reproduces the reference's 0/0 (subs.f90:169)
-        const double sgn = phiS * rsq(fma(phiS, phiS, cc.dx2 * gM));
-        return fma(cc.h, sgn * (1.0 - gM), phic);
+        const double r = rsq(fma(phiS, phiS, cc.dx2 * gM));
+        const double sgn = phiS * r;
+        const double k1 = sgn * (1.0 - gM);
+        const double amp = dabs(k1) * (cc.dx2 * (r * r));           // = 2 * |k1| dx^2 / (2 D)
+        // threshold calibrated on the reference's two inputs (oracle run of every sweep): cube40 peaks at 400 in
+        // its first two sweeps and is < 7 after 25 (FAST ends 2e-14 from the reference); twoCube10 -- which the
+        // reference NaN-STOPs on -- shows 1.8e9 in sweep 0 and the zero-source/zero-gradient cell from sweep 94
+        sens = !(amp <= 2000.0) || (phiS == 0.0 && gM < 1.0e-6);     // NaN amp (D == 0) is flagged too
+        return fma(cc.h, k1, phic);
     }
 };
 
@@ -255,7 +269,7 @@ struct FastArith {
 // hi = high-order branch condition of subs.f90:506.  Returns the new phi; g[3]/gM as in weno.
 template <class AR>
 LSF_HD double reinit_cell(const double vx[7], const double vy[7], const double vz[7], double phiS, bool hi,
-                          const CellConst &cc, double g[3], double &gM)
+                          const CellConst &cc, double g[3], double &gM, bool &sens)
 {
     double a, b, c, d, e, f;
     if (hi) {
@@ -268,7 +282,7 @@ LSF_HD double reinit_cell(const double vx[7], const double vy[7], const double v
         AR::lo_dir(vz[2], vz[3], vz[4], cc, e, f);
     }
     gM = AR::godunov(vx[3], a, b, c, d, e, f, g);
-    return AR::update(vx[3], phiS, gM, cc);
+    return AR::update(vx[3], phiS, gM, cc, sens);
 }
 
 }  // namespace lsf

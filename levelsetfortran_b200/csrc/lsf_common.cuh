@@ -23,6 +23,7 @@ struct Ctrl {
     int status;   // 0 = EXIT on tolerance / still running, 1 = NaN, <0 = LSF_ERR_*
     int n;        // index of the iteration being executed (reinit: 0-based; min/max: 1-based)
     int n_exit;   // n at which the loop left
+    int guard;    // set by the FAST sweep kernels when a cell update was ill-conditioned (lsf_cell.cuh)
 };
 
 struct Dims {

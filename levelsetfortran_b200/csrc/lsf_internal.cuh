@@ -36,7 +36,9 @@ struct Global {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int arith = LSF_ARITH_FAST;
+    int arith = LSF_ARITH_AUTO;    // requested mode
+    int arith_run = LSF_ARITH_FAST; // arithmetic the kernels currently use (FAST or EXACT)
+    int arith_last = LSF_ARITH_FAST;
     int sched = LSF_SCHED_MARCH;
     int n_launch = 0;
     double last_ms = 0.;
@@ -75,5 +77,11 @@ void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_s
 int march_prepare(Grid *g);
 int march_ntiles(const Grid *g);
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc);
+const int *march_order();
+
+// lsf_mm_march.cu
+int mm_march_prepare(Grid *g);
+void launch_mm_check_boundary(Grid *g, const uint8_t *mask, double dx, bool check_abs);
+void launch_minmax_iteration_march(Grid *g, const double *A, double *B, const uint8_t *mask, double dx, double h1);
 
 }  // namespace lsf

@@ -16,7 +16,7 @@ template <class AR, bool WG>
 __global__ void __launch_bounds__(128)
 k_reinit_plane(double *__restrict__ phi, const double *__restrict__ phiS, Dims dm, int d0, int d1, int d2,
                int s, CellConst cc, double *__restrict__ gradPhi, double *__restrict__ gradPhiMag,
-               const Ctrl *__restrict__ ctrl)
+               Ctrl *__restrict__ ctrl)
 {
     if (ctrl->done) return;
     const int a = 1 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,7 +44,9 @@ k_reinit_plane(double *__restrict__ phi, const double *__restrict__ phiS, Dims d
         vz[2] = phi[q - dm.sxy]; vz[4] = phi[q + dm.sxy];
     }
     double g[3], gM;
-    const double pn = reinit_cell<AR>(vx, vy, vz, phiS[q], hi, cc, g, gM);
+    bool sens;
+    const double pn = reinit_cell<AR>(vx, vy, vz, phiS[q], hi, cc, g, gM, sens);
+    if (sens) ctrl->guard = 1;
     phi[q] = pn;
     if (WG) {
         const long long np = dm.sxy * (dm.nz + 1);
@@ -61,7 +63,7 @@ void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double 
     dim3 blk(128), grd((dm.nx - 1 + 127) / 128, dm.ny - 1);
     const bool wg = gradPhi || gradPhiMag;
     for (int s = 3; s <= (dm.nx - 1) + (dm.ny - 1) + (dm.nz - 1); ++s) {
-        if (G.arith == LSF_ARITH_EXACT) {
+        if (G.arith_run == LSF_ARITH_EXACT) {
             if (wg) k_reinit_plane<ExactArith, true><<<grd, blk, 0, G.stream>>>(g->phi, g->phiS, dm, d[0], d[1], d[2], s, cc, gradPhi, gradPhiMag, g->ctrl);
             else k_reinit_plane<ExactArith, false><<<grd, blk, 0, G.stream>>>(g->phi, g->phiS, dm, d[0], d[1], d[2], s, cc, nullptr, nullptr, g->ctrl);
         } else {
@@ -202,6 +204,10 @@ k_finalize(const double *__restrict__ partial, int npart, Ctrl *ctrl, double *__
            double denom, double tol)
 {
     if (ctrl->done) return;
+    if (ctrl->status < 0) {          // an error flagged by a kernel of this iteration ends the loop as it is
+        if (threadIdx.x == 0) { ctrl->done = 1; ctrl->n_exit = ctrl->n; }
+        return;
+    }
     __shared__ double sh[256];
     double acc = 0.;
     for (int q = threadIdx.x; q < npart; q += 256) acc = __dadd_rn(acc, partial[q]);

@@ -50,6 +50,8 @@ struct MarchHost {
 };
 static MarchHost MH;   // order table of the most recent grid shape
 
+const int *march_order() { return MH.d_order; }
+
 int march_ntiles(const Grid *g)
 {
     return ((g->dm.ny - 1 + CFG::TB - 1) / CFG::TB) * ((g->dm.nz - 1 + CFG::TC - 1) / CFG::TC);
@@ -106,7 +108,7 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
 #endif
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     const int ncta = p.ntiles < LSF_OCC * G.num_sms ? p.ntiles : LSF_OCC * G.num_sms;
-    MarchKernel kern = (G.arith == LSF_ARITH_EXACT) ? march_kernel<ExactArith>(p.fa, p.fb, p.fc)
+    MarchKernel kern = (G.arith_run == LSF_ARITH_EXACT) ? march_kernel<ExactArith>(p.fa, p.fb, p.fc)
                                                     : march_kernel<FastArith>(p.fa, p.fb, p.fc);
     kern<<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(p);
     G.n_launch++;

@@ -109,7 +109,7 @@ struct MarchParams {
     const int *order;              // ticket -> J | (K << 16)
     long long *progress;           // per tile (J + ntb*K)
     long long epoch;               // progress values are epoch*2^32 + step + BIAS
-    const Ctrl *ctrl;
+    Ctrl *ctrl;
     long long *dbg;                // timing experiments only (LSF_EXP_TIMING): 6 words per tile
 };
 
@@ -276,7 +276,9 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             vy[3] = vx[3]; vz[3] = vx[3];
             const bool hi = hiBC && (a >= p.lo_a) && (a <= p.hi_a);
             double g[3], gM;
-            pn = reinit_cell<AR>(vx, vy, vz, ps, hi, p.cc, g, gM);
+            bool sens;
+            pn = reinit_cell<AR>(vx, vy, vz, ps, hi, p.cc, g, gM, sens);
+            if (sens) p.ctrl->guard = 1;
             const double df = pn - vx[3];
             acc += df * df;
             p_stcg(pOut, pn);

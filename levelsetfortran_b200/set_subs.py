@@ -48,8 +48,17 @@ def _grid_array(a, nx, ny, nz, dtype, name, extra=()):
     return a
 
 
-def set_arith(exact: bool):
-    check(lib().lsf_set_arith(_lib.ARITH_EXACT if exact else _lib.ARITH_FAST))
+def set_arith(exact):
+    """True / "exact": bit-identical reference arithmetic; False / "fast": FMA + reciprocal-reduced form;
+    None / "auto" (library default): fast with a conditioning guard that falls back to exact."""
+    mode = {True: _lib.ARITH_EXACT, False: _lib.ARITH_FAST, None: _lib.ARITH_AUTO,
+            "exact": _lib.ARITH_EXACT, "fast": _lib.ARITH_FAST, "auto": _lib.ARITH_AUTO}[exact]
+    check(lib().lsf_set_arith(mode))
+
+
+def last_arith() -> str:
+    """Arithmetic the most recent reinit call finished in."""
+    return "exact" if lib().lsf_last_arith() == _lib.ARITH_EXACT else "fast"
 
 
 def set_sched(plane: bool):

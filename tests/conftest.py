@@ -47,3 +47,18 @@ def synth_field(shape, seed=0, noise=0.01, dx=0.05):
     r = np.sqrt((x - nxp / 2.1) ** 2 + (y - nyp / 1.9) ** 2 + (z - nzp / 2.2) ** 2) * dx - 0.3 * min(shape) * dx
     s = r / np.sqrt(r * r + dx * dx)
     return np.asfortranarray(s + noise * rng.standard_normal(shape))
+
+
+def dist_field(shape, seed=0, noise=0.002, dx=0.05):
+    """A noisy signed-distance-like field of an off-centre sphere: wide narrow band for min/max tests."""
+    rng = np.random.default_rng(seed)
+    nxp, nyp, nzp = shape
+    x, y, z = np.meshgrid(np.arange(nxp), np.arange(nyp), np.arange(nzp), indexing="ij")
+    r = np.sqrt((x - nxp / 2.1) ** 2 + (y - nyp / 1.9) ** 2 + (z - nzp / 2.2) ** 2) * dx - 0.3 * min(shape) * dx
+    # keep the band off the grid boundary (the reference would read out of bounds there)
+    r = np.maximum(r, -10.0)
+    edge = np.ones(shape, dtype=bool)
+    edge[1:-1, 1:-1, 1:-1] = False
+    f = r + noise * rng.standard_normal(shape)
+    f[edge & (np.abs(f) < 5 * dx)] = 5 * dx
+    return np.asfortranarray(f)

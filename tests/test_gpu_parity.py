@@ -8,7 +8,7 @@ The EXACT arithmetic mode and the whole min/max path are additionally required t
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_mesh, synth_field
+from conftest import GOLDEN, dist_field, load_mesh, synth_field
 
 pytestmark = pytest.mark.gpu
 DX = 0.05
@@ -21,7 +21,7 @@ def S(lsf):
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from levelsetfortran_b200 import set_subs
     yield set_subs
-    set_subs.set_arith(False)
+    set_subs.set_arith(None)
     set_subs.set_sched(False)
 
 
@@ -114,34 +114,48 @@ def test_cube40_reinit_full_parity(S, exact):
 def test_twocube10_nan_stop_parity(S):
     """BASELINE config 2: the reference STOPs with a NaN RMS at n = 272.  The NaN is
     0/0 in phiSign (subs.f90:169) at a cell whose frozen sign source is exactly -0.0, in the sweep where
-    its Godunov gradient first evaluates to exactly 0 -- a bit-level coincidence, so the iteration is
-    pinned in the EXACT arithmetic mode (bit-identical to the reference); the default FAST mode is held
-    to the 1e-10 field bar up to the last finite iteration and must also end in the NaN STOP."""
+    its Godunov gradient first evaluates to exactly 0 -- a bit-level event.  EXACT arithmetic reproduces it
+    (and the field before it) bit for bit; the library default, AUTO, detects the ill-conditioned updates
+    with its guard and finishes in EXACT, so the drop-in call gives the same answer."""
     from levelsetfortran_b200 import ReferenceStop, stl
     X, E = load_mesh("twoCube10")
     g = stl.grid_from_surface(X, DX)
     gold = np.load(f"{GOLDEN}/twoCube10_fields.npz")
     h = 0.1 * g["dxx"]
-    for plane in (False, True):
-        _mode(S, True, plane)
+    for arith, plane in ((True, False), (True, True), (None, False)):
+        _mode(S, arith, plane)
         phi = np.asfortranarray(gold["sign"].copy())
         with pytest.raises(ReferenceStop) as e:
             S.reinit(phi, None, None, 261, 41, 41, 10000, DX, h)
+        assert S.last_arith() == "exact"
         assert e.value.n == 272 == int(gold["n_nan"][0])
         assert np.allclose(e.value.rms_hist[:272], gold["rms_reinit1"][:272], rtol=1e-9, atol=0)
         assert np.isnan(e.value.rms_hist[272])
         phi = np.asfortranarray(gold["sign"].copy())
         n, hist = S.reinit(phi, None, None, 261, 41, 41, 271, DX, h)
         assert n == 271 and np.array_equal(phi, gold["phi_n271"])
+    # explicit FAST: no guarantee on this ill-conditioned input beyond "it also ends in the NaN STOP"
     _mode(S, False, False)
-    phi = np.asfortranarray(gold["sign"].copy())
-    n, hist = S.reinit(phi, None, None, 261, 41, 41, 271, DX, h)
-    assert n == 271 and np.abs(phi - gold["phi_n271"]).max() <= TOL
-    assert np.allclose(hist, gold["rms_reinit1"][:272], rtol=1e-9, atol=0)
     phi = np.asfortranarray(gold["sign"].copy())
     with pytest.raises(ReferenceStop) as e:
         S.reinit(phi, None, None, 261, 41, 41, 10000, DX, h)
-    assert e.value.n >= 272
+    assert e.value.n >= 200 and S.last_arith() == "fast"
+    assert np.allclose(e.value.rms_hist[:100], gold["rms_reinit1"][:100], rtol=1e-6, atol=0)
+
+
+def test_auto_mode_stays_fast_on_well_conditioned_input(S):
+    """cube40 (BASELINE config 1) in the default AUTO mode: the guard does not fire, the call finishes in FAST
+    arithmetic, within 1e-10 of the reference and with the reference's iteration count."""
+    _mode(S, None, False)
+    from levelsetfortran_b200 import stl
+    X, E = load_mesh("cube40")
+    g = stl.grid_from_surface(X, DX)
+    gold = np.load(f"{GOLDEN}/cube40_fields.npz")
+    phi = np.asfortranarray(gold["sign"].copy())
+    n, hist = S.reinit(phi, None, None, 61, 61, 61, 10000, DX, 0.1 * g["dxx"])
+    assert n == 2154
+    assert np.abs(phi - gold["reinit1"]).max() <= TOL
+    assert S.last_arith() == "fast"
 
 
 # ------------------------------------------------------------------------------------ narrow band + min/max
@@ -172,20 +186,85 @@ def test_cube40_minmax_full_parity_bit_exact(S):
     assert np.array_equal(nb, gold["phiNB"].astype(np.int32)) and np.array_equal(sb, gold["phiSB"].astype(np.int32))
 
 
-def test_minmax_small_vs_oracle_iteration_limit(S, oracle):
-    shape = (30, 28, 26)
-    p0 = synth_field(shape, seed=11, noise=0.002)
+@pytest.mark.parametrize("plane", [False, True], ids=["march", "plane"])
+@pytest.mark.parametrize("shape", [(30, 28, 26), (45, 20, 37), (19, 50, 33), (6, 5, 7)])
+def test_minmax_small_vs_oracle_iteration_limit(S, oracle, shape, plane):
+    _mode(S, False, plane)
+    p0 = dist_field(shape, seed=11)
     a, b = p0.copy(order="F"), p0.copy(order="F")
     st, n, hist, nbo, sbo = oracle.minmax(a, 12, DX, 1.0e-4, tol=1e-30)
     assert st == 2 and n == 12
     phiN = b.copy(order="F")
     nb = np.zeros(shape, dtype=np.int32, order="F")
     sb = np.zeros(shape, dtype=np.int32, order="F")
-    S.narrowBand(29, 27, 25, DX, b, nb, sb)
-    n2, hist2 = S.minMaxFlow(b, phiN, nb, sb, 29, 27, 25, 12, DX, 1.0e-4, tol=1e-30)
+    nx, ny, nz = (q - 1 for q in shape)
+    S.narrowBand(nx, ny, nz, DX, b, nb, sb)
+    n2, hist2 = S.minMaxFlow(b, phiN, nb, sb, nx, ny, nz, 12, DX, 1.0e-4, tol=1e-30)
     assert n2 == 12 and np.array_equal(a, b) and np.array_equal(phiN, b)
     assert np.array_equal(nb, nbo) and np.array_equal(sb, sbo)
     assert np.allclose(hist, hist2, rtol=1e-12, atol=0)
+
+
+def test_minmax_given_mask_first_iteration(S, oracle):
+    """Iteration 1 uses the caller's phiNB (set3d.f90:360), later ones narrowBand of the iterate (:460)."""
+    import ctypes
+    shape = (28, 26, 24)
+    p0 = dist_field(shape, seed=14)
+    nx, ny, nz = (q - 1 for q in shape)
+    rng = np.random.default_rng(1)
+    nb0 = np.zeros(shape, dtype=np.int32, order="F")
+    nb0[2:-2, 2:-2, 2:-2] = rng.random((shape[0] - 4, shape[1] - 4, shape[2] - 4)) < 0.3
+    dp = ctypes.POINTER(ctypes.c_double)
+    for plane in (False, True):
+        _mode(S, False, plane)
+        a, an, nba, sba = p0.copy(order="F"), p0.copy(order="F"), nb0.copy(order="F"), np.zeros(shape, dtype=np.int32, order="F")
+        hist = np.zeros(3)
+        ne = ctypes.c_int(0)
+        st = oracle.lib().orc_minmax(a.ctypes.data_as(dp), an.ctypes.data_as(dp), nba.ctypes.data_as(oracle.c_i32_p),
+                                     sba.ctypes.data_as(oracle.c_i32_p), nx, ny, nz, 3, DX, 1.0e-4, 1e-30,
+                                     ctypes.byref(ne), hist.ctypes.data_as(dp))
+        assert st == 2
+        b, bn, nbb, sbb = p0.copy(order="F"), p0.copy(order="F"), nb0.copy(order="F"), np.zeros(shape, dtype=np.int32, order="F")
+        n2, hist2 = S.minMaxFlow(b, bn, nbb, sbb, nx, ny, nz, 3, DX, 1.0e-4, tol=1e-30)
+        assert n2 == 3 and np.array_equal(a, b) and np.array_equal(an, bn)
+        assert np.array_equal(nba, nbb) and np.array_equal(sba, sbb)
+        assert np.allclose(hist, hist2, rtol=1e-12, atol=0)
+
+
+def test_minmax_band_on_boundary_is_an_error(S):
+    from levelsetfortran_b200._lib import LsfError, LSF_ERR_BAND_ON_BOUNDARY
+    shape = (12, 12, 12)
+    phi = np.full(shape, 0.01, order="F")              # every cell, including the boundary, is in the band
+    nb = np.ones(shape, dtype=np.int32, order="F")
+    sb = np.ones(shape, dtype=np.int32, order="F")
+    for plane in (False, True):
+        _mode(S, False, plane)
+        with pytest.raises(LsfError) as e:
+            S.minMaxFlow(phi.copy(order="F"), phi.copy(order="F"), nb, sb, 11, 11, 11, 2, DX, 1.0e-4)
+        assert e.value.code == LSF_ERR_BAND_ON_BOUNDARY
+    _mode(S, False, False)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 128), (96, 160, 200)])
+def test_minmax_march_equals_plane_schedule_at_size(S, shape):
+    """Size-independent property: the fused march kernel and the per-hyperplane cross-check path are both
+    exact re-orderings of the reference loop, so they agree bit for bit (phi, phiN, masks, RMS history)."""
+    p0 = dist_field(shape, seed=15)
+    nx, ny, nz = (q - 1 for q in shape)
+    out = []
+    for plane in (True, False):
+        _mode(S, False, plane)
+        b, bn = p0.copy(order="F"), p0.copy(order="F")
+        nb = np.zeros(shape, dtype=np.int32, order="F")
+        sb = np.zeros(shape, dtype=np.int32, order="F")
+        S.narrowBand(nx, ny, nz, DX, b, nb, sb)
+        n, hist = S.minMaxFlow(b, bn, nb, sb, nx, ny, nz, 5, DX, 1.0e-4, tol=1e-30)
+        out.append((n, b, bn, nb, sb, hist))
+    assert out[0][0] == out[1][0] == 5
+    for q in range(1, 5):
+        assert np.array_equal(out[0][q], out[1][q])
+    assert np.allclose(out[0][5], out[1][5], rtol=1e-12, atol=0)
+    assert not np.array_equal(out[0][1], p0)
 
 
 # ------------------------------------------------------------------------------------ device-resident pipeline + larger sizes

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, synth_field
+from conftest import ROOT, dist_field, synth_field
 
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 dp = C.POINTER(C.c_double)
@@ -23,6 +23,8 @@ def emu():
     L = C.CDLL(so)
     L.emu_march_sweep.restype = C.c_double
     L.emu_march_sweep.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.emu_mm_iteration.restype = C.c_double
+    L.emu_mm_iteration.argtypes = [dp, dp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     return L
 
 
@@ -42,3 +44,47 @@ def test_march_schedule_is_an_exact_reordering(emu, oracle, shape, ncta):
         assert abs(s - ref) <= 1e-12 * max(ref, 1e-300)
         emu.emu_march_sweep(f.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, r, 0.05, 0.0014, 0, ncta)
         assert np.abs(a - f).max() < 1e-13, f"raster {r}: fast arithmetic drifted"
+
+
+@pytest.mark.parametrize("shape,ncta", [((22, 21, 23), 1), ((24, 36, 22), 4), ((40, 38, 36), 9), ((12, 50, 20), 6)])
+def test_minmax_march_iteration_is_bit_exact(emu, oracle, shape, ncta):
+    """The fused min/max iteration kernel (lsf_mm_march.cuh: out-of-place march, old/new rings) against
+    the oracle's literal two-pass loop (set3d.f90:399-431), several iterations, ping-pong buffers."""
+    p0 = dist_field(shape, seed=3)
+    nx, ny, nz = (s - 1 for s in shape)
+    a = p0.copy(order="F")
+    st, n, hist, nbo, sbo = oracle.minmax(a, 6, 0.05, 1.0e-4, tol=1e-30)
+    assert st == 2 and n == 6
+    buf = [p0.copy(order="F"), p0.copy(order="F")]
+    sums = []
+    for it in range(1, 7):
+        A, B = buf[(it - 1) & 1], buf[it & 1]
+        s = emu.emu_mm_iteration(A.ctypes.data_as(dp), B.ctypes.data_as(dp), None, nx, ny, nz, 0.05, 1.0e-4, ncta)
+        sums.append(np.sqrt(s / (nx * ny * nz)))
+    assert np.array_equal(buf[0], a)                     # 6 iterations: result back in buffer 0
+    assert np.allclose(sums, hist, rtol=1e-12, atol=0)
+    assert (np.abs(p0) < 4.1 * 0.05).sum() > 100         # the band was not empty
+
+
+def test_minmax_march_given_mask(emu, oracle):
+    """Iteration 1 honours a caller-provided band mask (phiNB, set3d.f90:360) instead of the abs test."""
+    shape = (24, 22, 20)
+    p0 = dist_field(shape, seed=4)
+    nx, ny, nz = (s - 1 for s in shape)
+    rng = np.random.default_rng(0)
+    nb = np.zeros(shape, dtype=np.int32, order="F")
+    nb[2:-2, 2:-2, 2:-2] = (rng.random((shape[0] - 4, shape[1] - 4, shape[2] - 4)) < 0.3)
+    a = p0.copy(order="F")
+    phiN = a.copy(order="F")
+    sb = np.zeros(shape, dtype=np.int32, order="F")
+    import ctypes
+    from oracle import oracle as O
+    hist = np.zeros(1)
+    ne = ctypes.c_int(0)
+    O.lib().orc_minmax(a.ctypes.data_as(dp), phiN.ctypes.data_as(dp), nb.copy(order="F").ctypes.data_as(O.c_i32_p),
+                       sb.ctypes.data_as(O.c_i32_p), nx, ny, nz, 1, 0.05, 1.0e-4, 1e-30, ctypes.byref(ne),
+                       hist.ctypes.data_as(dp))
+    A, B = p0.copy(order="F"), p0.copy(order="F")
+    m8 = np.asfortranarray(nb.astype(np.uint8))
+    emu.emu_mm_iteration(A.ctypes.data_as(dp), B.ctypes.data_as(dp), m8.ctypes.data, nx, ny, nz, 0.05, 1.0e-4, 3)
+    assert np.array_equal(B, a)
