@@ -178,7 +178,7 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from levelsetfortran_b200 import DeviceGrid, _lib, build, stl
+    from levelsetfortran_b200 import DeviceGrid, ShardedGrid, _lib, build, stl
     if not os.path.exists(_lib.LIB_PATH):
         build.build()
     L = _lib.lib()
@@ -189,15 +189,21 @@ def run_gpu(args):
 
     n = args.grid
     shape_pts = (n, n, n)                                      # per GPU (weak scaling)
-    tris = stl.torus_cube_config(shape_pts, DX)
+    # N > 1: BASELINE config 5, ONE grid of n x n x (n*N) points cut into z-slabs, one per GPU
+    tris = stl.torus_cube_config((n, n, n * world), DX)
     surfX, surfElem = stl.dedup_nodes(tris)
     g = stl.grid_from_surface(surfX, DX)
     nx, ny, nz = g["nx"], g["ny"], g["nz"]
-    assert (nx + 1, ny + 1, nz + 1) == shape_pts
+    assert (nx + 1, ny + 1, nz + 1) == (n, n, n * world)
     h = 0.1 * g["dxx"]                                         # CFL = .1, set3d.f90:304-305
-    cells_per_step = (nx - 1) * (ny - 1) * (nz - 1) * SWEEPS_PER_STEP
+    cells_per_step = (nx - 1) * (ny - 1) * (nz - 1) * SWEEPS_PER_STEP     # whole job
 
-    G = DeviceGrid(nx, ny, nz)
+    if world > 1:
+        G = ShardedGrid(nx, ny, nz)
+        k_upd = min(G.k1 - 1, nz - 1) - max(G.k0, 1) + 1      # planes this rank's sweeps update
+    else:
+        G = DeviceGrid(nx, ny, nz)
+        k_upd = nz - 1
     G.fill(1.0)
     t0 = time.perf_counter()
     G.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
@@ -235,7 +241,7 @@ def run_gpu(args):
 
     # ---- companion measurements on the same resident grid (not part of `value`): min/max flow ----
     mm = None
-    if args.minmax_iters > 0:
+    if args.minmax_iters > 0 and world == 1:
         rc, n_mm, hist_mm = G.minMaxFlow(3, DX, 0.01 * g["dxx"], tol=0.0)          # warm-up
         barrier()
         rc, n_mm, hist_mm = G.minMaxFlow(args.minmax_iters, DX, 0.01 * g["dxx"], tol=0.0)
@@ -251,17 +257,23 @@ def run_gpu(args):
     # ---- e2e: the host-buffer drop-in call, pinned host memory, H2D + compute + D2H timed ------
     e2e = None
     if not args.no_e2e:
-        npts = (nx + 1) * (ny + 1) * (nz + 1)
+        npts = (nx + 1) * (ny + 1) * ((G.k1 - G.k0) if world > 1 else (nz + 1))     # this rank's owned points
         host = torch.empty(npts, dtype=torch.float64, pin_memory=True)
         G.download_ptr(host.data_ptr())                        # current phi as the e2e input
         hist_buf = np.zeros(SWEEPS_PER_STEP)
         import ctypes as C
         n_exit = C.c_int(0)
-        def e2e_step():
-            rc = L.lsf_reinit(C.cast(host.data_ptr(), _lib.c_double_p), None, None, nx, ny, nz, SWEEPS_PER_STEP - 1,
-                              DX, h, C.byref(n_exit), hist_buf.ctypes.data_as(_lib.c_double_p))
-            _lib.check(rc)
-        G.close()                                              # free the resident grid: lsf_reinit allocates its own
+        if world == 1:
+            def e2e_step():
+                rc = L.lsf_reinit(C.cast(host.data_ptr(), _lib.c_double_p), None, None, nx, ny, nz, SWEEPS_PER_STEP - 1,
+                                  DX, h, C.byref(n_exit), hist_buf.ctypes.data_as(_lib.c_double_p))
+                _lib.check(rc)
+            G.close()                                          # free the resident grid: lsf_reinit allocates its own
+        else:
+            def e2e_step():                                    # sharded: every rank moves its own slab (pinned host <-> its GPU)
+                G.upload_ptr(host.data_ptr())
+                step()
+                G.download_ptr(host.data_ptr())
         e2e_step()                                             # warm-up
         barrier()
         t0 = time.perf_counter()
@@ -271,6 +283,8 @@ def run_gpu(args):
         barrier()
         e2e_s = (time.perf_counter() - t0) / k_e2e
         e2e = {"e2e_s": e2e_s, "bytes": npts * 8}
+        if world > 1:
+            G.close()
     else:
         G.close()
 
@@ -281,10 +295,10 @@ def run_gpu(args):
     dev_ms_max, wall_ms_max, e2e_s_max = (float(v) for v in t.cpu())
 
     if rank == 0:
-        value = world * cells_per_step * args.steps / (dev_ms_max * 1e-3) / 1e9
+        value = cells_per_step * args.steps / (dev_ms_max * 1e-3) / 1e9
         peak, peak_src = measured_peak()
         launch_ms = sweep_ms / max(n_sweeps, 1)
-        cells_per_launch = (nx - 1) * (ny - 1) * (nz - 1)
+        cells_per_launch = (nx - 1) * (ny - 1) * k_upd          # rank 0's sweep kernel
         achieved = BYTES_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
         cpu = None
         if not args.no_cpu:
@@ -295,12 +309,15 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"BASELINE config 4/5: synthetic torus+cube STL ({len(surfElem)} triangles) on a "
-                                       f"{n}x{n}x{n} fp64 grid per GPU, reinit-only, one step = {SWEEPS_PER_STEP} Gauss-Seidel "
-                                       "raster sweeps (+BC+RMS each)",
+                "config": {"workload": f"BASELINE config {'4' if world == 1 else '5'}: synthetic torus+cube STL ({len(surfElem)} triangles) on "
+                                       f"ONE {n}x{n}x{n * world} fp64 grid ({n}^3 points per GPU), reinit-only, one step = "
+                                       f"{SWEEPS_PER_STEP} Gauss-Seidel raster sweeps (+BC+RMS each)",
+                           "global_grid": [n, n, n * world],
                            "grid_per_gpu": list(shape_pts), "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX, "h": h,
                            "arith": args.arith, "arith_used": "exact" if L.lsf_last_arith() == _lib.ARITH_EXACT else "fast", "sched": args.sched,
-                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak)",
+                           "parallelism": "single GPU" if world == 1 else
+                           f"{world} z-slabs, Gauss-Seidel pipeline along k: streaming halo + ghost-plane exchange + RMS reduction "
+                           "as peer stores over NVLink from inside the kernels (bit-identical to 1 GPU)",
                            "l2": "inputs larger than L2 (%.1f GB per field)" % (8e-9 * n ** 3),
                            "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
                            "last_rms": float(hist[-1]) if hist is not None else None},
@@ -314,9 +331,10 @@ def run_gpu(args):
                                                % (FP64_PER_UPDATE, FP64_PIPE_PEAK / 1e12),
                              "note": "fp64 WENO5 is FP64-pipe bound (SURVEY.md fact 4); see DESIGN.md"},
                 "cpu_baseline": cpu,
-                "e2e": ({"value": world * cells_per_step / e2e_s_max / 1e9, "unit": UNIT,
-                         "h2d_bytes_per_step": e2e["bytes"], "d2h_bytes_per_step": e2e["bytes"],
-                         "api": "lsf_reinit (host-buffer drop-in)"} if e2e else None),
+                "e2e": ({"value": cells_per_step / e2e_s_max / 1e9, "unit": UNIT,
+                         "h2d_bytes_per_step": e2e["bytes"] * world, "d2h_bytes_per_step": e2e["bytes"] * world,
+                         "api": "lsf_reinit (host-buffer drop-in)" if world == 1 else
+                                "lsf_grid_upload + lsf_grid_reinit + lsf_grid_download on each rank's slab"} if e2e else None),
                 "minmax_flow": mm,
                 "sign_search": {"ms": sign_ms, "points": int(np.prod([g["box"][1] - g["box"][0] + 1, g["box"][3] - g["box"][2] + 1,
                                                                       g["box"][5] - g["box"][4] + 1])),

@@ -36,6 +36,8 @@ extern "C" {
 #define LSF_ERR_ARG (-2)
 #define LSF_ERR_BAND_ON_BOUNDARY (-3) /* a narrow-band cell lies on the grid boundary: the
                                          reference would read phi(-1,..) (set3d.f90:402-403) */
+#define LSF_ERR_TIMEOUT (-4)          /* sharded grid: a neighbouring rank stopped answering */
+#define LSF_IPC_HANDLE_BYTES 64       /* size of the opaque per-rank handle of lsf_sgrid_ipc_handle */
 
 /* arithmetic of the WENO5 cell update */
 #define LSF_ARITH_FAST 0  /* FMA + reciprocal-reduced form; <= 1e-10 of the reference on well-conditioned data */
@@ -111,6 +113,22 @@ int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol,
 int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *phiSB_host);
 int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol,
                     int *n_exit, double *rms_hist);
+
+/* ---- z-slab sharding over the GPUs of one node -----------------------------------
+ * The reference is serial ("Parallel version is in the works", README.md:17).  Here phi(0:nx,0:ny,0:nz) is
+ * cut along k -- the slowest index, so a slab is a contiguous range of the reference array -- into one
+ * slab per process/GPU.  A sharded grid is used through the same lsf_grid_* calls as a whole one
+ * (sign_init, reinit, narrowband, fill, upload, download): all ranks make the same calls in the same order
+ * (SPMD), host arrays hold the rank's OWNED planes k0..k1-1 only, n_exit / rms_hist are identical on all
+ * ranks, and the result is bit-identical to the single-GPU one (the in-place Gauss-Seidel sweeps run as a
+ * software pipeline along k: peer stores over NVLink from inside the sweep kernels, no collective on the
+ * data path).  Set-up: every rank creates its slab, obtains its handle, the host program all-gathers the
+ * handles (MPI_Allgather / torch.distributed.all_gather) and every rank attaches. */
+int lsf_slab_range(int nz, int nranks, int rank, int *k0, int *k1);   /* owned planes [k0, k1) of rank */
+int lsf_sgrid_create(lsf_grid **g, int nx, int ny, int nz, int rank, int nranks);   /* nz: GLOBAL extent */
+int lsf_sgrid_ipc_handle(lsf_grid *g, void *handle /* LSF_IPC_HANDLE_BYTES */);
+int lsf_sgrid_attach(lsf_grid *g, const void *handles /* nranks * LSF_IPC_HANDLE_BYTES, rank order */);
+int lsf_sgrid_sync_ghosts(lsf_grid *g);   /* refresh the ghost planes after writing phi through lsf_grid_device_ptr */
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,8 @@ c_i32_p = C.POINTER(C.c_int32)
 c_int_p = C.POINTER(C.c_int)
 
 LSF_OK, LSF_NAN = 0, 1
-LSF_ERR_CUDA, LSF_ERR_ARG, LSF_ERR_BAND_ON_BOUNDARY = -1, -2, -3
+LSF_ERR_CUDA, LSF_ERR_ARG, LSF_ERR_BAND_ON_BOUNDARY, LSF_ERR_TIMEOUT = -1, -2, -3, -4
+IPC_HANDLE_BYTES = 64
 ARITH_FAST, ARITH_EXACT, ARITH_AUTO = 0, 1, 2
 SCHED_MARCH, SCHED_PLANE = 0, 1
 
@@ -48,6 +49,11 @@ SYMBOLS = {
     "lsf_grid_reinit": (_I, [_V, _I, _D, _D, _D, c_int_p, c_double_p]),
     "lsf_grid_narrowband": (_I, [_V, _D, c_i32_p, c_i32_p]),
     "lsf_grid_minmax": (_I, [_V, _I, _D, _D, _D, c_int_p, c_double_p]),
+    "lsf_slab_range": (_I, [_I, _I, _I, c_int_p, c_int_p]),
+    "lsf_sgrid_create": (_I, [C.POINTER(_V), _I, _I, _I, _I, _I]),
+    "lsf_sgrid_ipc_handle": (_I, [_V, _V]),
+    "lsf_sgrid_attach": (_I, [_V, _V]),
+    "lsf_sgrid_sync_ghosts": (_I, [_V]),
 }
 
 _lib = None

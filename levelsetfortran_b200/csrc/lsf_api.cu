@@ -20,6 +20,9 @@ int set_error(int code, const char *fmt, ...)
     return code;
 }
 
+static size_t owned_off(const Grid *g) { return (size_t)g->sg.own_lo * (size_t)g->dm.sxy; }
+static size_t owned_elems(const Grid *g) { return (size_t)(g->sg.k1 - g->sg.k0) * (size_t)g->dm.sxy; }
+
 static int ensure_init()
 {
     if (G.inited) return LSF_OK;
@@ -70,7 +73,9 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
     cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
     const bool want_grad = d_gradPhi || d_gradPhiMag;
     const bool march = (G.sched == LSF_SCHED_MARCH) && !want_grad;
+    if (sharded(g) && !march) return set_error(LSF_ERR_ARG, "reinit: a sharded grid supports the march schedule without gradPhi outputs only");
     int rc;
+    slab_exchange(g, false);                                            // z-slabs: ghost planes = neighbours' current phi
     if (march) { rc = march_prepare(g); if (rc) return rc; }
     else LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
     const int check = march ? 8 : (g->np > 2000000 ? 1 : 8);
@@ -93,7 +98,8 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
             // RMS fused: interior sums come from the sweep (one per column tile), boundary sums from the
             // BC kernel; phiN (subs.f90:732,921) is never materialised on this path
             launch_reinit_bc_rms(g, dx, march_ntiles(g));               // subs.f90:858-897 + boundary part of :902-914
-            launch_finalize(g, march_ntiles(g) + BC_BLOCKS, 0, tol);    // subs.f90:914-926
+            slab_exchange(g, true);                                     // z-slabs: OLD-value snapshot for the next sweep
+            launch_finalize(g, march_ntiles(g) + BC_BLOCKS, 0, tol);    // subs.f90:914-926 (sum over all ranks)
         } else {
             launch_reinit_bc(g, dx);                                    // subs.f90:858-897
             launch_rms(g, true);                                        // subs.f90:902-914,921
@@ -124,7 +130,9 @@ static int reinit_core(Grid *g, int iter, double dx, double h, double tol, doubl
 {
     if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "reinit: bad iter/dx");
     if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "reinit: grid too small");
-    int rc = ensure_hist(g, iter + 1);
+    int rc = slab_check_attached(g);
+    if (rc) return rc;
+    rc = ensure_hist(g, iter + 1);
     if (rc) return rc;
     const size_t bytes = sizeof(double) * (size_t)g->np;
     LSF_CUDA(cudaMemcpyAsync(g->phiS, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:731
@@ -220,6 +228,7 @@ static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool
 {
     if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "minmax: bad iter/dx");
     if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "minmax: grid too small");
+    if (sharded(g)) return set_error(LSF_ERR_ARG, "minmax: sharded grids are not supported yet");
     int rc = ensure_hist(g, iter + 1);
     if (rc) return rc;
     Ctrl init = {0, 0, 1, 0, 0};
@@ -251,7 +260,8 @@ static int sign_core(Grid *g, const double xLo[3], double dx, const double *surf
 {
     const Dims &dm = g->dm;
     if (nNode < 1 || nElem < 1) return set_error(LSF_ERR_ARG, "sign_init: empty surface");
-    if (im < 0 || jm < 0 || km < 0 || ip > dm.nx || jp > dm.ny || kp > dm.nz || ip < im || jp < jm || kp < km)
+    { int rc0 = slab_check_attached(g); if (rc0) return rc0; }
+    if (im < 0 || jm < 0 || km < 0 || ip > dm.nx || jp > dm.ny || kp > g->sg.NZ || ip < im || jp < jm || kp < km)
         return set_error(LSF_ERR_ARG, "sign_init: sub-box outside the grid");
     for (long long q = 0; q < 3LL * nElem; ++q)
         if (surfElem[q] < 1 || surfElem[q] > nNode) return set_error(LSF_ERR_ARG, "sign_init: surfElem index out of range");
@@ -265,6 +275,7 @@ static int sign_core(Grid *g, const double xLo[3], double dx, const double *surf
     Timer tm;
     tm.start();
     launch_sign_init(g, xLo, dx, d_X, nNode, d_E, nElem, d_cen, im, ip, jm, jp, km, kp);
+    slab_exchange(g, false);
     int rc = tm.stop();
     cudaError_t e = cudaGetLastError();
     cudaFree(d_X); cudaFree(d_E); cudaFree(d_cen);
@@ -373,6 +384,7 @@ int lsf_grid_create(lsf_grid **out, int nx, int ny, int nz)
     g->dm.sx = (long long)nx + 1;
     g->dm.sxy = g->dm.sx * ((long long)ny + 1);
     g->np = g->dm.sxy * ((long long)nz + 1);
+    slab_geom(nz, 1, 0, g->sg);                                         // one slab: the whole grid
     const size_t bytes = sizeof(double) * (size_t)g->np;
     cudaError_t e;
     if ((e = cudaMalloc(&g->phi, bytes)) != cudaSuccess || (e = cudaMalloc(&g->phiS, bytes)) != cudaSuccess ||
@@ -390,7 +402,13 @@ int lsf_grid_destroy(lsf_grid *g)
 {
     if (!g) return LSF_OK;
     if (G.inited) cudaStreamSynchronize(G.stream);
-    cudaFree(g->phi); cudaFree(g->phiS); cudaFree(g->phiN); cudaFree(g->lap); cudaFree(g->mask);
+    if (g->shared_base) {                                               // sharded: phi/phiN live in the shared allocation
+        for (int r = 0; r < g->sg.nranks; ++r)
+            if (r != g->sg.rank && g->peer_base[r]) cudaIpcCloseMemHandle(g->peer_base[r]);
+        cudaFree(g->shared_base);
+        cudaFree(g->exch_counter);
+    } else { cudaFree(g->phi); cudaFree(g->phiN); }
+    cudaFree(g->phiS); cudaFree(g->lap); cudaFree(g->mask);
     cudaFree(g->partial); cudaFree(g->hist); cudaFree(g->ctrl);
     cudaFree(g->march_ticket); cudaFree(g->march_progress);
     free(g);
@@ -400,7 +418,7 @@ int lsf_grid_destroy(lsf_grid *g)
 int lsf_grid_fill(lsf_grid *g, double value)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
-    launch_fill(g, g->phi, value);
+    launch_fill(g, g->phi, value);                                      // ghost planes included: consistent on all ranks
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
 }
@@ -408,7 +426,11 @@ int lsf_grid_fill(lsf_grid *g, double value)
 int lsf_grid_upload(lsf_grid *g, const double *phi_host)
 {
     if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
-    LSF_CUDA(cudaMemcpyAsync(g->phi, phi_host, sizeof(double) * (size_t)g->np, cudaMemcpyHostToDevice, G.stream));
+    int rc = slab_check_attached(g);
+    if (rc) return rc;
+    // z-slab: the host array holds this rank's owned planes k0..k1-1 (a contiguous range of the global array)
+    LSF_CUDA(cudaMemcpyAsync(g->phi + owned_off(g), phi_host, sizeof(double) * owned_elems(g), cudaMemcpyHostToDevice, G.stream));
+    slab_exchange(g, false);
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
 }
@@ -416,7 +438,7 @@ int lsf_grid_upload(lsf_grid *g, const double *phi_host)
 int lsf_grid_download(lsf_grid *g, double *phi_host)
 {
     if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
-    LSF_CUDA(cudaMemcpyAsync(phi_host, g->phi, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToHost, G.stream));
+    LSF_CUDA(cudaMemcpyAsync(phi_host, g->phi + owned_off(g), sizeof(double) * owned_elems(g), cudaMemcpyDeviceToHost, G.stream));
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
 }
@@ -424,7 +446,7 @@ int lsf_grid_download(lsf_grid *g, double *phi_host)
 int lsf_grid_download_phiN(lsf_grid *g, double *phiN_host)
 {
     if (!g || !phiN_host) return set_error(LSF_ERR_ARG, "null argument");
-    LSF_CUDA(cudaMemcpyAsync(phiN_host, g->phiN, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToHost, G.stream));
+    LSF_CUDA(cudaMemcpyAsync(phiN_host, g->phiN + owned_off(g), sizeof(double) * owned_elems(g), cudaMemcpyDeviceToHost, G.stream));
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
 }
@@ -452,8 +474,9 @@ static int narrowband_to_host(Grid *g, const double *d_phi, double dx, int32_t *
     cudaError_t e = cudaMalloc(&d_sb, bytes);
     if (e != cudaSuccess) { cudaFree(d_nb); return set_error(LSF_ERR_CUDA, "narrowband: %s", cudaGetErrorString(e)); }
     launch_narrowband(g, d_phi, dx, d_nb, d_sb);
-    if (nb_host) cudaMemcpyAsync(nb_host, d_nb, bytes, cudaMemcpyDeviceToHost, G.stream);
-    if (sb_host) cudaMemcpyAsync(sb_host, d_sb, bytes, cudaMemcpyDeviceToHost, G.stream);
+    const size_t obytes = sizeof(int32_t) * owned_elems(g);
+    if (nb_host) cudaMemcpyAsync(nb_host, d_nb + owned_off(g), obytes, cudaMemcpyDeviceToHost, G.stream);
+    if (sb_host) cudaMemcpyAsync(sb_host, d_sb + owned_off(g), obytes, cudaMemcpyDeviceToHost, G.stream);
     e = cudaStreamSynchronize(G.stream);
     cudaFree(d_nb); cudaFree(d_sb);
     if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "narrowband: %s", cudaGetErrorString(e));

@@ -2,10 +2,11 @@
 #pragma once
 #include "../../include/lsf_b200.h"
 #include "lsf_common.cuh"
+#include "lsf_slab.cuh"
 
 struct lsf_grid {
-    lsf::Dims dm;
-    long long np;             // (nx+1)(ny+1)(nz+1)
+    lsf::Dims dm;             // LOCAL array extents (a z-slab: owned + ghost planes)
+    long long np;             // (nx+1)(ny+1)(nz+1) of the local array
     double *phi;              // the level set, reference layout
     double *phiS;             // frozen sign source of reinit (subs.f90:731)
     double *phiN;             // previous iterate for the RMS test (subs.f90:732,921; set3d.f90:377,454)
@@ -20,6 +21,16 @@ struct lsf_grid {
     long long *march_progress;    // per column-tile progress, epoch-encoded
     int march_tiles_cap;
     long long march_epoch;
+    // z-slab sharding (lsf_slab.cu); sg.nranks == 1: the whole grid lives on this GPU
+    lsf::SlabGeom sg;
+    void *shared_base;            // sharded: ONE peer-visible allocation [SlabSync | phi | phiN]
+    size_t shared_bytes;
+    lsf::SlabSync *sync;          // = shared_base
+    void *peer_base[lsf::SLAB_MAX_RANKS];   // the ranks' shared allocations mapped into this process (own entry = shared_base)
+    bool attached;
+    long long phase;              // number of ghost-plane exchanges so far (lockstep on all ranks)
+    long long sum_seq;            // number of cross-rank reductions so far
+    unsigned int *exch_counter;
 };
 
 namespace lsf {
@@ -72,6 +83,18 @@ void launch_fill(Grid *g, double *p, double v);
 void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode,
                       const int32_t *d_surfElem, int nElem, double *d_cen,
                       int im, int ip, int jm, int jp, int km, int kp);
+
+inline long long global_cells(const Grid *g) { return (long long)g->dm.nx * g->dm.ny * g->sg.NZ; }
+inline bool sharded(const Grid *g) { return g->sg.nranks > 1; }
+
+// lsf_slab.cu
+int slab_check_attached(Grid *g);
+void slab_exchange(Grid *g, bool in_loop);       // ghost-plane refresh (k_slab_exchange); no-op on one GPU
+void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol);
+template <class T> inline T *peer_ptr(const Grid *g, int rank, T *mine)
+{
+    return (T *)((char *)g->peer_base[rank] + ((char *)mine - (char *)g->shared_base));
+}
 
 // lsf_march.cu
 int march_prepare(Grid *g);

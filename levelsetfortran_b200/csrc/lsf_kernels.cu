@@ -117,26 +117,31 @@ void launch_reinit_bc(Grid *g, double dx)
 // (subs.f90:902-914) accumulated on the fly: the sweep never writes boundary points, so the value
 // found in phi IS phiN there.  Together with the per-tile sums of the sweep kernel this makes the
 // separate RMS pass and the phiN array unnecessary in reinit.  Per-block partials, fixed order.
+// z-slabs (lsf_slab.cuh): a rank visits the boundary points of its OWNED planes only -- the global k faces if
+// it holds them (hasLo / hasHi), and the i/j faces of its updated planes kA..kB; B, H and the clamp are
+// properties of the GLOBAL plane index k + kbase in 0..NZ.  One GPU: kA = 1, kB = nz-1, kbase = 0, NZ = nz.
 __global__ void __launch_bounds__(256)
 k_reinit_bc_rms(double *__restrict__ phi, Dims dm, double dx, double *__restrict__ partial,
-                const Ctrl *__restrict__ ctrl)
+                const Ctrl *__restrict__ ctrl, int kA, int kB, int kbase, int NZ, int hasLo, int hasHi)
 {
     if (ctrl->done) return;
     __shared__ double sh[256];
-    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzm = dm.nz - 1, nym = dm.ny - 1;
+    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzm = kB - kA + 1, nym = dm.ny - 1;
     const long long fk = nxp * nyp, fj = nxp * nzm, fi = nym * nzm;
-    const long long tot = 2 * (fk + fj + fi);
+    const long long nkf = (long long)(hasLo + hasHi) * fk;
+    const long long tot = nkf + 2 * (fj + fi);
     double acc = 0.;
     for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < tot; t0 += (long long)gridDim.x * blockDim.x) {
         long long t = t0;
         int i, j, k;
-        if (t < 2 * fk) { k = (t >= fk) ? dm.nz : 0; t %= fk; i = (int)(t % nxp); j = (int)(t / nxp); }
-        else if ((t -= 2 * fk) < 2 * fj) { j = (t >= fj) ? dm.ny : 0; t %= fj; i = (int)(t % nxp); k = 1 + (int)(t / nxp); }
-        else { t -= 2 * fj; i = (t >= fi) ? dm.nx : 0; t %= fi; j = 1 + (int)(t % nym); k = 1 + (int)(t / nym); }
-        const int B = (i == 0 || i == dm.nx) + (j == 0 || j == dm.ny) + (k == 0 || k == dm.nz);
-        const int H = (i == dm.nx) + (j == dm.ny) + (k == dm.nz);
+        if (t < nkf) { k = (t >= fk || !hasLo) ? NZ - kbase : -kbase; t %= fk; i = (int)(t % nxp); j = (int)(t / nxp); }
+        else if ((t -= nkf) < 2 * fj) { j = (t >= fj) ? dm.ny : 0; t %= fj; i = (int)(t % nxp); k = kA + (int)(t / nxp); }
+        else { t -= 2 * fj; i = (t >= fi) ? dm.nx : 0; t %= fi; j = 1 + (int)(t % nym); k = kA + (int)(t / nym); }
+        const int kg = k + kbase;
+        const int B = (i == 0 || i == dm.nx) + (j == 0 || j == dm.ny) + (kg == 0 || kg == NZ);
+        const int H = (i == dm.nx) + (j == dm.ny) + (kg == NZ);
         const int m = min(1 + H, B);
-        const int ci = min(max(i, 1), dm.nx - 1), cj = min(max(j, 1), dm.ny - 1), ck = min(max(k, 1), dm.nz - 1);
+        const int ci = min(max(i, 1), dm.nx - 1), cj = min(max(j, 1), dm.ny - 1), ck = min(max(kg, 1), NZ - 1) - kbase;
         double v = phi[ci + dm.sx * cj + dm.sxy * ck];
         for (int r = 0; r < m; ++r) v = __dadd_rn(v, dx);
         const long long q = i + dm.sx * j + dm.sxy * k;
@@ -155,7 +160,9 @@ k_reinit_bc_rms(double *__restrict__ phi, Dims dm, double dx, double *__restrict
 
 void launch_reinit_bc_rms(Grid *g, double dx, int partial_off)
 {
-    k_reinit_bc_rms<<<BC_BLOCKS, 256, 0, G.stream>>>(g->phi, g->dm, dx, g->partial + partial_off, g->ctrl);
+    const SlabGeom &sg = g->sg;
+    k_reinit_bc_rms<<<BC_BLOCKS, 256, 0, G.stream>>>(g->phi, g->dm, dx, g->partial + partial_off, g->ctrl, sg.kupd_lo, sg.kupd_hi,
+                                                     sg.kbase, sg.NZ, sg.k0 == 0, sg.k1 == sg.NZ + 1);
     G.n_launch++;
 }
 
@@ -229,6 +236,7 @@ k_finalize(const double *__restrict__ partial, int npart, Ctrl *ctrl, double *__
 
 void launch_finalize(Grid *g, int npart, int hist_off, double tol)
 {
+    if (sharded(g)) { launch_finalize_slab(g, npart, hist_off, tol); return; }
     const double denom = (double)((long long)g->dm.nx * g->dm.ny * g->dm.nz);
     k_finalize<<<1, 256, 0, G.stream>>>(g->partial, npart, g->ctrl, g->hist, hist_off, denom, tol);
     G.n_launch++;
@@ -393,7 +401,7 @@ constexpr int SIGN_TILE = 256;
 __global__ void __launch_bounds__(SIGN_TILE)
 k_sign_search(double *__restrict__ phi, Dims dm, double x0, double y0, double z0, double dx,
               const double *__restrict__ surfX, int nNode, const int32_t *__restrict__ surfElem, int nElem,
-              const double *__restrict__ cen, int im, int jm, int km, int ni, int nj, int nk)
+              const double *__restrict__ cen, int im, int jm, int km, int ni, int nj, int nk, int kbase)
 {
     __shared__ double sc[3][SIGN_TILE];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +445,7 @@ k_sign_search(double *__restrict__ phi, Dims dm, double x0, double y0, double z0
     const double pSz = __dsub_rn(__dmul_rn(A1, B2), __dmul_rn(B1, A2));
     const double pS = -__dadd_rn(__dadd_rn(__dmul_rn(pSx, C1), __dmul_rn(pSy, C2)), __dmul_rn(pSz, C3));
     const double den = __dsqrt_rn(__dadd_rn(__dmul_rn(pS, pS), __dmul_rn(__dmul_rn(dx, dx), 1.)));
-    phi[i + dm.sx * j + dm.sxy * k] = __ddiv_rn(pS, den);
+    phi[i + dm.sx * j + dm.sxy * (k - kbase)] = __ddiv_rn(pS, den);   // k is the GLOBAL plane (z-slab: local plane k - kbase)
 }
 
 void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode,
@@ -446,10 +454,14 @@ void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_s
 {
     k_sign_centroids<<<(nElem + 255) / 256, 256, 0, G.stream>>>(d_surfX, nNode, d_surfElem, nElem, d_cen);
     G.n_launch++;
+    // z-slab: this rank searches the planes of the sub-box it owns (points are independent: no collective)
+    km = km > g->sg.k0 ? km : g->sg.k0;
+    kp = kp < g->sg.k1 - 1 ? kp : g->sg.k1 - 1;
+    if (kp < km) return;
     const int ni = ip - im + 1, nj = jp - jm + 1, nk = kp - km + 1;
     const long long npts = (long long)ni * nj * nk;
     k_sign_search<<<(unsigned)((npts + SIGN_TILE - 1) / SIGN_TILE), SIGN_TILE, 0, G.stream>>>(
-        g->phi, g->dm, xLo[0], xLo[1], xLo[2], dx, d_surfX, nNode, d_surfElem, nElem, d_cen, im, jm, km, ni, nj, nk);
+        g->phi, g->dm, xLo[0], xLo[1], xLo[2], dx, d_surfX, nNode, d_surfElem, nElem, d_cen, im, jm, km, ni, nj, nk, g->sg.kbase);
     G.n_launch++;
 }
 

@@ -46,7 +46,7 @@ static MarchKernel march_kernel(int fa, int fb, int fc)
 
 struct MarchHost {
     int *d_order = nullptr;
-    int ntb = 0, ntc = 0;
+    int ntb = 0, ntc = 0, m = 0;
 };
 static MarchHost MH;   // order table of the most recent grid shape
 
@@ -54,14 +54,31 @@ const int *march_order() { return MH.d_order; }
 
 int march_ntiles(const Grid *g)
 {
-    return ((g->dm.ny - 1 + CFG::TB - 1) / CFG::TB) * ((g->dm.nz - 1 + CFG::TC - 1) / CFG::TC);
+    return ((g->dm.ny - 1 + CFG::TB - 1) / CFG::TB) * ((g->sg.kupd_hi - g->sg.kupd_lo + 1 + CFG::TC - 1) / CFG::TC);
+}
+
+// Tilt of the ticket fronts (march_fill_order).  One GPU: anti-diagonals.  z-slabs: the downstream rank can
+// only start once this rank's sweep has crossed the slab in c, so the fronts are tilted as far as the
+// LAG between successive tiles of a column allows without starving the resident CTAs.
+static int march_order_tilt(const Grid *g)
+{
+    if (const char *e = getenv("LSF_ORDER_TILT")) { const int m = atoi(e); if (m >= 1 && m <= 64) return m; }
+    return sharded(g) ? 8 : 1;
+}
+
+static void march_orient_grid(MarchParams &p, const Grid *g, int raster)
+{
+    const SlabGeom &sg = g->sg;
+    march_orient<CFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, raster, sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ);
 }
 
 int march_prepare(Grid *g)
 {
     MarchParams p;
-    march_orient<CFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, 1);
+    march_orient_grid(p, g, 1);
     if (p.ntiles > 65536) return set_error(LSF_ERR_ARG, "march: more than 65536 column tiles");
+    if (sharded(g) && p.ntb > SLAB_MAX_NTB) return set_error(LSF_ERR_ARG, "march: more than %d tile columns on a sharded grid", SLAB_MAX_NTB);
+    const int tilt = march_order_tilt(g);
     if (!g->march_ticket) LSF_CUDA(cudaMalloc(&g->march_ticket, sizeof(unsigned)));
     if (g->march_tiles_cap < p.ntiles) {
         cudaFree(g->march_progress);
@@ -71,14 +88,14 @@ int march_prepare(Grid *g)
         g->march_tiles_cap = p.ntiles;
         g->march_epoch = 0;
     }
-    if (MH.ntb != p.ntb || MH.ntc != p.ntc || !MH.d_order) {
+    if (MH.ntb != p.ntb || MH.ntc != p.ntc || MH.m != tilt || !MH.d_order) {
         cudaFree(MH.d_order);
         MH.d_order = nullptr;
         std::vector<int> order(p.ntiles);
-        march_fill_order(p.ntb, p.ntc, order.data());
+        march_fill_order(p.ntb, p.ntc, order.data(), tilt);
         LSF_CUDA(cudaMalloc(&MH.d_order, sizeof(int) * (size_t)p.ntiles));
         LSF_CUDA(cudaMemcpy(MH.d_order, order.data(), sizeof(int) * (size_t)p.ntiles, cudaMemcpyHostToDevice));
-        MH.ntb = p.ntb; MH.ntc = p.ntc;
+        MH.ntb = p.ntb; MH.ntc = p.ntc; MH.m = tilt;
     }
     static bool attr_done = false;
     if (!attr_done) {
@@ -94,11 +111,29 @@ int march_prepare(Grid *g)
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
 {
     MarchParams p;
-    march_orient<CFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, raster);
+    march_orient_grid(p, g, raster);
     p.phi = g->phi; p.phiS = g->phiS; p.cc = cc;
     p.partial = g->partial; p.ticket = g->march_ticket; p.order = MH.d_order;
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
     p.dbg = nullptr;
+    p.in_progress = nullptr; p.push_delta = 0; p.push_progress = nullptr; p.halo_seq = nullptr;
+    p.halo_need[0] = p.halo_need[1] = 0;
+    if (sharded(g)) {
+        // the Gauss-Seidel pipeline along k (lsf_slab.cuh): upstream = the rank owning lower oriented c
+        const SlabGeom &sg = g->sg;
+        const int up = p.fc ? sg.rank + 1 : sg.rank - 1, down = p.fc ? sg.rank - 1 : sg.rank + 1;
+        if (up >= 0 && up < sg.nranks) p.in_progress = g->sync->in_progress;
+        if (down >= 0 && down < sg.nranks) {
+            SlabGeom dg;
+            slab_geom(sg.NZ, sg.nranks, down, dg);
+            double *dphi = peer_ptr(g, down, g->phi) + (long long)(sg.kbase - dg.kbase) * g->dm.sxy;
+            p.push_delta = dphi - g->phi;
+            p.push_progress = peer_ptr(g, down, g->sync)->in_progress;   // address computation only
+        }
+        p.halo_seq = g->sync->halo_seq;
+        if (sg.rank > 0) p.halo_need[0] = g->phase;
+        if (sg.rank < sg.nranks - 1) p.halo_need[1] = g->phase;
+    }
 #if defined(LSF_EXP_TIMING)
     {   // experiment: dump per-tile timing of this sweep to $LSF_TIMING_DUMP after the launch (synchronous)
         static long long *d_dbg = nullptr; static int cap = 0;

@@ -66,6 +66,21 @@ LSF_DEV long long p_ld_relaxed(const long long *p)
 }
 LSF_DEV void p_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 LSF_DEV void p_sleep() { __nanosleep(100); }
+// system-scope flavours for flags / data that cross NVLink (z-slab sharding, lsf_slab.cuh): a flag that a
+// PEER GPU writes into this GPU's memory is polled relaxed.sys and followed by one acq_rel.sys fence; data
+// pushed into a peer's ghost planes is an L1-bypassing store made visible by fence.sys + st.release.sys.
+LSF_DEV long long p_ld_relaxed_sys(const long long *p)
+{
+    long long v;
+    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+LSF_DEV void p_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+LSF_DEV void p_st_release_sys(long long *p, long long v)
+{
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+LSF_DEV void p_st_peer(double *p, double v) { __stcg(p, v); }
 }  // namespace lsf
 #endif
 
@@ -78,6 +93,8 @@ constexpr int M_CHUNK = 8;                   // publish / wait granularity in st
 constexpr int M_LOOK = 4;                    // old values are deposited this many steps ahead
 constexpr long long M_FIN = 1LL << 30;       // "tile finished" progress value
 constexpr long long M_BIAS = 1000;
+constexpr long long M_SPIN_LIMIT = 40000000; // polls before a flag wait gives up (tens of seconds): a lost peer must not hang the GPU
+constexpr int M_ERR_TIMEOUT = -4;            // = LSF_ERR_TIMEOUT (include/lsf_b200.h)
 
 // Tile geometry.  TB x TC rows per CTA (oriented b x c), one thread per row.
 template <int TB_, int TC_>
@@ -101,6 +118,8 @@ struct MarchParams {
     long long sa, sb, sc, off0;    // signed strides / origin of the sweep-oriented frame
     int fa, fb, fc;                // axis flipped?
     int lo_a, hi_a, lo_b, hi_b, lo_c, hi_c;   // high-order window (subs.f90:506) in oriented indices
+    int c_lo, c_hi, c_max;         // oriented c: planes c_lo..c_hi are updated, planes 0..c_max exist
+                                   // (whole grid on one GPU: 1, nz-1, nz; a z-slab with ghost planes: lsf_slab.cu)
     int ntb, ntc, ntiles;
     int tend;                      // last step index
     CellConst cc;
@@ -111,7 +130,34 @@ struct MarchParams {
     long long epoch;               // progress values are epoch*2^32 + step + BIAS
     Ctrl *ctrl;
     long long *dbg;                // timing experiments only (LSF_EXP_TIMING): 6 words per tile
+    // ---- z-slab sharding: the streaming halo of the Gauss-Seidel pipeline (all zero on a single GPU) ----
+    // The rank upstream in c (the one owning lower oriented c) pushes the NEW values of its last three
+    // updated planes straight into this rank's ghost planes (peer stores over NVLink) and publishes the
+    // progress of its last tile row into in_progress[J]; tiles (J,0) of this rank wait on that flag exactly
+    // as they would on a predecessor tile of their own GPU.  Ghost planes on the +c side hold the OLD values
+    // (snapshot exchanged between sweeps).
+    const long long *in_progress;  // [ntb], written by the upstream rank; null: no upstream rank
+    long long push_delta;          // (downstream rank's phi, shifted to this rank's indexing) - phi, in elements; 0: none
+    long long *push_progress;      // downstream rank's in_progress; null: no downstream rank
+    const long long *halo_seq;     // [2] counters the neighbours bump when they have refreshed this rank's ghost planes
+    long long halo_need[2];        // the sweep starts once halo_seq[s] >= halo_need[s] (0: no neighbour on side s)
 };
+
+// Spin until *flag >= need.  SYS: the flag is written by a peer GPU.  Gives up (and poisons the loop
+// status) after M_SPIN_LIMIT polls or as soon as another waiter has given up.
+template <bool SYS>
+LSF_DEV void wait_ge(const long long *flag, long long need, Ctrl *ctrl)
+{
+    long long spins = 0;
+    while ((SYS ? p_ld_relaxed_sys(flag) : p_ld_relaxed(flag)) < need) {
+        p_sleep();
+        if (((++spins) & 1023) == 0) {
+            if (*(volatile int *)&ctrl->status == M_ERR_TIMEOUT) return;
+            if (spins > M_SPIN_LIMIT) { *(volatile int *)&ctrl->status = M_ERR_TIMEOUT; return; }
+        }
+    }
+    if (SYS) p_fence_sys(); else p_fence_acquire();
+}
 
 template <class CFG>
 struct MarchSmem {
@@ -121,9 +167,15 @@ struct MarchSmem {
 };
 
 // Host helper shared with the emulator: fill the orientation-dependent fields.
+// nz = last plane index of the LOCAL array.  Whole grid on one GPU: kupd_lo = 1, kupd_hi = nz-1, kbase = 0,
+// NZ = nz.  z-slab: local planes kupd_lo..kupd_hi are updated, local plane k is global plane k + kbase of
+// a grid 0..NZ (the high-order window of subs.f90:506 is a property of the GLOBAL index).
 template <class CFG>
-inline void march_orient(MarchParams &p, int nx, int ny, int nz, long long sx, long long sxy, int raster)
+inline void march_orient(MarchParams &p, int nx, int ny, int nz, long long sx, long long sxy, int raster,
+                         int kupd_lo = 1, int kupd_hi = -1, int kbase = 0, int NZ = -1)
 {
+    if (kupd_hi < 0) kupd_hi = nz - 1;
+    if (NZ < 0) NZ = nz;
     int d[3];
     raster_dirs(raster, d);
     p.nx = nx; p.ny = ny; p.nz = nz;
@@ -135,22 +187,26 @@ inline void march_orient(MarchParams &p, int nx, int ny, int nz, long long sx, l
     // physical window i in [4, n-5]; flipped index a = n - i -> [5, n-4]
     p.lo_a = p.fa ? 5 : 4; p.hi_a = p.fa ? nx - 4 : nx - 5;
     p.lo_b = p.fb ? 5 : 4; p.hi_b = p.fb ? ny - 4 : ny - 5;
-    p.lo_c = p.fc ? 5 : 4; p.hi_c = p.fc ? nz - 4 : nz - 5;
+    const int wlo = 4 - kbase, whi = NZ - 5 - kbase;          // window in local plane indices
+    p.lo_c = p.fc ? nz - whi : wlo; p.hi_c = p.fc ? nz - wlo : whi;
+    p.c_lo = p.fc ? nz - kupd_hi : kupd_lo; p.c_hi = p.fc ? nz - kupd_lo : kupd_hi; p.c_max = nz;
     p.ntb = (ny - 1 + CFG::TB - 1) / CFG::TB;
-    p.ntc = (nz - 1 + CFG::TC - 1) / CFG::TC;
+    p.ntc = (p.c_hi - p.c_lo + 1 + CFG::TC - 1) / CFG::TC;
     p.ntiles = p.ntb * p.ntc;
     p.tend = (nx - 1) - 1 + (CFG::TB - 1) + (CFG::TC - 1) + M_H;
 }
 
-// ticket order: anti-diagonals of the tile grid (J+K ascending): topological, and all tiles of
-// a diagonal are mutually independent, so the resident CTAs are never blocked for long.
-inline void march_fill_order(int ntb, int ntc, int *order)
+// ticket order: fronts m*J + K ascending (m = 1: anti-diagonals of the tile grid).  Topological for
+// (J-1,K) -> (J,K) <- (J,K-1), and all tiles of a front are mutually independent, so the resident CTAs
+// are never blocked for long.  m > 1 tilts the front so that the sweep crosses the c extent of the grid
+// sooner: on a z-slab this is what lets the downstream rank start early (lsf_slab.cu).
+inline void march_fill_order(int ntb, int ntc, int *order, int m = 1)
 {
     int n = 0;
-    for (int s = 0; s <= ntb + ntc - 2; ++s)
-        for (int K = 0; K < ntc; ++K) {
-            const int J = s - K;
-            if (J < 0 || J >= ntb) continue;
+    for (int s = 0; s <= m * (ntb - 1) + ntc - 1; ++s)
+        for (int K = s % m; K < ntc && K <= s; K += m) {
+            const int J = (s - K) / m;
+            if (J >= ntb) continue;
             order[n++] = J | (K << 16);
         }
 }
@@ -161,9 +217,10 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
     constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP;
     constexpr int W = M_SLOTW;
     const int tb = tid % TB, tc = tid / TB;
-    const int b = 1 + J * TB + tb, c = 1 + K * TC + tc;
-    const bool rowValid = (b <= p.ny) && (c <= p.nz);
-    const bool compValid = (b <= p.ny - 1) && (c <= p.nz - 1);
+    const int b = 1 + J * TB + tb, c = p.c_lo + K * TC + tc;
+    const bool rowValid = (b <= p.ny) && (c <= p.c_max);
+    const bool compValid = (b <= p.ny - 1) && (c <= p.c_hi);
+    const bool pushRow = (p.push_delta != 0) && compValid && (c > p.c_hi - M_H);
     const bool hiBC = (b >= p.lo_b) && (b <= p.hi_b) && (c >= p.lo_c) && (c <= p.hi_c);
     const int sig = tb + tc + M_H;
     const long long rowoff = p.off0 + (long long)b * p.sb + (long long)c * p.sc;
@@ -194,8 +251,8 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
                 htb = idx;
                 if (side == 0) { htc = -m; hlow[r] = true; } else htc = TC - 1 + m;
             }
-            const int hb = 1 + J * TB + htb, hc = 1 + K * TC + htc;
-            hvalid[r] = (hb >= 0) && (hb <= p.ny) && (hc >= 0) && (hc <= p.nz);
+            const int hb = 1 + J * TB + htb, hc = p.c_lo + K * TC + htc;
+            hvalid[r] = (hb >= 0) && (hb <= p.ny) && (hc >= 0) && (hc <= p.c_max);
             hsig[r] = htb + htc + M_H;
             hS[r] = sm.S + (htc + M_H) * RP + (htb + M_H) * W;
             if (hvalid[r]) hrow[r] = p.phi + p.off0 + (long long)hb * p.sb + (long long)hc * p.sc;
@@ -204,8 +261,10 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
 
     const long long ebase = p.epoch << 32;
     const long long *predB = (J > 0) ? p.progress + ((J - 1) + p.ntb * K) : nullptr;
-    const long long *predC = (K > 0) ? p.progress + (J + p.ntb * (K - 1)) : nullptr;
+    const bool predCpeer = (K == 0) && p.in_progress;       // predecessor in c lives on the upstream rank
+    const long long *predC = (K > 0) ? p.progress + (J + p.ntb * (K - 1)) : (predCpeer ? p.in_progress + J : nullptr);
     long long *mine = p.progress + (J + p.ntb * K);
+    long long *minePeer = (K == p.ntc - 1 && p.push_progress) ? p.push_progress + J : nullptr;
 
     double acc = 0.;
 #if defined(LSF_EXP_TIMING)
@@ -231,8 +290,10 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             long long tw0 = 0;
             if (tid == 0) tw0 = clock64();
 #endif
-            if (tid == 0 && predB) { while (p_ld_relaxed(predB) < need_b) p_sleep(); p_fence_acquire(); }
-            if (tid == 32 % THREADS && predC) { while (p_ld_relaxed(predC) < need_c) p_sleep(); p_fence_acquire(); }
+            if (tid == 0 && predB) wait_ge<false>(predB, need_b, p.ctrl);
+            if (tid == 32 % THREADS && predC) {
+                if (predCpeer) wait_ge<true>(predC, need_c, p.ctrl); else wait_ge<false>(predC, need_c, p.ctrl);
+            }
             p_sync();
 #if defined(LSF_EXP_TIMING)
             if (tid == 0) dbg_wait += clock64() - tw0;
@@ -282,6 +343,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             const double df = pn - vx[3];
             acc += df * df;
             p_stcg(pOut, pn);
+            if (pushRow) p_st_peer(pOut + p.push_delta, pn);
         }
         // ---- (3) deposits into the slot ring (each value to slot h&7 and its double) ----------
         if (active) { double *d = Sown + (t & (M_NSLOT - 1)); d[0] = pn; d[M_NSLOT] = pn; }
@@ -298,12 +360,18 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
 #else
         p_sync();
 #endif
-        if (pub && tid == 0) { p_fence(); p_st_release(mine, ebase + M_BIAS + t); }
+        if (pub && tid == 0) {
+            p_fence(); p_st_release(mine, ebase + M_BIAS + t);
+            if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + t); }
+        }
     }
     // ---- tile done: final publish + deterministic block reduction of the RMS partial --------
     sm.red[tid] = acc;
     p_sync();
-    if (tid == 0) { p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN); }
+    if (tid == 0) {
+        p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN);
+        if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + M_FIN); }
+    }
     for (int wdt = THREADS / 2; wdt > 0; wdt >>= 1) {
         if (tid < wdt) sm.red[tid] = sm.red[tid] + sm.red[tid + wdt];
         p_sync();
@@ -326,6 +394,13 @@ template <class AR, bool FA, bool FB, bool FC, class CFG>
 LSF_DEV void march_cta(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
 {
     if (p.ctrl->done) return;
+    if (p.halo_seq) {          // z-slab: both neighbours must have refreshed this rank's ghost planes
+        if (tid == 0) {
+            if (p.halo_need[0]) wait_ge<true>(p.halo_seq + 0, p.halo_need[0], p.ctrl);
+            if (p.halo_need[1]) wait_ge<true>(p.halo_seq + 1, p.halo_need[1], p.ctrl);
+        }
+        p_sync();
+    }
     for (;;) {
         if (tid == 0) sm.tile = (int)p_ticket(p.ticket);
         p_sync();

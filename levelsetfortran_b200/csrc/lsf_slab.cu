@@ -1,0 +1,281 @@
+// lsf_slab.cu -- z-slab sharding over the GPUs of one node (design: lsf_slab.cuh): creation of the
+// peer-visible slab, CUDA-IPC attachment, the ghost-plane exchange kernel and the cross-rank reduction of
+// the RMS exit test.  All inter-GPU traffic is peer stores over NVLink issued by these kernels and by the
+// sweep kernels themselves (streaming halo); the host only exchanges the IPC handles once.
+#include <stdlib.h>
+#include <string.h>
+
+#include "lsf_internal.cuh"
+#include "lsf_march.cuh"
+
+namespace lsf {
+
+static_assert(sizeof(cudaIpcMemHandle_t) <= LSF_IPC_HANDLE_BYTES, "IPC handle does not fit the ABI's buffer");
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int slab_check_attached(Grid *g)
+{
+    if (sharded(g) && !g->attached) return set_error(LSF_ERR_ARG, "sharded grid used before lsf_sgrid_attach");
+    return LSF_OK;
+}
+
+// =====================================================================================
+// Ghost-plane exchange.  Side s = 0: low neighbour, 1: high neighbour.
+//  1. tell both neighbours "I have finished compute phase e" (they may now overwrite my ghost planes'
+//     SOURCE -- i.e. nothing -- and, more to the point, I may overwrite THEIR ghost planes only once they
+//     have said the same to me: their sweep may still be reading the old snapshot);
+//  2. wait for the neighbours' announcements;
+//  3. copy my 3 outermost owned planes on each side into the neighbour's ghost planes (peer stores);
+//  4. the last CTA to finish publishes halo_seq = e on both neighbours (fence.sys + release).
+// =====================================================================================
+struct ExchArgs {
+    SlabSync *self;
+    SlabSync *nbr[2];
+    const double *src[2];
+    double *dst[2];
+    long long n;               // doubles per side (3 planes)
+    long long phase;
+    unsigned *counter;
+    Ctrl *ctrl;
+    int in_loop;
+};
+
+__global__ void __launch_bounds__(256)
+k_slab_exchange(const ExchArgs a)
+{
+    if (a.in_loop && a.ctrl->done) return;
+    if (blockIdx.x == 0 && threadIdx.x < 2 && a.nbr[threadIdx.x]) {
+        p_fence_sys();
+        p_st_release_sys(&a.nbr[threadIdx.x]->phase_done[1 - threadIdx.x], a.phase);
+    }
+    if (threadIdx.x < 2 && a.nbr[threadIdx.x]) wait_ge<true>(&a.self->phase_done[threadIdx.x], a.phase, a.ctrl);
+    __syncthreads();
+    const long long n2 = a.n / 2;     // planes are even-sized or not: handle the tail below
+    for (int s = 0; s < 2; ++s) {
+        if (!a.nbr[s]) continue;
+        const double2 *src = reinterpret_cast<const double2 *>(a.src[s]);
+        double2 *dst = reinterpret_cast<double2 *>(a.dst[s]);
+        const bool vec = ((((uintptr_t)a.src[s]) | ((uintptr_t)a.dst[s])) & 15) == 0;
+        if (vec) {
+            for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += (long long)gridDim.x * blockDim.x)
+                __stcg(dst + q, __ldcg(src + q));
+            if (blockIdx.x == 0 && threadIdx.x == 0 && (a.n & 1)) __stcg(a.dst[s] + a.n - 1, __ldcg(a.src[s] + a.n - 1));
+        } else {
+            for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < a.n; q += (long long)gridDim.x * blockDim.x)
+                __stcg(a.dst[s] + q, __ldcg(a.src[s] + q));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p_fence_sys();
+        const unsigned prev = atomicAdd(a.counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *a.counter = 0;
+            p_fence_sys();
+            for (int s = 0; s < 2; ++s)
+                if (a.nbr[s]) p_st_release_sys(&a.nbr[s]->halo_seq[1 - s], a.phase);
+        }
+    }
+}
+
+void slab_exchange(Grid *g, bool in_loop)
+{
+    if (!sharded(g)) return;
+    const SlabGeom &sg = g->sg;
+    ExchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.self = g->sync;
+    a.n = (long long)SLAB_GHOST * g->dm.sxy;
+    a.phase = ++g->phase;
+    a.counter = g->exch_counter;
+    a.ctrl = g->ctrl;
+    a.in_loop = in_loop ? 1 : 0;
+    if (sg.rank > 0) {
+        SlabGeom ng;
+        slab_geom(sg.NZ, sg.nranks, sg.rank - 1, ng);
+        a.nbr[0] = peer_ptr(g, sg.rank - 1, g->sync);
+        a.src[0] = g->phi + (long long)sg.own_lo * g->dm.sxy;                                   // my global planes k0..k0+2
+        a.dst[0] = peer_ptr(g, sg.rank - 1, g->phi) + (long long)(sg.k0 - ng.kbase) * g->dm.sxy;   // = its upper ghost planes
+    }
+    if (sg.rank < sg.nranks - 1) {
+        SlabGeom ng;
+        slab_geom(sg.NZ, sg.nranks, sg.rank + 1, ng);
+        a.nbr[1] = peer_ptr(g, sg.rank + 1, g->sync);
+        a.src[1] = g->phi + (long long)(sg.own_hi - SLAB_GHOST + 1) * g->dm.sxy;                // my global planes k1-3..k1-1
+        a.dst[1] = peer_ptr(g, sg.rank + 1, g->phi) + (long long)(sg.k1 - SLAB_GHOST - ng.kbase) * g->dm.sxy;   // = its lower ghost planes
+    }
+    k_slab_exchange<<<2 * G.num_sms, 256, 0, G.stream>>>(a);
+    G.n_launch++;
+}
+
+// =====================================================================================
+// Loop control on a sharded grid: k_finalize (lsf_kernels.cu) with the sum taken over all ranks.
+// Every rank adds up its own partials in a fixed order, writes the result (and its status flags) into
+// every rank's SlabSync block, waits until all P contributions of this sequence number have arrived and
+// sums them in rank order: all ranks compute the bit-identical phiErr and take the same EXIT / NaN /
+// error decision without a host round trip or a collective library call.
+// =====================================================================================
+struct PeerSyncs { SlabSync *s[SLAB_MAX_RANKS]; };
+
+__global__ void __launch_bounds__(256)
+k_finalize_slab(const double *__restrict__ partial, int npart, Ctrl *ctrl, double *__restrict__ hist, int hist_off,
+                double denom, double tol, PeerSyncs peers, int rank, int nranks, long long seq)
+{
+    if (ctrl->done) return;
+    __shared__ double sh[256];
+    double acc = 0.;
+    for (int q = threadIdx.x; q < npart; q += 256) acc = __dadd_rn(acc, partial[q]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + w]);
+        __syncthreads();
+    }
+    const int par = (int)(seq & 1);
+    SlabSync *self = peers.s[rank];
+    if (threadIdx.x < nranks) {
+        const int st = *(volatile int *)&ctrl->status;
+        const int flags = (ctrl->guard ? 1 : 0) | (st == LSF_ERR_BAND_ON_BOUNDARY ? 2 : 0) | (st == LSF_ERR_TIMEOUT ? 4 : 0);
+        SlabSync *q = peers.s[threadIdx.x];
+        *(volatile double *)&q->rank_sum[par][rank] = sh[0];
+        *(volatile int *)&q->rank_flag[par][rank] = flags;
+        p_fence_sys();
+        p_st_release_sys(&q->sum_seq[rank], seq);
+        wait_ge<true>(&self->sum_seq[threadIdx.x], seq, ctrl);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.;
+        int flags = 0;
+        for (int r = 0; r < nranks; ++r) {
+            tot = __dadd_rn(tot, *(volatile double *)&self->rank_sum[par][r]);
+            flags |= *(volatile int *)&self->rank_flag[par][r];
+        }
+        if (*(volatile int *)&ctrl->status == LSF_ERR_TIMEOUT) flags |= 4;
+        const int n = ctrl->n;
+        if (flags & 1) ctrl->guard = 1;
+        if (flags & 6) {
+            ctrl->status = (flags & 4) ? LSF_ERR_TIMEOUT : LSF_ERR_BAND_ON_BOUNDARY;
+            ctrl->done = 1; ctrl->n_exit = n;
+            return;
+        }
+        const double err = sqrt(tot / denom);
+        hist[n - hist_off] = err;
+        if (err < tol) { ctrl->done = 1; ctrl->status = 0; ctrl->n_exit = n; }
+        else if (err != err) { ctrl->done = 1; ctrl->status = 1; ctrl->n_exit = n; }
+        ctrl->n = n + 1;
+    }
+}
+
+void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol)
+{
+    PeerSyncs ps;
+    memset(&ps, 0, sizeof(ps));
+    for (int r = 0; r < g->sg.nranks; ++r) ps.s[r] = (SlabSync *)g->peer_base[r];
+    const double denom = (double)global_cells(g);
+    k_finalize_slab<<<1, 256, 0, G.stream>>>(g->partial, npart, g->ctrl, g->hist, hist_off, denom, tol, ps, g->sg.rank,
+                                             g->sg.nranks, ++g->sum_seq);
+    G.n_launch++;
+}
+
+}  // namespace lsf
+
+using namespace lsf;
+
+// =============================================================================================
+extern "C" {
+
+int lsf_slab_range(int nz, int nranks, int rank, int *k0, int *k1)
+{
+    SlabGeom sg;
+    if (!slab_geom(nz, nranks, rank, sg))
+        return set_error(LSF_ERR_ARG, "slab_range: %d planes cannot be cut into %d slabs of >= %d planes", nz + 1, nranks, SLAB_MIN_PLANES);
+    if (k0) *k0 = sg.k0;
+    if (k1) *k1 = sg.k1;
+    return LSF_OK;
+}
+
+int lsf_sgrid_create(lsf_grid **out, int nx, int ny, int nz, int rank, int nranks)
+{
+    if (!out) return set_error(LSF_ERR_ARG, "null handle");
+    *out = nullptr;
+    if (nranks == 1) return lsf_grid_create(out, nx, ny, nz);
+    if (!G.inited) { int rc = lsf_init(-1); if (rc) return rc; }
+    if (nx < 2 || ny < 2) return set_error(LSF_ERR_ARG, "grid extents must be >= 2");
+    SlabGeom sg;
+    if (!slab_geom(nz, nranks, rank, sg))
+        return set_error(LSF_ERR_ARG, "sgrid_create: %d planes cannot be cut into %d slabs of >= %d planes (rank %d)", nz + 1, nranks,
+                         SLAB_MIN_PLANES, rank);
+    Grid *g = (Grid *)calloc(1, sizeof(Grid));
+    if (!g) return set_error(LSF_ERR_ARG, "out of host memory");
+    g->sg = sg;
+    g->dm.nx = nx; g->dm.ny = ny; g->dm.nz = sg.nzl;
+    g->dm.sx = (long long)nx + 1;
+    g->dm.sxy = g->dm.sx * ((long long)ny + 1);
+    g->np = g->dm.sxy * ((long long)sg.nzl + 1);
+    const size_t fbytes = align_up(sizeof(double) * (size_t)g->np, 256);
+    const size_t sbytes = align_up(sizeof(SlabSync), 256);
+    g->shared_bytes = sbytes + 2 * fbytes;
+    cudaError_t e;
+    if ((e = cudaMalloc(&g->shared_base, g->shared_bytes)) != cudaSuccess ||
+        (e = cudaMemset(g->shared_base, 0, sbytes)) != cudaSuccess ||
+        (e = cudaMalloc(&g->phiS, sizeof(double) * (size_t)g->np)) != cudaSuccess ||
+        (e = cudaMalloc(&g->partial, sizeof(double) * PARTIAL_CAP)) != cudaSuccess ||
+        (e = cudaMalloc(&g->ctrl, sizeof(Ctrl))) != cudaSuccess ||
+        (e = cudaMalloc(&g->exch_counter, sizeof(unsigned))) != cudaSuccess ||
+        (e = cudaMemset(g->exch_counter, 0, sizeof(unsigned))) != cudaSuccess ||
+        (e = cudaMemset(g->ctrl, 0, sizeof(Ctrl))) != cudaSuccess) {
+        lsf_grid_destroy(g);
+        return set_error(LSF_ERR_CUDA, "sgrid_create: %s", cudaGetErrorString(e));
+    }
+    g->sync = (SlabSync *)g->shared_base;
+    g->phi = (double *)((char *)g->shared_base + sbytes);
+    g->phiN = (double *)((char *)g->shared_base + sbytes + fbytes);
+    g->peer_base[rank] = g->shared_base;
+    *out = g;
+    return LSF_OK;
+}
+
+int lsf_sgrid_ipc_handle(lsf_grid *g, void *handle)
+{
+    if (!g || !handle) return set_error(LSF_ERR_ARG, "null argument");
+    if (!sharded(g)) return set_error(LSF_ERR_ARG, "not a sharded grid");
+    cudaIpcMemHandle_t h;
+    LSF_CUDA(cudaIpcGetMemHandle(&h, g->shared_base));
+    memset(handle, 0, LSF_IPC_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return LSF_OK;
+}
+
+int lsf_sgrid_attach(lsf_grid *g, const void *handles)
+{
+    if (!g || !handles) return set_error(LSF_ERR_ARG, "null argument");
+    if (!sharded(g)) return LSF_OK;
+    if (g->attached) return set_error(LSF_ERR_ARG, "sgrid_attach: already attached");
+    for (int r = 0; r < g->sg.nranks; ++r) {
+        if (r == g->sg.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)r * LSF_IPC_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return set_error(LSF_ERR_CUDA, "sgrid_attach: cudaIpcOpenMemHandle(rank %d) -> %s (GPUs of one node with peer access are required)",
+                             r, cudaGetErrorString(e));
+        g->peer_base[r] = p;
+    }
+    g->attached = true;
+    return LSF_OK;
+}
+
+int lsf_sgrid_sync_ghosts(lsf_grid *g)
+{
+    if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    int rc = slab_check_attached(g);
+    if (rc) return rc;
+    slab_exchange(g, false);
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    return LSF_OK;
+}
+
+}  // extern "C"

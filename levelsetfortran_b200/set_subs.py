@@ -183,3 +183,62 @@ class DeviceGrid:
         n_exit = C.c_int(-1)
         rc = check(lib().lsf_grid_minmax(self._h, int(iter), float(dx), float(h1), float(tol), C.byref(n_exit), _dp(hist)))
         return rc, n_exit.value, hist[: n_exit.value]
+
+
+def slab_range(nz, nranks, rank):
+    """Planes [k0, k1) of phi(0:nx,0:ny,0:nz) that `rank` of `nranks` owns (lsf_slab_range)."""
+    k0, k1 = C.c_int(0), C.c_int(0)
+    check(lib().lsf_slab_range(int(nz), int(nranks), int(rank), C.byref(k0), C.byref(k1)))
+    return k0.value, k1.value
+
+
+class ShardedGrid(DeviceGrid):
+    """One z-slab of a global phi(0:nx,0:ny,0:nz), one per process / GPU (include/lsf_b200.h, z-slab
+    sharding).  Same methods as DeviceGrid; every rank makes the same calls in the same order, host arrays
+    hold the rank's OWNED planes k0..k1-1 -- shape (nx+1, ny+1, k1-k0) -- and n_exit / rms_hist are identical
+    on all ranks.  `torch.distributed` must be initialised: it is used once, to all-gather the CUDA-IPC
+    handles; the data path itself is peer stores over NVLink from inside the kernels."""
+
+    def __init__(self, nx, ny, nz, rank=None, nranks=None):
+        import torch
+        import torch.distributed as dist
+        self.rank = dist.get_rank() if rank is None else int(rank)
+        self.nranks = dist.get_world_size() if nranks is None else int(nranks)
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.k0, self.k1 = slab_range(self.nz, self.nranks, self.rank)
+        self._h = C.c_void_p()
+        check(lib().lsf_sgrid_create(C.byref(self._h), self.nx, self.ny, self.nz, self.rank, self.nranks))
+        if self.nranks > 1:
+            buf = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+            check(lib().lsf_sgrid_ipc_handle(self._h, buf))
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            mine = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+            every = [torch.empty_like(mine) for _ in range(self.nranks)]
+            dist.all_gather(every, mine)
+            blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in every)
+            check(lib().lsf_sgrid_attach(self._h, blob))
+            dist.barrier()
+
+    @property
+    def shape(self):
+        return (self.nx + 1, self.ny + 1, self.k1 - self.k0)
+
+    def _slab_array(self, a, dtype, name):
+        if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.f_contiguous or a.shape != self.shape:
+            raise ValueError(f"{name} must be a Fortran-ordered {np.dtype(dtype).name} array of shape {self.shape} "
+                             f"(planes {self.k0}..{self.k1 - 1} of the global grid)")
+        return a
+
+    def upload(self, phi):
+        self._slab_array(phi, np.float64, "phi")
+        check(lib().lsf_grid_upload(self._h, phi.ctypes.data))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, order="F")
+        self._slab_array(out, np.float64, "out")
+        check(lib().lsf_grid_download(self._h, out.ctypes.data))
+        return out
+
+    def sync_ghosts(self):
+        check(lib().lsf_sgrid_sync_ghosts(self._h))

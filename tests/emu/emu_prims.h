@@ -17,4 +17,8 @@ inline long long p_ld_relaxed(const long long *p) { return __atomic_load_n(p, __
 inline void p_fence_acquire() { __atomic_thread_fence(__ATOMIC_ACQ_REL); }
 inline void p_st_release(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void p_sleep() { sched_yield(); }
+inline long long p_ld_relaxed_sys(const long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void p_fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void p_st_release_sys(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void p_st_peer(double *p, double v) { *(volatile double *)p = v; }
 }  // namespace lsf

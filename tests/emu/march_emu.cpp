@@ -9,6 +9,7 @@
 
 #include "../../levelsetfortran_b200/csrc/lsf_march.cuh"
 #include "../../levelsetfortran_b200/csrc/lsf_mm_march.cuh"
+#include "../../levelsetfortran_b200/csrc/lsf_slab.cuh"
 
 namespace lsf { thread_local EmuCta *emu_cta = nullptr; }
 using namespace lsf;
@@ -65,6 +66,86 @@ extern "C" double emu_march_sweep(double *phi, const double *phiS, int nx, int n
     for (int c = 0; c < ncta; ++c) pthread_barrier_destroy(&ctas[c].bar);
     double s = 0.;
     for (int q = 0; q < p.ntiles; ++q) s += partial[q];
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same sweep on a grid cut into `nranks` z-slabs (lsf_slab.cuh), all ranks running concurrently in this
+// process: every rank has its own local array with ghost planes, its own tickets / progress flags / CTAs,
+// and talks to its neighbours only through the streaming-halo protocol of lsf_march.cuh (peer stores into
+// the downstream rank's ghost planes + in_progress flags).  phi/phiS are the GLOBAL arrays; the ghost
+// planes are filled from the pre-sweep state (what k_slab_exchange leaves there) and the owned planes are
+// gathered back.  Returns the sum of all ranks' partials, -1 on failure, -2 on a bad partition.
+extern "C" double emu_march_sweep_slabs(double *phi, const double *phiS, int nx, int ny, int NZ, int nranks, int raster,
+                                        double dx, double h, int arith, int ncta, int order_m)
+{
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    std::vector<SlabGeom> geo(nranks);
+    for (int r = 0; r < nranks; ++r) if (!slab_geom(NZ, nranks, r, geo[r])) return -2.;
+    std::vector<std::vector<double>> lphi(nranks), lphiS(nranks), partial(nranks);
+    std::vector<std::vector<int>> order(nranks);
+    std::vector<std::vector<long long>> progress(nranks);
+    std::vector<SlabSync> sync(nranks);
+    std::vector<MarchParams> P(nranks);
+    std::vector<unsigned> ticket(nranks, 0u);
+    std::vector<Ctrl> ctrl(nranks, Ctrl{0, 0, 0, 0, 0});
+    memset(sync.data(), 0, sizeof(SlabSync) * nranks);
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        const size_t n = (size_t)sxy * (g.nzl + 1);
+        lphi[r].assign(phi + (size_t)g.kbase * sxy, phi + (size_t)g.kbase * sxy + n);
+        lphiS[r].assign(phiS + (size_t)g.kbase * sxy, phiS + (size_t)g.kbase * sxy + n);
+    }
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        MarchParams &p = P[r];
+        memset(&p, 0, sizeof(p));
+        march_orient<CFG>(p, nx, ny, g.nzl, sx, sxy, raster, g.kupd_lo, g.kupd_hi, g.kbase, NZ);
+        p.phi = lphi[r].data(); p.phiS = lphiS[r].data();
+        p.cc.dx = dx; p.cc.inv_dx = 1. / dx; p.cc.k12 = 1. / (12. * dx); p.cc.dx2 = dx * dx; p.cc.h = h;
+        partial[r].assign(p.ntiles, 0.); order[r].resize(p.ntiles); progress[r].assign(p.ntiles, 0);
+        march_fill_order(p.ntb, p.ntc, order[r].data(), order_m);
+        p.partial = partial[r].data(); p.order = order[r].data(); p.progress = progress[r].data();
+        p.ticket = &ticket[r]; p.ctrl = &ctrl[r]; p.epoch = 1;
+        const int up = p.fc ? r + 1 : r - 1, down = p.fc ? r - 1 : r + 1;
+        if (up >= 0 && up < nranks) p.in_progress = sync[r].in_progress;
+        if (down >= 0 && down < nranks) {
+            p.push_delta = (lphi[down].data() + (long long)(g.kbase - geo[down].kbase) * sxy) - lphi[r].data();
+            p.push_progress = sync[down].in_progress;
+        }
+    }
+    std::vector<int> nc(nranks);
+    size_t nthreads = 0;
+    for (int r = 0; r < nranks; ++r) { nc[r] = ncta < P[r].ntiles ? ncta : P[r].ntiles; nthreads += (size_t)nc[r] * M_THREADS; }
+    std::vector<std::vector<Smem>> sm(nranks);
+    std::vector<std::vector<EmuCta>> ctas(nranks);
+    std::vector<ThreadArg> args(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    for (int r = 0; r < nranks; ++r) {
+        sm[r] = std::vector<Smem>(nc[r]);
+        ctas[r] = std::vector<EmuCta>(nc[r]);
+        for (int c = 0; c < nc[r]; ++c) pthread_barrier_init(&ctas[r][c].bar, nullptr, M_THREADS);
+    }
+    size_t q = 0;
+    for (int r = 0; r < nranks; ++r)
+        for (int c = 0; c < nc[r]; ++c)
+            for (int t = 0; t < M_THREADS; ++t, ++q) {
+                ThreadArg &a = args[q];
+                a.p = &P[r]; a.sm = &sm[r][c]; a.cta = &ctas[r][c]; a.tid = t; a.arith = arith;
+                if (pthread_create(&th[q], &attr, thread_main, &a) != 0) return -1.;
+            }
+    for (size_t i = 0; i < th.size(); ++i) pthread_join(th[i], nullptr);
+    double s = 0.;
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        for (int c = 0; c < nc[r]; ++c) pthread_barrier_destroy(&ctas[r][c].bar);
+        if (ctrl[r].status != 0) return -3.;
+        memcpy(phi + (size_t)g.k0 * sxy, lphi[r].data() + (size_t)g.own_lo * sxy, sizeof(double) * (size_t)sxy * (g.k1 - g.k0));
+        for (int i = 0; i < P[r].ntiles; ++i) s += partial[r][i];
+    }
     return s;
 }
 

@@ -23,6 +23,9 @@ def emu():
     L = C.CDLL(so)
     L.emu_march_sweep.restype = C.c_double
     L.emu_march_sweep.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.emu_march_sweep_slabs.restype = C.c_double
+    L.emu_march_sweep_slabs.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                        C.c_int, C.c_int, C.c_int]
     L.emu_mm_iteration.restype = C.c_double
     L.emu_mm_iteration.argtypes = [dp, dp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     return L
@@ -44,6 +47,28 @@ def test_march_schedule_is_an_exact_reordering(emu, oracle, shape, ncta):
         assert abs(s - ref) <= 1e-12 * max(ref, 1e-300)
         emu.emu_march_sweep(f.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, r, 0.05, 0.0014, 0, ncta)
         assert np.abs(a - f).max() < 1e-13, f"raster {r}: fast arithmetic drifted"
+
+
+@pytest.mark.parametrize("shape,nranks,ncta,m", [((22, 21, 40), 2, 2, 1), ((20, 36, 51), 3, 3, 2), ((14, 70, 33), 4, 2, 3),
+                                                 ((12, 20, 64), 8, 1, 1)])
+def test_march_slab_pipeline_is_an_exact_reordering(emu, oracle, shape, nranks, ncta, m):
+    """z-slab sharding (lsf_slab.cuh): `nranks` slabs sweep concurrently, each on its own local array with
+    ghost planes, coupled only through the streaming halo (peer stores + in_progress flags).  The gathered
+    result must be bit-identical to the oracle's serial sweep of the whole grid, for all 8 rasters (both
+    pipeline directions) and for tilted ticket orders."""
+    p0 = synth_field(shape, seed=2)
+    pS = p0.copy(order="F")
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    nx, ny, nz = (s - 1 for s in shape)
+    for r in range(1, 9):
+        before = a.copy(order="F")
+        oracle.reinit_sweep(a, pS, 0.05, 0.0014, r)
+        s = emu.emu_march_sweep_slabs(b.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, nranks, r, 0.05, 0.0014,
+                                      1, ncta, m)
+        assert s >= 0, f"emulator failed ({s})"
+        assert np.array_equal(a, b), f"raster {r}: sharded sweep differs from the serial oracle"
+        ref = float(((a - before)[1:-1, 1:-1, 1:-1] ** 2).sum())
+        assert abs(s - ref) <= 1e-12 * max(ref, 1e-300)
 
 
 @pytest.mark.parametrize("shape,ncta", [((22, 21, 23), 1), ((24, 36, 22), 4), ((40, 38, 36), 9), ((12, 50, 20), 6)])
