@@ -61,6 +61,28 @@ static int read_ctrl(Grid *g, Ctrl *h)
     return LSF_OK;
 }
 
+// per-sweep event pairs of the profiling mode (lsf_set_profile): recorded around every sweep launch, read
+// back whenever the host synchronises anyway
+struct SweepEvents {
+    cudaEvent_t ev[16][2];
+    bool init = false;
+    int npend = 0;
+    void begin() {
+        if (!G.profile) return;
+        if (!init) { for (int q = 0; q < 16; ++q) { cudaEventCreate(&ev[q][0]); cudaEventCreate(&ev[q][1]); } init = true; }
+        cudaEventRecord(ev[npend][0], G.stream);
+    }
+    void end() { if (G.profile) { cudaEventRecord(ev[npend][1], G.stream); ++npend; } }
+    void collect() {
+        for (int q = 0; q < npend; ++q) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[q][0], ev[q][1]) == cudaSuccess) { G.sweep_ms += ms; G.n_sweeps++; }
+        }
+        npend = 0;
+    }
+};
+static SweepEvents SE;
+
 // reinit, subs.f90:717-931.  d_gradPhi / d_gradPhiMag: optional device arrays.
 // One attempt in the arithmetic G.arith_run.  *guard_hit is set when a FAST attempt met an ill-conditioned
 // cell update (then phi is NOT valid and the caller restarts from phiS in EXACT).
@@ -73,33 +95,24 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
     cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
     const bool want_grad = d_gradPhi || d_gradPhiMag;
     const bool march = (G.sched == LSF_SCHED_MARCH) && !want_grad;
-    if (sharded(g) && !march) return set_error(LSF_ERR_ARG, "reinit: a sharded grid supports the march schedule without gradPhi outputs only");
     int rc;
-    slab_exchange(g, false);                                            // z-slabs: ghost planes = neighbours' current phi
     if (march) { rc = march_prepare(g); if (rc) return rc; }
     else LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
     const int check = march ? 8 : (g->np > 2000000 ? 1 : 8);
     Ctrl hc = {0, 0, 0, 0, 0};
-    static cudaEvent_t pev[16][2];
-    static bool pev_init = false;
-    if (G.profile && !pev_init) {
-        for (int q = 0; q < 16; ++q) { LSF_CUDA(cudaEventCreate(&pev[q][0])); LSF_CUDA(cudaEventCreate(&pev[q][1])); }
-        pev_init = true;
-    }
-    int npend = 0;
+    SE.npend = 0;
     *guard_hit = false;
     for (int n = 0; n <= iter; ++n) {                                   // subs.f90:735
         const int raster = n % 8 + 1;                                   // subs.f90:740,855
-        if (G.profile) cudaEventRecord(pev[npend][0], G.stream);
+        SE.begin();
         if (march) launch_reinit_sweep_march(g, raster, cc);
         else launch_reinit_sweep_plane(g, raster, cc, d_gradPhi, d_gradPhiMag);
-        if (G.profile) { cudaEventRecord(pev[npend][1], G.stream); ++npend; }
+        SE.end();
         if (march) {
             // RMS fused: interior sums come from the sweep (one per column tile), boundary sums from the
             // BC kernel; phiN (subs.f90:732,921) is never materialised on this path
             launch_reinit_bc_rms(g, dx, march_ntiles(g));               // subs.f90:858-897 + boundary part of :902-914
-            slab_exchange(g, true);                                     // z-slabs: OLD-value snapshot for the next sweep
-            launch_finalize(g, march_ntiles(g) + BC_BLOCKS, 0, tol);    // subs.f90:914-926 (sum over all ranks)
+            launch_finalize(g, march_ntiles(g) + BC_BLOCKS, 0, tol);    // subs.f90:914-926
         } else {
             launch_reinit_bc(g, dx);                                    // subs.f90:858-897
             launch_rms(g, true);                                        // subs.f90:902-914,921
@@ -108,11 +121,7 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
         if ((n + 1) % check == 0 || n == iter) {
             rc = read_ctrl(g, &hc);
             if (rc) return rc;
-            for (int q = 0; q < npend; ++q) {
-                float ms = 0.f;
-                if (cudaEventElapsedTime(&ms, pev[q][0], pev[q][1]) == cudaSuccess) { G.sweep_ms += ms; G.n_sweeps++; }
-            }
-            npend = 0;
+            SE.collect();
             if (watch_guard && hc.guard) { *guard_hit = true; return LSF_OK; }
             if (hc.done) break;
         }
@@ -122,6 +131,77 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
     if (G.profile && G.n_sweeps > ne + 1) G.n_sweeps = ne + 1;   // sweeps enqueued after the exit were no-ops
     if (n_exit) *n_exit = ne;
     if (rms_hist) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)(ne + 1), cudaMemcpyDeviceToHost));
+    return hc.done ? hc.status : LSF_OK;
+}
+
+// reinit on a z-slab (lsf_slab.cuh).  The sweeps of all ranks form one free-running Gauss-Seidel pipeline
+// along k: no bulk halo exchange and no reduction barrier between sweeps.  Every rank publishes its RMS
+// partial sum after each sweep, but the EXIT / NaN tests (subs.f90:914-926) are evaluated only after rasters
+// 1 and 5 -- where the k direction of the sweep flips and the ranks have to wait for each other anyway --
+// for all sweeps since the previous evaluation, in order.  If the loop turns out to have left in the middle
+// of such a batch, phi is rolled back to the snapshot taken at the previous evaluation (phiN is free on
+// this path) and the sweeps up to the exit are replayed, so phi, n_exit and rms_hist are exactly those of
+// the sweep-by-sweep loop.  Snapshots are only taken when an EXIT is possible (tol > 0).
+static int reinit_attempt_slab(Grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist,
+                               bool watch_guard, bool *guard_hit)
+{
+    if (G.sched != LSF_SCHED_MARCH) return set_error(LSF_ERR_ARG, "reinit: a sharded grid supports the march schedule only");
+    const size_t bytes = sizeof(double) * (size_t)g->np;
+    LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
+    CellConst cc;
+    cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
+    int rc = march_prepare(g);
+    if (rc) return rc;
+    *guard_hit = false;
+    const bool snap = tol > 0.;
+    const int npart = march_ntiles(g) + BC_BLOCKS;
+    Ctrl hc = {0, 0, 0, 0, 0};
+    slab_exchange(g, false);                                            // ghost planes = neighbours' current phi
+    if (snap) LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));
+    int batch_first = 0;
+    long long seq_first = 0;
+    SE.npend = 0;
+    for (int n = 0; n <= iter; ++n) {                                   // subs.f90:735
+        const int raster = n % 8 + 1;                                   // subs.f90:740,855
+        SE.begin();
+        launch_reinit_sweep_march(g, raster, cc);
+        SE.end();
+        launch_reinit_bc_rms(g, dx, march_ntiles(g));                   // subs.f90:858-897 + boundary part of :902-914
+        const long long seq = slab_publish_sum(g, npart);
+        if (n == batch_first) seq_first = seq;
+        if (n % 4 == 0 || n == iter) {                                  // after raster 1 / 5: the k direction flips next
+            slab_decide(g, seq_first, n - batch_first + 1, batch_first, 0, tol);
+            rc = read_ctrl(g, &hc);
+            if (rc) return rc;
+            SE.collect();
+            if (watch_guard && hc.guard) { *guard_hit = true; break; }
+            if (hc.done) {
+                if (hc.status >= 0 && hc.n_exit < n && snap) {
+                    // left in the middle of the batch: roll back and replay sweeps batch_first..n_exit
+                    LSF_CUDA(cudaMemcpyAsync(g->phi, g->phiN, bytes, cudaMemcpyDeviceToDevice, G.stream));
+                    LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
+                    slab_exchange(g, false);
+                    for (int m = batch_first; m <= hc.n_exit; ++m) {
+                        launch_reinit_sweep_march(g, m % 8 + 1, cc);
+                        launch_reinit_bc_rms(g, dx, march_ntiles(g));
+                    }
+                    LSF_CUDA(cudaMemcpyAsync(g->ctrl, &hc, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
+                    LSF_CUDA(cudaStreamSynchronize(G.stream));
+                }
+                break;
+            }
+            if (snap && n < iter) LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));
+            batch_first = n + 1;
+        }
+    }
+    slab_exchange(g, false);                                            // leave the ghost planes (faces included) current
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    LSF_CUDA(cudaGetLastError());
+    if (hc.done && hc.status < 0)
+        return set_error(hc.status, hc.status == LSF_ERR_TIMEOUT ? "reinit: a neighbouring rank stopped answering" : "reinit: device-side error");
+    const int ne = hc.done ? hc.n_exit : iter;
+    if (n_exit) *n_exit = ne;
+    if (rms_hist && !*guard_hit) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)(ne + 1), cudaMemcpyDeviceToHost));
     return hc.done ? hc.status : LSF_OK;
 }
 
@@ -141,14 +221,18 @@ static int reinit_core(Grid *g, int iter, double dx, double h, double tol, doubl
     G.sweep_ms = 0.; G.n_sweeps = 0;
     G.arith_run = (G.arith == LSF_ARITH_EXACT) ? LSF_ARITH_EXACT : LSF_ARITH_FAST;
     bool guard_hit = false;
-    int st = reinit_attempt(g, iter, dx, h, tol, d_gradPhi, d_gradPhiMag, n_exit, rms_hist, G.arith == LSF_ARITH_AUTO, &guard_hit);
+    const bool auto_arith = G.arith == LSF_ARITH_AUTO;
+    if (sharded(g) && (d_gradPhi || d_gradPhiMag)) return set_error(LSF_ERR_ARG, "reinit: gradPhi outputs are not available on a sharded grid");
+    int st = sharded(g) ? reinit_attempt_slab(g, iter, dx, h, tol, n_exit, rms_hist, auto_arith, &guard_hit)
+                        : reinit_attempt(g, iter, dx, h, tol, d_gradPhi, d_gradPhiMag, n_exit, rms_hist, auto_arith, &guard_hit);
     if (st >= 0 && guard_hit) {
         // LSF_ARITH_AUTO: an ill-conditioned update was met -> the FAST result cannot be trusted to 1e-10;
         // start over from the frozen input (phiS still holds it) in the reference's exact arithmetic
         LSF_CUDA(cudaMemcpyAsync(g->phi, g->phiS, bytes, cudaMemcpyDeviceToDevice, G.stream));
         G.arith_run = LSF_ARITH_EXACT;
         G.sweep_ms = 0.; G.n_sweeps = 0;
-        st = reinit_attempt(g, iter, dx, h, tol, d_gradPhi, d_gradPhiMag, n_exit, rms_hist, false, &guard_hit);
+        st = sharded(g) ? reinit_attempt_slab(g, iter, dx, h, tol, n_exit, rms_hist, false, &guard_hit)
+                        : reinit_attempt(g, iter, dx, h, tol, d_gradPhi, d_gradPhiMag, n_exit, rms_hist, false, &guard_hit);
     }
     G.arith_last = G.arith_run;
     rc = tm.stop();

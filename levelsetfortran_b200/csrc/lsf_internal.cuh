@@ -31,6 +31,9 @@ struct lsf_grid {
     long long phase;              // number of ghost-plane exchanges so far (lockstep on all ranks)
     long long sum_seq;            // number of cross-rank reductions so far
     unsigned int *exch_counter;
+    bool prev_sweep_valid;        // the previous launch on this grid was a sweep of the same free-running sequence
+    long long prev_sweep_epoch;
+    int prev_sweep_fb;
 };
 
 namespace lsf {
@@ -90,7 +93,8 @@ inline bool sharded(const Grid *g) { return g->sg.nranks > 1; }
 // lsf_slab.cu
 int slab_check_attached(Grid *g);
 void slab_exchange(Grid *g, bool in_loop);       // ghost-plane refresh (k_slab_exchange); no-op on one GPU
-void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol);
+long long slab_publish_sum(Grid *g, int npart);  // this rank's sum of partials -> every rank (fire and forget); returns its sequence number
+void slab_decide(Grid *g, long long seq_first, int count, int n_first, int hist_off, double tol);   // EXIT / NaN tests of `count` iterations
 template <class T> inline T *peer_ptr(const Grid *g, int rank, T *mine)
 {
     return (T *)((char *)g->peer_base[rank] + ((char *)mine - (char *)g->shared_base));

@@ -236,7 +236,6 @@ k_finalize(const double *__restrict__ partial, int npart, Ctrl *ctrl, double *__
 
 void launch_finalize(Grid *g, int npart, int hist_off, double tol)
 {
-    if (sharded(g)) { launch_finalize_slab(g, npart, hist_off, tol); return; }
     const double denom = (double)((long long)g->dm.nx * g->dm.ny * g->dm.nz);
     k_finalize<<<1, 256, 0, G.stream>>>(g->partial, npart, g->ctrl, g->hist, hist_off, denom, tol);
     G.n_launch++;

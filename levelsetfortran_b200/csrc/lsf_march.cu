@@ -118,21 +118,36 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
     p.dbg = nullptr;
     p.in_progress = nullptr; p.push_delta = 0; p.push_progress = nullptr; p.halo_seq = nullptr;
     p.halo_need[0] = p.halo_need[1] = 0;
+    p.push_up_delta = 0; p.edge_pub[0] = p.edge_pub[1] = nullptr; p.edge_wait = nullptr; p.edge_need = 0; p.edge_prev_fb = 0;
     if (sharded(g)) {
         // the Gauss-Seidel pipeline along k (lsf_slab.cuh): upstream = the rank owning lower oriented c
         const SlabGeom &sg = g->sg;
         const int up = p.fc ? sg.rank + 1 : sg.rank - 1, down = p.fc ? sg.rank - 1 : sg.rank + 1;
-        if (up >= 0 && up < sg.nranks) p.in_progress = g->sync->in_progress;
+        const int side_up = p.fc ? 1 : 0, side_down = p.fc ? 0 : 1;     // which of THIS rank's sides that neighbour is on
+        if (up >= 0 && up < sg.nranks) {
+            SlabGeom ug;
+            slab_geom(sg.NZ, sg.nranks, up, ug);
+            p.in_progress = g->sync->in_progress;
+            p.push_up_delta = (peer_ptr(g, up, g->phi) + (long long)(sg.kbase - ug.kbase) * g->dm.sxy) - g->phi;
+            p.edge_pub[0] = peer_ptr(g, up, g->sync)->edge_done[1 - side_up];        // address computation only
+        }
         if (down >= 0 && down < sg.nranks) {
             SlabGeom dg;
             slab_geom(sg.NZ, sg.nranks, down, dg);
-            double *dphi = peer_ptr(g, down, g->phi) + (long long)(sg.kbase - dg.kbase) * g->dm.sxy;
-            p.push_delta = dphi - g->phi;
-            p.push_progress = peer_ptr(g, down, g->sync)->in_progress;   // address computation only
+            p.push_delta = (peer_ptr(g, down, g->phi) + (long long)(sg.kbase - dg.kbase) * g->dm.sxy) - g->phi;
+            p.push_progress = peer_ptr(g, down, g->sync)->in_progress;
+            p.edge_pub[1] = peer_ptr(g, down, g->sync)->edge_done[1 - side_down];
+            if (g->prev_sweep_valid) {
+                p.edge_wait = g->sync->edge_done[side_down];
+                p.edge_need = g->prev_sweep_epoch;
+                p.edge_prev_fb = g->prev_sweep_fb;
+            }
         }
+        // the first sweep after a bulk exchange: both neighbours' planes must have landed in the ghost planes
         p.halo_seq = g->sync->halo_seq;
         if (sg.rank > 0) p.halo_need[0] = g->phase;
         if (sg.rank < sg.nranks - 1) p.halo_need[1] = g->phase;
+        g->prev_sweep_valid = true; g->prev_sweep_epoch = p.epoch; g->prev_sweep_fb = p.fb;
     }
 #if defined(LSF_EXP_TIMING)
     {   // experiment: dump per-tile timing of this sweep to $LSF_TIMING_DUMP after the launch (synchronous)

@@ -81,6 +81,7 @@ LSF_DEV void p_st_release_sys(long long *p, long long v)
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 LSF_DEV void p_st_peer(double *p, double v) { __stcg(p, v); }
+LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 }  // namespace lsf
 #endif
 
@@ -141,6 +142,17 @@ struct MarchParams {
     long long *push_progress;      // downstream rank's in_progress; null: no downstream rank
     const long long *halo_seq;     // [2] counters the neighbours bump when they have refreshed this rank's ghost planes
     long long halo_need[2];        // the sweep starts once halo_seq[s] >= halo_need[s] (0: no neighbour on side s)
+    // Write-through on the other side: the first three updated planes are also stored into the UPSTREAM
+    // rank's ghost planes.  That rank reads them as OLD values LOOK steps ahead of its own march and this
+    // rank runs >= TC steps behind it, so the store can never overtake the read -- the very argument that
+    // makes the in-place update of neighbouring tiles safe on one GPU.  With both pushes a rank's ghost
+    // planes are always what an in-place sweep of the whole grid would hold there, and consecutive sweeps
+    // need no bulk halo exchange: only per-tile completion flags (edge_*).
+    long long push_up_delta;       // (upstream rank's phi, shifted) - phi; 0: none
+    long long *edge_pub[2];        // where the tiles of row K = 0 / K = ntc-1 publish "done in sweep `epoch`" (the adjacent rank's memory), or null
+    const long long *edge_wait;    // [ntb of the previous sweep] completion flags of the DOWNSTREAM rank's adjacent tile row, or null
+    long long edge_need;           // epoch of the previous sweep (tiles of row ntc-1 wait for it before reading / overwriting that rank's planes)
+    int edge_prev_fb;              // b-orientation of the previous sweep (maps this sweep's tile columns onto that sweep's)
 };
 
 // Spin until *flag >= need.  SYS: the flag is written by a peer GPU.  Gives up (and poisons the loop
@@ -221,6 +233,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
     const bool rowValid = (b <= p.ny) && (c <= p.c_max);
     const bool compValid = (b <= p.ny - 1) && (c <= p.c_hi);
     const bool pushRow = (p.push_delta != 0) && compValid && (c > p.c_hi - M_H);
+    const bool pushUpRow = (p.push_up_delta != 0) && compValid && (c < p.c_lo + M_H);
     const bool hiBC = (b >= p.lo_b) && (b <= p.hi_b) && (c >= p.lo_c) && (c <= p.hi_c);
     const int sig = tb + tc + M_H;
     const long long rowoff = p.off0 + (long long)b * p.sb + (long long)c * p.sc;
@@ -266,6 +279,21 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
     long long *mine = p.progress + (J + p.ntb * K);
     long long *minePeer = (K == p.ntc - 1 && p.push_progress) ? p.push_progress + J : nullptr;
 
+    // z-slabs: before a tile of the last row touches the downstream rank's planes (reads them as OLD values,
+    // streams NEW values into its ghost planes) that rank's adjacent tiles of the PREVIOUS sweep covering the
+    // same physical j range must be complete (they may have used a different b orientation).
+    // (a short last tile row leaves some of the three boundary planes to the row before it: any tile whose
+    // rows or +c halo reach beyond c_hi is concerned)
+    if (p.edge_wait && p.c_lo + (K + 1) * TC + M_H - 1 > p.c_hi) {
+        if (tid < 2) {
+            const int bq = 1 + J * TB + (tid ? TB - 1 : 0);
+            const int be = bq < p.ny - 1 ? bq : p.ny - 1;                       // clamp to the updated range
+            const int bp = (p.edge_prev_fb != (FB ? 1 : 0)) ? p.ny - be : be;    // same physical j in the previous orientation
+            wait_ge<true>(p.edge_wait + (bp - 1) / TB, p.edge_need, p.ctrl);
+        }
+        p_sync();
+    }
+
     double acc = 0.;
 #if defined(LSF_EXP_TIMING)
     long long dbg_wait = 0, dbg_t0 = 0, dbg_c0 = 0;
@@ -299,6 +327,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             if (tid == 0) dbg_wait += clock64() - tw0;
 #endif
         }
+        p_emu_hook(tid == 0 && t == 6);
         const int a = 1 + t - sig;
         // ---- (1) issue the global loads of this step --------------------------------------
         const int a4 = a + M_LOOK;
@@ -344,6 +373,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             acc += df * df;
             p_stcg(pOut, pn);
             if (pushRow) p_st_peer(pOut + p.push_delta, pn);
+            if (pushUpRow) p_st_peer(pOut + p.push_up_delta, pn);
         }
         // ---- (3) deposits into the slot ring (each value to slot h&7 and its double) ----------
         if (active) { double *d = Sown + (t & (M_NSLOT - 1)); d[0] = pn; d[M_NSLOT] = pn; }
@@ -371,6 +401,8 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
     if (tid == 0) {
         p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN);
         if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + M_FIN); }
+        if (K == 0 && p.edge_pub[0]) { p_fence_sys(); p_st_release_sys(p.edge_pub[0] + J, p.epoch); }
+        if (K == p.ntc - 1 && p.edge_pub[1]) { p_fence_sys(); p_st_release_sys(p.edge_pub[1] + J, p.epoch); }
     }
     for (int wdt = THREADS / 2; wdt > 0; wdt >>= 1) {
         if (tid < wdt) sm.red[tid] = sm.red[tid] + sm.red[tid + wdt];

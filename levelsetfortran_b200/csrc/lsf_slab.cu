@@ -107,20 +107,25 @@ void slab_exchange(Grid *g, bool in_loop)
     }
     k_slab_exchange<<<2 * G.num_sms, 256, 0, G.stream>>>(a);
     G.n_launch++;
+    g->prev_sweep_valid = false;      // the per-tile completion flags of earlier sweeps are history now
 }
 
 // =====================================================================================
-// Loop control on a sharded grid: k_finalize (lsf_kernels.cu) with the sum taken over all ranks.
-// Every rank adds up its own partials in a fixed order, writes the result (and its status flags) into
-// every rank's SlabSync block, waits until all P contributions of this sequence number have arrived and
-// sums them in rank order: all ranks compute the bit-identical phiErr and take the same EXIT / NaN /
-// error decision without a host round trip or a collective library call.
+// Loop control on a sharded grid: k_finalize (lsf_kernels.cu) with the sum taken over all ranks, split in two
+// so that the reduction never stalls the pipeline of sweeps:
+//   k_rank_publish : adds up this rank's partials in a fixed order and writes the result (and its status
+//                    flags) into slot seq % SLOTS of EVERY rank's SlabSync block -- fire and forget;
+//   k_decide_slab  : waits until all P contributions of `count` consecutive sequence numbers have arrived,
+//                    sums each in rank order and replays the reference's per-sweep test (subs.f90:914-926) on
+//                    them in order.  All ranks compute bit-identical phiErr values and take the same EXIT /
+//                    NaN / error decision on the device: no host round trip, no collective library call.
+// The reinit loop decides only where the sweep direction along k flips (after rasters 1 and 5,
+// subs.f90:743-852): there the ranks have to wait for each other anyway (the pipeline reverses).
 // =====================================================================================
 struct PeerSyncs { SlabSync *s[SLAB_MAX_RANKS]; };
 
 __global__ void __launch_bounds__(256)
-k_finalize_slab(const double *__restrict__ partial, int npart, Ctrl *ctrl, double *__restrict__ hist, int hist_off,
-                double denom, double tol, PeerSyncs peers, int rank, int nranks, long long seq)
+k_rank_publish(const double *__restrict__ partial, int npart, Ctrl *ctrl, PeerSyncs peers, int rank, int nranks, long long seq)
 {
     if (ctrl->done) return;
     __shared__ double sh[256];
@@ -132,51 +137,81 @@ k_finalize_slab(const double *__restrict__ partial, int npart, Ctrl *ctrl, doubl
         if (threadIdx.x < w) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + w]);
         __syncthreads();
     }
-    const int par = (int)(seq & 1);
-    SlabSync *self = peers.s[rank];
+    const int slot = (int)(seq % SLAB_SUM_SLOTS);
     if (threadIdx.x < nranks) {
         const int st = *(volatile int *)&ctrl->status;
         const int flags = (ctrl->guard ? 1 : 0) | (st == LSF_ERR_BAND_ON_BOUNDARY ? 2 : 0) | (st == LSF_ERR_TIMEOUT ? 4 : 0);
         SlabSync *q = peers.s[threadIdx.x];
-        *(volatile double *)&q->rank_sum[par][rank] = sh[0];
-        *(volatile int *)&q->rank_flag[par][rank] = flags;
+        *(volatile double *)&q->rank_sum[slot][rank] = sh[0];
+        *(volatile int *)&q->rank_flag[slot][rank] = flags;
         p_fence_sys();
-        p_st_release_sys(&q->sum_seq[rank], seq);
-        wait_ge<true>(&self->sum_seq[threadIdx.x], seq, ctrl);
+        p_st_release_sys(&q->sum_seq[slot][rank], seq);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_decide_slab(Ctrl *ctrl, double *__restrict__ hist, int hist_off, double denom, double tol, SlabSync *self, int nranks,
+              long long seq_first, int count, int n_first)
+{
+    if (ctrl->done) return;
+    for (int t = threadIdx.x; t < count * nranks; t += blockDim.x) {
+        const long long seq = seq_first + t / nranks;
+        wait_ge<true>(&self->sum_seq[seq % SLAB_SUM_SLOTS][t % nranks], seq, ctrl);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x != 0) return;
+    const bool timed_out = *(volatile int *)&ctrl->status == LSF_ERR_TIMEOUT;
+    for (int m = 0; m < count; ++m) {
+        const int slot = (int)((seq_first + m) % SLAB_SUM_SLOTS);
+        const int n = n_first + m;
         double tot = 0.;
-        int flags = 0;
+        int flags = timed_out ? 4 : 0;
         for (int r = 0; r < nranks; ++r) {
-            tot = __dadd_rn(tot, *(volatile double *)&self->rank_sum[par][r]);
-            flags |= *(volatile int *)&self->rank_flag[par][r];
+            tot = __dadd_rn(tot, *(volatile double *)&self->rank_sum[slot][r]);
+            flags |= *(volatile int *)&self->rank_flag[slot][r];
         }
-        if (*(volatile int *)&ctrl->status == LSF_ERR_TIMEOUT) flags |= 4;
-        const int n = ctrl->n;
         if (flags & 1) ctrl->guard = 1;
         if (flags & 6) {
             ctrl->status = (flags & 4) ? LSF_ERR_TIMEOUT : LSF_ERR_BAND_ON_BOUNDARY;
-            ctrl->done = 1; ctrl->n_exit = n;
+            ctrl->done = 1; ctrl->n_exit = n; ctrl->n = n;
             return;
         }
         const double err = sqrt(tot / denom);
         hist[n - hist_off] = err;
-        if (err < tol) { ctrl->done = 1; ctrl->status = 0; ctrl->n_exit = n; }
-        else if (err != err) { ctrl->done = 1; ctrl->status = 1; ctrl->n_exit = n; }
-        ctrl->n = n + 1;
+        if (err < tol) { ctrl->done = 1; ctrl->status = 0; ctrl->n_exit = n; ctrl->n = n; return; }
+        if (err != err) { ctrl->done = 1; ctrl->status = 1; ctrl->n_exit = n; ctrl->n = n; return; }
     }
+    ctrl->n = n_first + count;
 }
 
-void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol)
+static PeerSyncs peer_syncs(const Grid *g)
 {
     PeerSyncs ps;
     memset(&ps, 0, sizeof(ps));
     for (int r = 0; r < g->sg.nranks; ++r) ps.s[r] = (SlabSync *)g->peer_base[r];
-    const double denom = (double)global_cells(g);
-    k_finalize_slab<<<1, 256, 0, G.stream>>>(g->partial, npart, g->ctrl, g->hist, hist_off, denom, tol, ps, g->sg.rank,
-                                             g->sg.nranks, ++g->sum_seq);
+    return ps;
+}
+
+long long slab_publish_sum(Grid *g, int npart)
+{
+    const long long seq = ++g->sum_seq;
+    k_rank_publish<<<1, 256, 0, G.stream>>>(g->partial, npart, g->ctrl, peer_syncs(g), g->sg.rank, g->sg.nranks, seq);
     G.n_launch++;
+    return seq;
+}
+
+void slab_decide(Grid *g, long long seq_first, int count, int n_first, int hist_off, double tol)
+{
+    k_decide_slab<<<1, 256, 0, G.stream>>>(g->ctrl, g->hist, hist_off, (double)global_cells(g), tol, g->sync, g->sg.nranks,
+                                           seq_first, count, n_first);
+    G.n_launch++;
+}
+
+// per-iteration form (min/max flow): publish + decide at once; the caller passes the iteration index
+void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol, int n)
+{
+    const long long seq = slab_publish_sum(g, npart);
+    slab_decide(g, seq, 1, n, hist_off, tol);
 }
 
 }  // namespace lsf

@@ -26,6 +26,7 @@ constexpr int SLAB_GHOST = 3;
 constexpr int SLAB_MAX_RANKS = 16;
 constexpr int SLAB_MIN_PLANES = 8;      // owned planes per rank (>= 2*ghost, keeps every exchange nearest-neighbour)
 constexpr int SLAB_MAX_NTB = 4096;
+constexpr int SLAB_SUM_SLOTS = 16;      // reductions may be published this many sequence numbers ahead of their consumption
 
 struct SlabGeom {
     int rank, nranks;
@@ -63,10 +64,11 @@ inline bool slab_geom(int NZ, int nranks, int rank, SlabGeom &s)
 struct SlabSync {
     long long halo_seq[2];                   // [0] bumped by the low neighbour, [1] by the high one: "my planes of phase e are in your ghosts"
     long long phase_done[2];                 // same sides: "I have finished compute phase e" (I no longer read my ghost planes)
-    long long sum_seq[SLAB_MAX_RANKS];       // per source rank: sequence number of its most recent contribution
-    double rank_sum[2][SLAB_MAX_RANKS];      // parity-buffered partial sums of the RMS test
-    int rank_flag[2][SLAB_MAX_RANKS];        // parity-buffered flags travelling with the sums (bit 0 guard, bit 1 band-on-boundary, bit 2 timeout)
+    long long sum_seq[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];   // per slot and source rank: sequence number of the contribution held there
+    double rank_sum[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];     // per-rank partial sums of the RMS test, slot = sequence number mod SLOTS
+    int rank_flag[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];       // flags travelling with the sums (bit 0 guard, bit 1 band-on-boundary, bit 2 timeout)
     long long in_progress[SLAB_MAX_NTB];     // streaming-halo progress of the upstream rank's last tile row
+    long long edge_done[2][SLAB_MAX_NTB];    // [side][J]: epoch of the last sweep in which that neighbour's tile J adjacent to this rank completed
 };
 
 }  // namespace lsf

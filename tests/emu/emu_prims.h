@@ -3,6 +3,7 @@
 #pragma once
 #include <pthread.h>
 #include <sched.h>
+#include <unistd.h>
 #define LSF_DEV inline
 namespace lsf {
 struct EmuCta { pthread_barrier_t bar; };
@@ -17,6 +18,10 @@ inline long long p_ld_relaxed(const long long *p) { return __atomic_load_n(p, __
 inline void p_fence_acquire() { __atomic_thread_fence(__ATOMIC_ACQ_REL); }
 inline void p_st_release(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void p_sleep() { sched_yield(); }
+// test hook: stall a CTA close to the end of its tile, so that ranks / tiles that are allowed to run ahead
+// really do (widens the hazard windows the flag protocol has to close)
+extern int emu_stall_us;
+inline void p_emu_hook(bool at) { if (at && emu_stall_us) usleep((useconds_t)emu_stall_us); }
 inline long long p_ld_relaxed_sys(const long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 inline void p_fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void p_st_release_sys(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }

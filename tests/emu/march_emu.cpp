@@ -4,6 +4,7 @@
 #define LSF_EMU 1
 #include <pthread.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 #include <vector>
 
@@ -11,7 +12,8 @@
 #include "../../levelsetfortran_b200/csrc/lsf_mm_march.cuh"
 #include "../../levelsetfortran_b200/csrc/lsf_slab.cuh"
 
-namespace lsf { thread_local EmuCta *emu_cta = nullptr; }
+namespace lsf { thread_local EmuCta *emu_cta = nullptr; int emu_stall_us = 0; }
+extern "C" void emu_set_stall(int us) { lsf::emu_stall_us = us; }
 using namespace lsf;
 
 typedef MarchCfgDefault CFG;
@@ -145,6 +147,119 @@ extern "C" double emu_march_sweep_slabs(double *phi, const double *phiS, int nx,
         if (ctrl[r].status != 0) return -3.;
         memcpy(phi + (size_t)g.k0 * sxy, lphi[r].data() + (size_t)g.own_lo * sxy, sizeof(double) * (size_t)sxy * (g.k1 - g.k0));
         for (int i = 0; i < P[r].ntiles; ++i) s += partial[r][i];
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Several consecutive sweeps on z-slabs with NO synchronisation between the ranks other than the flags of
+// lsf_march.cuh (streaming halo, write-through to the upstream rank, per-tile completion flags): every rank
+// runs its sweeps back to back from its own controller thread, so ranks drift apart by whole sweeps exactly
+// as the GPUs do.  `skew_us` delays the ranks differently before every sweep to provoke that drift.
+struct RankCtl {
+    int r, nranks, nx, ny, NZ, nsweeps, first_raster, arith, ncta, order_m, skew_us;
+    double dx, h;
+    std::vector<SlabGeom> *geo;
+    std::vector<std::vector<double>> *lphi, *lphiS;
+    std::vector<SlabSync> *sync;
+    double sum;
+    int status;
+};
+
+static void *rank_main(void *v)
+{
+    RankCtl &R = *(RankCtl *)v;
+    const int r = R.r, nranks = R.nranks;
+    const long long sx = R.nx + 1, sxy = sx * (R.ny + 1);
+    const SlabGeom &g = (*R.geo)[r];
+    std::vector<SlabSync> &sync = *R.sync;
+    R.sum = 0.; R.status = 0;
+    int prev_fb = 0;
+    std::vector<long long> progress;
+    for (int n = 0; n < R.nsweeps; ++n) {
+        const int raster = (R.first_raster - 1 + n) % 8 + 1;
+        if (R.skew_us) usleep((useconds_t)R.skew_us * (unsigned)((n & 1) ? r : nranks - 1 - r));
+        MarchParams p;
+        memset(&p, 0, sizeof(p));
+        march_orient<CFG>(p, R.nx, R.ny, g.nzl, sx, sxy, raster, g.kupd_lo, g.kupd_hi, g.kbase, R.NZ);
+        p.phi = (*R.lphi)[r].data(); p.phiS = (*R.lphiS)[r].data();
+        p.cc.dx = R.dx; p.cc.inv_dx = 1. / R.dx; p.cc.k12 = 1. / (12. * R.dx); p.cc.dx2 = R.dx * R.dx; p.cc.h = R.h;
+        std::vector<double> partial(p.ntiles, 0.);
+        std::vector<int> order(p.ntiles);
+        if (progress.empty()) progress.assign(p.ntiles, 0);
+        march_fill_order(p.ntb, p.ntc, order.data(), R.order_m);
+        unsigned ticket = 0;
+        Ctrl ctrl = {0, 0, 0, 0, 0};
+        p.partial = partial.data(); p.order = order.data(); p.progress = progress.data();
+        p.ticket = &ticket; p.ctrl = &ctrl; p.epoch = n + 1;
+        const int up = p.fc ? r + 1 : r - 1, down = p.fc ? r - 1 : r + 1;
+        const int side_up = p.fc ? 1 : 0, side_down = p.fc ? 0 : 1;      // which of MY sides that neighbour is on
+        if (up >= 0 && up < nranks) {
+            p.in_progress = sync[r].in_progress;
+            p.push_up_delta = ((*R.lphi)[up].data() + (long long)(g.kbase - (*R.geo)[up].kbase) * sxy) - p.phi;
+            p.edge_pub[0] = sync[up].edge_done[1 - side_up];
+        }
+        if (down >= 0 && down < nranks) {
+            p.push_delta = ((*R.lphi)[down].data() + (long long)(g.kbase - (*R.geo)[down].kbase) * sxy) - p.phi;
+            p.push_progress = sync[down].in_progress;
+            p.edge_pub[1] = sync[down].edge_done[1 - side_down];
+            if (n > 0 && !getenv("EMU_NO_EDGE")) { p.edge_wait = sync[r].edge_done[side_down]; p.edge_need = n; p.edge_prev_fb = prev_fb; }
+        }
+        prev_fb = p.fb;
+        const int nc = R.ncta < p.ntiles ? R.ncta : p.ntiles;
+        std::vector<Smem> sm(nc);
+        std::vector<EmuCta> ctas(nc);
+        std::vector<ThreadArg> args((size_t)nc * M_THREADS);
+        std::vector<pthread_t> th((size_t)nc * M_THREADS);
+        pthread_attr_t attr;
+        pthread_attr_init(&attr);
+        pthread_attr_setstacksize(&attr, 256 * 1024);
+        for (int c = 0; c < nc; ++c) pthread_barrier_init(&ctas[c].bar, nullptr, M_THREADS);
+        for (int c = 0; c < nc; ++c)
+            for (int t = 0; t < M_THREADS; ++t) {
+                ThreadArg &a = args[(size_t)c * M_THREADS + t];
+                a.p = &p; a.sm = &sm[c]; a.cta = &ctas[c]; a.tid = t; a.arith = R.arith;
+                if (pthread_create(&th[(size_t)c * M_THREADS + t], &attr, thread_main, &a) != 0) { R.status = -1; return nullptr; }
+            }
+        for (size_t i = 0; i < th.size(); ++i) pthread_join(th[i], nullptr);
+        for (int c = 0; c < nc; ++c) pthread_barrier_destroy(&ctas[c].bar);
+        if (ctrl.status != 0) { R.status = -3; return nullptr; }
+        for (int i = 0; i < p.ntiles; ++i) R.sum += partial[i];
+    }
+    return nullptr;
+}
+
+extern "C" double emu_march_multi_slabs(double *phi, const double *phiS, int nx, int ny, int NZ, int nranks, int nsweeps,
+                                        int first_raster, double dx, double h, int arith, int ncta, int order_m, int skew_us)
+{
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    std::vector<SlabGeom> geo(nranks);
+    for (int r = 0; r < nranks; ++r) if (!slab_geom(NZ, nranks, r, geo[r])) return -2.;
+    std::vector<std::vector<double>> lphi(nranks), lphiS(nranks);
+    std::vector<SlabSync> sync(nranks);
+    memset(sync.data(), 0, sizeof(SlabSync) * nranks);
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        const size_t n = (size_t)sxy * (g.nzl + 1);
+        lphi[r].assign(phi + (size_t)g.kbase * sxy, phi + (size_t)g.kbase * sxy + n);
+        lphiS[r].assign(phiS + (size_t)g.kbase * sxy, phiS + (size_t)g.kbase * sxy + n);
+    }
+    std::vector<RankCtl> ctl(nranks);
+    std::vector<pthread_t> th(nranks);
+    for (int r = 0; r < nranks; ++r) {
+        RankCtl &R = ctl[r];
+        R.r = r; R.nranks = nranks; R.nx = nx; R.ny = ny; R.NZ = NZ; R.nsweeps = nsweeps; R.first_raster = first_raster;
+        R.arith = arith; R.ncta = ncta; R.order_m = order_m; R.skew_us = skew_us; R.dx = dx; R.h = h;
+        R.geo = &geo; R.lphi = &lphi; R.lphiS = &lphiS; R.sync = &sync;
+        if (pthread_create(&th[r], nullptr, rank_main, &R) != 0) return -1.;
+    }
+    for (int r = 0; r < nranks; ++r) pthread_join(th[r], nullptr);
+    double s = 0.;
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        if (ctl[r].status != 0) return (double)ctl[r].status;
+        memcpy(phi + (size_t)g.k0 * sxy, lphi[r].data() + (size_t)g.own_lo * sxy, sizeof(double) * (size_t)sxy * (g.k1 - g.k0));
+        s += ctl[r].sum;
     }
     return s;
 }

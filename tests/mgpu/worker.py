@@ -48,7 +48,8 @@ def main():
             hp = whole(shape, probe)
             cand = [n for n in range(10, iters - 2) if hp[n] < hp[:n].min()]
             assert cand, "probe run has no new RMS minimum to place the tolerance at"
-            n_star = cand[len(cand) // 2]
+            mid = [n for n in cand if n % 4 == 2] or cand      # not where the sharded loop evaluates its tests anyway:
+            n_star = mid[len(mid) // 2]                         # exercises the roll-back + replay of the batch
             tol = 0.5 * (hp[n_star] + hp[:n_star].min())
 
         def run_whole(G):

@@ -26,6 +26,8 @@ def emu():
     L.emu_march_sweep_slabs.restype = C.c_double
     L.emu_march_sweep_slabs.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                         C.c_int, C.c_int, C.c_int]
+    L.emu_march_multi_slabs.restype = C.c_double
+    L.emu_march_multi_slabs.argtypes = [dp, dp] + [C.c_int] * 6 + [C.c_double, C.c_double] + [C.c_int] * 4
     L.emu_mm_iteration.restype = C.c_double
     L.emu_mm_iteration.argtypes = [dp, dp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     return L
@@ -69,6 +71,34 @@ def test_march_slab_pipeline_is_an_exact_reordering(emu, oracle, shape, nranks, 
         assert np.array_equal(a, b), f"raster {r}: sharded sweep differs from the serial oracle"
         ref = float(((a - before)[1:-1, 1:-1, 1:-1] ** 2).sum())
         assert abs(s - ref) <= 1e-12 * max(ref, 1e-300)
+
+
+@pytest.mark.parametrize("shape,nranks,ncta,m,skew", [((22, 21, 40), 2, 2, 1, 0), ((20, 41, 51), 3, 2, 2, 3000),
+                                                      ((14, 70, 33), 4, 2, 8, 1000), ((12, 20, 64), 8, 1, 1, 2000),
+                                                      ((20, 36, 37), 2, 3, 1, 3000), ((16, 25, 38), 2, 2, 2, 2000)])
+def test_march_slab_pipeline_free_running_sweeps(emu, oracle, shape, nranks, ncta, m, skew):
+    """Eleven consecutive sweeps (all 8 rasters, both k flips, a b-orientation change between neighbouring
+    sweeps on a grid whose tile columns do not align) with the ranks running freely: no exchange or barrier
+    between sweeps, only the per-tile flags.  Must equal the oracle's serial sweeps bit for bit."""
+    p0 = synth_field(shape, seed=5)
+    pS = p0.copy(order="F")
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    nx, ny, nz = (s - 1 for s in shape)
+    nsweeps, first = 11, 7
+    ref = 0.0
+    for n in range(nsweeps):
+        before = a.copy(order="F")
+        oracle.reinit_sweep(a, pS, 0.05, 0.0014, (first - 1 + n) % 8 + 1)
+        ref += float(((a - before)[1:-1, 1:-1, 1:-1] ** 2).sum())
+    emu.emu_set_stall(300000 if skew else 0)     # every tile stalls 0.3 s shortly before its end: ranks run ahead where allowed
+    try:
+        s = emu.emu_march_multi_slabs(b.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, nranks, nsweeps, first,
+                                      0.05, 0.0014, 1, ncta, m, skew)
+    finally:
+        emu.emu_set_stall(0)
+    assert s >= 0, f"emulator failed ({s})"
+    assert np.array_equal(a, b), "free-running sharded sweeps differ from the serial oracle"
+    assert abs(s - ref) <= 1e-12 * ref
 
 
 @pytest.mark.parametrize("shape,ncta", [((22, 21, 23), 1), ((24, 36, 22), 4), ((40, 38, 36), 9), ((12, 50, 20), 6)])
