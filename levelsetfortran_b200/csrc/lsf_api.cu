@@ -74,9 +74,14 @@ struct SweepEvents {
     }
     void end() { if (G.profile) { cudaEventRecord(ev[npend][1], G.stream); ++npend; } }
     void collect() {
+        static const bool log = getenv("LSF_SWEEP_LOG") != nullptr;      // experiments: per-sweep kernel times on stderr
         for (int q = 0; q < npend; ++q) {
-            float ms = 0.f;
+            float ms = 0.f, gap = 0.f;
             if (cudaEventElapsedTime(&ms, ev[q][0], ev[q][1]) == cudaSuccess) { G.sweep_ms += ms; G.n_sweeps++; }
+            if (log) {
+                if (q + 1 < npend) cudaEventElapsedTime(&gap, ev[q][1], ev[q + 1][0]);
+                fprintf(stderr, "[lsf sweep] dev %d #%d kernel %.3f ms, then %.3f ms to the next sweep\n", G.device, G.n_sweeps, ms, gap);
+            }
         }
         npend = 0;
     }
@@ -282,9 +287,14 @@ static int minmax_core_march(Grid *g, int iter, double dx, double h1, double tol
     Ctrl hc = {0, 0, 1, 0, 0};
     if (iter >= 1) {
         launch_mm_check_boundary(g, mask_given ? g->mask : nullptr, dx, !mask_given || iter >= 2);
+        if (sharded(g)) launch_finalize_slab(g, 0, 1, -1., 1);          // all ranks must agree on the verdict (no sum, no test)
         rc = read_ctrl(g, &hc);
         if (rc) return rc;
         if (hc.status < 0) { *hc_out = hc; return LSF_OK; }
+        if (sharded(g)) {                                               // the agreement round advanced n: restore it
+            Ctrl init = {0, 0, 1, 0, 0};
+            LSF_CUDA(cudaMemcpyAsync(g->ctrl, &init, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
+        }
     }
     const int ntiles = march_ntiles(g);
     double *buf[2] = {g->phi, g->phiN};                                 // buf[0] = phi_0, buf[1] = copy of it
@@ -292,6 +302,10 @@ static int minmax_core_march(Grid *g, int iter, double dx, double h1, double tol
         const double *A = buf[(n - 1) & 1];
         double *B = buf[n & 1];
         launch_minmax_iteration_march(g, A, B, (mask_given && n == 1) ? g->mask : nullptr, dx, h1);   // :399-431
+        if (sharded(g)) {
+            slab_exchange(g, true, B);                                  // B's boundary planes -> the neighbours' ghost planes
+            launch_finalize_slab(g, ntiles, 1, tol, n);                 // :435-458, sum over all ranks
+        } else
         launch_finalize(g, ntiles, 1, tol);                             // :435-458
         if (n % 8 == 0 || n == iter) {
             rc = read_ctrl(g, &hc);
@@ -312,8 +326,11 @@ static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool
 {
     if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "minmax: bad iter/dx");
     if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "minmax: grid too small");
-    if (sharded(g)) return set_error(LSF_ERR_ARG, "minmax: sharded grids are not supported yet");
-    int rc = ensure_hist(g, iter + 1);
+    if (sharded(g) && (G.sched != LSF_SCHED_MARCH || mask_given))
+        return set_error(LSF_ERR_ARG, "minmax: a sharded grid supports the march schedule through lsf_grid_minmax only");
+    int rc = slab_check_attached(g);
+    if (rc) return rc;
+    rc = ensure_hist(g, iter + 1);
     if (rc) return rc;
     Ctrl init = {0, 0, 1, 0, 0};
     LSF_CUDA(cudaMemcpyAsync(g->ctrl, &init, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
@@ -576,8 +593,11 @@ int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *ph
 int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol, int *n_exit, double *rms_hist)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    slab_exchange(g, false);                                            // z-slabs: phi's ghost planes current before they are copied
     LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToDevice, G.stream)); // set3d.f90:377
-    return minmax_core(g, iter, dx, h1, tol, false, n_exit, rms_hist, nullptr);
+    const int st = minmax_core(g, iter, dx, h1, tol, false, n_exit, rms_hist, nullptr);
+    if (st >= 0) slab_exchange(g, false);
+    return st;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -92,7 +92,8 @@ inline bool sharded(const Grid *g) { return g->sg.nranks > 1; }
 
 // lsf_slab.cu
 int slab_check_attached(Grid *g);
-void slab_exchange(Grid *g, bool in_loop);       // ghost-plane refresh (k_slab_exchange); no-op on one GPU
+void slab_exchange(Grid *g, bool in_loop, double *buf = nullptr);   // ghost-plane refresh of buf (default phi); no-op on one GPU
+void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol, int n);
 long long slab_publish_sum(Grid *g, int npart);  // this rank's sum of partials -> every rank (fire and forget); returns its sequence number
 void slab_decide(Grid *g, long long seq_first, int count, int n_first, int hist_off, double tol);   // EXIT / NaN tests of `count` iterations
 template <class T> inline T *peer_ptr(const Grid *g, int rank, T *mine)

@@ -18,15 +18,17 @@ k_minmax_march(const MmParams p)
 // subs.f90:387): undefined there, an error here.  Boundary values never change during the flow, so one
 // check before the loop covers every iteration.
 __global__ void k_mm_check_boundary(const double *__restrict__ phi, const uint8_t *__restrict__ mask, Dims dm,
-                                    double bNB, int check_abs, Ctrl *ctrl)
+                                    double bNB, int check_abs, Ctrl *ctrl, int kA, int kB, int kbase, int NZ, int hasLo, int hasHi)
 {
-    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzp = dm.nz + 1;
-    const long long fxy = nxp * nyp, fxz = nxp * nzp, fyz = nyp * nzp;
+    // boundary points of this rank's OWNED planes (z-slab: the global k faces only where it holds them)
+    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzm = kB - kA + 1, nym = dm.ny - 1;
+    const long long fk = nxp * nyp, fj = nxp * nzm, fi = nym * nzm;
+    const long long nkf = (long long)(hasLo + hasHi) * fk;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int i, j, k;
-    if (t < 2 * fxy) { k = (t >= fxy) ? dm.nz : 0; t %= fxy; i = (int)(t % nxp); j = (int)(t / nxp); }
-    else if ((t -= 2 * fxy) < 2 * fxz) { j = (t >= fxz) ? dm.ny : 0; t %= fxz; i = (int)(t % nxp); k = (int)(t / nxp); }
-    else if ((t -= 2 * fxz) < 2 * fyz) { i = (t >= fyz) ? dm.nx : 0; t %= fyz; j = (int)(t % nyp); k = (int)(t / nyp); }
+    if (t < nkf) { k = (t >= fk || !hasLo) ? NZ - kbase : -kbase; t %= fk; i = (int)(t % nxp); j = (int)(t / nxp); }
+    else if ((t -= nkf) < 2 * fj) { j = (t >= fj) ? dm.ny : 0; t %= fj; i = (int)(t % nxp); k = kA + (int)(t / nxp); }
+    else if ((t -= 2 * fj) < 2 * fi) { i = (t >= fi) ? dm.nx : 0; t %= fi; j = 1 + (int)(t % nym); k = kA + (int)(t / nym); }
     else return;
     const long long q = i + dm.sx * j + dm.sxy * k;
     const bool hit = (mask && mask[q]) || (check_abs && fabs(phi[q]) < bNB);
@@ -36,9 +38,12 @@ __global__ void k_mm_check_boundary(const double *__restrict__ phi, const uint8_
 void launch_mm_check_boundary(Grid *g, const uint8_t *mask, double dx, bool check_abs)
 {
     const Dims &dm = g->dm;
-    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzp = dm.nz + 1;
-    const long long tot = 2 * (nxp * nyp + nxp * nzp + nyp * nzp);
-    k_mm_check_boundary<<<(unsigned)((tot + 255) / 256), 256, 0, G.stream>>>(g->phi, mask, dm, 4.1 * dx, check_abs ? 1 : 0, g->ctrl);
+    const SlabGeom &sg = g->sg;
+    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzm = sg.kupd_hi - sg.kupd_lo + 1, nym = dm.ny - 1;
+    const int hasLo = sg.k0 == 0, hasHi = sg.k1 == sg.NZ + 1;
+    const long long tot = (hasLo + hasHi) * nxp * nyp + 2 * (nxp * nzm + nym * nzm);
+    k_mm_check_boundary<<<(unsigned)((tot + 255) / 256), 256, 0, G.stream>>>(g->phi, mask, dm, 4.1 * dx, check_abs ? 1 : 0, g->ctrl,
+                                                                              sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ, hasLo, hasHi);
     G.n_launch++;
 }
 
@@ -47,7 +52,7 @@ int mm_march_prepare(Grid *g)
     int rc = march_prepare(g);   // ticket, per-tile progress flags, tile order: shared with the reinit sweep
     if (rc) return rc;
     MmParams p;
-    mm_orient<MCFG>(p, g->dm.nx, g->dm.ny, g->dm.nz);
+    mm_orient<MCFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->sg.kupd_lo, g->sg.kupd_hi);
     if (p.ntiles != march_ntiles(g)) return set_error(LSF_ERR_ARG, "minmax: tile grid mismatch");
     static bool attr_done = false;
     if (!attr_done) {
@@ -61,11 +66,28 @@ int mm_march_prepare(Grid *g)
 void launch_minmax_iteration_march(Grid *g, const double *A, double *B, const uint8_t *mask, double dx, double h1)
 {
     MmParams p;
-    mm_orient<MCFG>(p, g->dm.nx, g->dm.ny, g->dm.nz);
+    mm_orient<MCFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->sg.kupd_lo, g->sg.kupd_hi);
     p.A = A; p.B = B; p.mask = mask;
     p.bNB = 4.1 * dx; p.dxx = 1. / (dx * dx); p.h1 = h1;
     p.partial = g->partial; p.ticket = g->march_ticket; p.order = march_order();
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
+    p.in_progress = nullptr; p.push_delta = 0; p.push_progress = nullptr; p.halo_seq = nullptr;
+    p.halo_need[0] = p.halo_need[1] = 0;
+    if (sharded(g)) {
+        // pass B is an ascending-k Gauss-Seidel sweep (subs.f90:473): the rank below is upstream
+        const SlabGeom &sg = g->sg;
+        if (sg.rank > 0) p.in_progress = g->sync->in_progress;
+        if (sg.rank < sg.nranks - 1) {
+            SlabGeom dg;
+            slab_geom(sg.NZ, sg.nranks, sg.rank + 1, dg);
+            p.push_delta = (peer_ptr(g, sg.rank + 1, B) + (long long)(sg.kbase - dg.kbase) * g->dm.sxy) - B;
+            p.push_progress = peer_ptr(g, sg.rank + 1, g->sync)->in_progress;
+        }
+        p.halo_seq = g->sync->halo_seq;
+        if (sg.rank > 0) p.halo_need[0] = g->phase;
+        if (sg.rank < sg.nranks - 1) p.halo_need[1] = g->phase;
+        g->prev_sweep_valid = false;
+    }
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     const int ncta = p.ntiles < 4 * G.num_sms ? p.ntiles : 4 * G.num_sms;
     k_minmax_march<<<ncta, MCFG::THREADS, sizeof(MmSmem<MCFG>), G.stream>>>(p);

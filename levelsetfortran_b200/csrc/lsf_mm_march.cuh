@@ -53,13 +53,23 @@ struct MmParams {
     double bNB;                    // 4.1*dx (subs.f90:194)
     double dxx;                    // 1./(dx*dx) (subs.f90:384)
     double h1;
+    int c_lo, c_hi, c_max;         // planes c_lo..c_hi are updated, planes 0..c_max exist (one GPU: 1, nz-1, nz; z-slab: lsf_slab.cuh)
     int ntb, ntc, ntiles, tend;
     double *partial;
     unsigned *ticket;
     const int *order;
     long long *progress;
     long long epoch;
-    const Ctrl *ctrl;
+    Ctrl *ctrl;
+    // z-slab sharding (the sweep order is always ascending k: the rank below is upstream); all zero on one GPU.
+    // The upstream rank streams the NEW values of its last updated plane into this rank's ghost plane of B
+    // and publishes its last tile row's progress in in_progress[J]; ghost planes of A hold the OLD values
+    // (bulk exchange between iterations, k_slab_exchange).
+    const long long *in_progress;
+    long long push_delta;          // (downstream rank's B, shifted to this rank's indexing) - B, in elements; 0: none
+    long long *push_progress;
+    const long long *halo_seq;
+    long long halo_need[2];
 };
 
 template <class CFG>
@@ -71,13 +81,15 @@ struct MmSmem {
 };
 
 template <class CFG>
-inline void mm_orient(MmParams &p, int nx, int ny, int nz)
+inline void mm_orient(MmParams &p, int nx, int ny, int nz, int kupd_lo = 1, int kupd_hi = -1)
 {
+    if (kupd_hi < 0) kupd_hi = nz - 1;
     p.nx = nx; p.ny = ny; p.nz = nz;
     p.sx = (long long)nx + 1;
     p.sxy = p.sx * ((long long)ny + 1);
+    p.c_lo = kupd_lo; p.c_hi = kupd_hi; p.c_max = nz;
     p.ntb = (ny - 1 + CFG::TB - 1) / CFG::TB;
-    p.ntc = (nz - 1 + CFG::TC - 1) / CFG::TC;
+    p.ntc = (p.c_hi - p.c_lo + 1 + CFG::TC - 1) / CFG::TC;
     p.ntiles = p.ntb * p.ntc;
     p.tend = (nx - 1) - 1 + (CFG::TB - 1) + (CFG::TC - 1) + 1;
 }
@@ -88,9 +100,10 @@ LSF_DEV void mm_tile(const MmParams &p, MmSmem<CFG> &sm, const int tid, const in
     typedef ExactArith X;
     constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP, PW = CFG::PW;
     const int tb = tid % TB, tc = tid / TB;
-    const int b = 1 + J * TB + tb, c = 1 + K * TC + tc;
-    const bool rowValid = (b <= p.ny) && (c <= p.nz);
-    const bool compValid = (b <= p.ny - 1) && (c <= p.nz - 1);
+    const int b = 1 + J * TB + tb, c = p.c_lo + K * TC + tc;
+    const bool rowValid = (b <= p.ny) && (c <= p.c_max);
+    const bool compValid = (b <= p.ny - 1) && (c <= p.c_hi);
+    const bool pushRow = (p.push_delta != 0) && compValid && (c == p.c_hi);
     const int sig = tb + tc + 1;
     const long long rowoff = (long long)b * p.sx + (long long)c * p.sxy;
     const double *rowA = p.A + (rowValid ? rowoff : 0);
@@ -111,8 +124,8 @@ LSF_DEV void mm_tile(const MmParams &p, MmSmem<CFG> &sm, const int tid, const in
             int htb, htc;
             if (q < 2 * TC) { htc = q % TC; if (q < TC) { htb = -1; hlow[r] = true; } else htb = TB; }
             else { const int q2 = q - 2 * TC; htb = q2 % TB; if (q2 < TB) { htc = -1; hlow[r] = true; } else htc = TC; }
-            const int hb = 1 + J * TB + htb, hc = 1 + K * TC + htc;
-            hvalid[r] = (hb >= 0) && (hb <= p.ny) && (hc >= 0) && (hc <= p.nz);
+            const int hb = 1 + J * TB + htb, hc = p.c_lo + K * TC + htc;
+            hvalid[r] = (hb >= 0) && (hb <= p.ny) && (hc >= 0) && (hc <= p.c_max);
             hsig[r] = htb + htc + 1;
             hpos[r] = (htc + 1) * RP + (htb + 1) * PW;
             if (hvalid[r]) hoff[r] = (long long)hb * p.sx + (long long)hc * p.sxy;
@@ -121,8 +134,10 @@ LSF_DEV void mm_tile(const MmParams &p, MmSmem<CFG> &sm, const int tid, const in
 
     const long long ebase = p.epoch << 32;
     const long long *predB = (J > 0) ? p.progress + ((J - 1) + p.ntb * K) : nullptr;
-    const long long *predC = (K > 0) ? p.progress + (J + p.ntb * (K - 1)) : nullptr;
+    const bool predCpeer = (K == 0) && p.in_progress;
+    const long long *predC = (K > 0) ? p.progress + (J + p.ntb * (K - 1)) : (predCpeer ? p.in_progress + J : nullptr);
     long long *mine = p.progress + (J + p.ntb * K);
+    long long *minePeer = (K == p.ntc - 1 && p.push_progress) ? p.push_progress + J : nullptr;
     double acc = 0.;
 
     // Global loads are software-pipelined by one step: values requested in step t are deposited into the
@@ -140,8 +155,10 @@ LSF_DEV void mm_tile(const MmParams &p, MmSmem<CFG> &sm, const int tid, const in
         if (t >= 0 && (t % MM_CHUNK) == 0) {
             const long long need_b = ebase + M_BIAS + (t + MM_CHUNK + TB);
             const long long need_c = ebase + M_BIAS + (t + MM_CHUNK + TC);
-            if (tid == 0 && predB) { while (p_ld_relaxed(predB) < need_b) p_sleep(); p_fence_acquire(); }
-            if (tid == 32 % THREADS && predC) { while (p_ld_relaxed(predC) < need_c) p_sleep(); p_fence_acquire(); }
+            if (tid == 0 && predB) wait_ge<false>(predB, need_b, p.ctrl);
+            if (tid == 32 % THREADS && predC) {
+                if (predCpeer) wait_ge<true>(predC, need_c, p.ctrl); else wait_ge<false>(predC, need_c, p.ctrl);
+            }
             p_sync();
         }
         const int a = 1 + t - sig;
@@ -201,7 +218,10 @@ LSF_DEV void mm_tile(const MmParams &p, MmSmem<CFG> &sm, const int tid, const in
                 const double df = X::sub(pn, pc);
                 acc = X::add(acc, X::mul(df, df));
             }
-            if (active) p_stcg(rowB + a, pn);
+            if (active) {
+                p_stcg(rowB + a, pn);
+                if (pushRow) p_st_peer(rowB + a + p.push_delta, pn);
+            }
         }
         // ---- deposits: own new value, and the values requested one step ago -------------------------
         if (exists) Sn[t & (MM_NSLOT - 1)] = pn;
@@ -216,11 +236,17 @@ LSF_DEV void mm_tile(const MmParams &p, MmSmem<CFG> &sm, const int tid, const in
         for (int r = 0; r < CFG::HR; ++r) { q_do[r] = hdo[r]; q_vo[r] = hvo[r]; q_dn[r] = hdn[r]; q_vn[r] = hvn[r]; }
         const bool pub = (t >= 0) && ((t % MM_CHUNK) == MM_CHUNK - 1);
         p_sync();
-        if (pub && tid == 0) { p_fence(); p_st_release(mine, ebase + M_BIAS + t); }
+        if (pub && tid == 0) {
+            p_fence(); p_st_release(mine, ebase + M_BIAS + t);
+            if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + t); }
+        }
     }
     sm.red[tid] = acc;
     p_sync();
-    if (tid == 0) { p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN); }
+    if (tid == 0) {
+        p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN);
+        if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + M_FIN); }
+    }
     for (int wdt = THREADS / 2; wdt > 0; wdt >>= 1) {
         if (tid < wdt) sm.red[tid] = X::add(sm.red[tid], sm.red[tid + wdt]);
         p_sync();
@@ -233,6 +259,13 @@ template <class CFG>
 LSF_DEV void mm_cta(const MmParams &p, MmSmem<CFG> &sm, const int tid)
 {
     if (p.ctrl->done) return;
+    if (p.halo_seq) {          // z-slab: both neighbours must have refreshed this rank's ghost planes
+        if (tid == 0) {
+            if (p.halo_need[0]) wait_ge<true>(p.halo_seq + 0, p.halo_need[0], p.ctrl);
+            if (p.halo_need[1]) wait_ge<true>(p.halo_seq + 1, p.halo_need[1], p.ctrl);
+        }
+        p_sync();
+    }
     for (;;) {
         if (tid == 0) sm.tile = (int)p_ticket(p.ticket);
         p_sync();

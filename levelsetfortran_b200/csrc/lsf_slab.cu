@@ -79,9 +79,10 @@ k_slab_exchange(const ExchArgs a)
     }
 }
 
-void slab_exchange(Grid *g, bool in_loop)
+void slab_exchange(Grid *g, bool in_loop, double *buf)
 {
     if (!sharded(g)) return;
+    if (!buf) buf = g->phi;
     const SlabGeom &sg = g->sg;
     ExchArgs a;
     memset(&a, 0, sizeof(a));
@@ -95,15 +96,15 @@ void slab_exchange(Grid *g, bool in_loop)
         SlabGeom ng;
         slab_geom(sg.NZ, sg.nranks, sg.rank - 1, ng);
         a.nbr[0] = peer_ptr(g, sg.rank - 1, g->sync);
-        a.src[0] = g->phi + (long long)sg.own_lo * g->dm.sxy;                                   // my global planes k0..k0+2
-        a.dst[0] = peer_ptr(g, sg.rank - 1, g->phi) + (long long)(sg.k0 - ng.kbase) * g->dm.sxy;   // = its upper ghost planes
+        a.src[0] = buf + (long long)sg.own_lo * g->dm.sxy;                                      // my global planes k0..k0+2
+        a.dst[0] = peer_ptr(g, sg.rank - 1, buf) + (long long)(sg.k0 - ng.kbase) * g->dm.sxy;      // = its upper ghost planes
     }
     if (sg.rank < sg.nranks - 1) {
         SlabGeom ng;
         slab_geom(sg.NZ, sg.nranks, sg.rank + 1, ng);
         a.nbr[1] = peer_ptr(g, sg.rank + 1, g->sync);
-        a.src[1] = g->phi + (long long)(sg.own_hi - SLAB_GHOST + 1) * g->dm.sxy;                // my global planes k1-3..k1-1
-        a.dst[1] = peer_ptr(g, sg.rank + 1, g->phi) + (long long)(sg.k1 - SLAB_GHOST - ng.kbase) * g->dm.sxy;   // = its lower ghost planes
+        a.src[1] = buf + (long long)(sg.own_hi - SLAB_GHOST + 1) * g->dm.sxy;                   // my global planes k1-3..k1-1
+        a.dst[1] = peer_ptr(g, sg.rank + 1, buf) + (long long)(sg.k1 - SLAB_GHOST - ng.kbase) * g->dm.sxy;      // = its lower ghost planes
     }
     k_slab_exchange<<<2 * G.num_sms, 256, 0, G.stream>>>(a);
     G.n_launch++;
@@ -249,7 +250,11 @@ int lsf_sgrid_create(lsf_grid **out, int nx, int ny, int nz, int rank, int nrank
     g->dm.sx = (long long)nx + 1;
     g->dm.sxy = g->dm.sx * ((long long)ny + 1);
     g->np = g->dm.sxy * ((long long)sg.nzl + 1);
-    const size_t fbytes = align_up(sizeof(double) * (size_t)g->np, 256);
+    // the layout of the shared allocation must be the same on every rank (peer_ptr maps a local address
+    // to a peer's by its offset): size the two fields for the thickest slab
+    int nzl_max = sg.nzl;
+    for (int r = 0; r < nranks; ++r) { SlabGeom o; slab_geom(nz, nranks, r, o); if (o.nzl > nzl_max) nzl_max = o.nzl; }
+    const size_t fbytes = align_up(sizeof(double) * (size_t)g->dm.sxy * ((size_t)nzl_max + 1), 256);
     const size_t sbytes = align_up(sizeof(SlabSync), 256);
     g->shared_bytes = sbytes + 2 * fbytes;
     cudaError_t e;

@@ -242,3 +242,16 @@ class ShardedGrid(DeviceGrid):
 
     def sync_ghosts(self):
         check(lib().lsf_sgrid_sync_ghosts(self._h))
+
+    def close(self):
+        """Collective: no rank may free its slab while a neighbour can still store into it."""
+        if getattr(self, "_h", None) is not None and self._h:
+            if self.nranks > 1:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    lib().lsf_sgrid_sync_ghosts(self._h)
+                    dist.barrier()
+            lib().lsf_grid_destroy(self._h)
+            self._h = None
+
+    __del__ = close

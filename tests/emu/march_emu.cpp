@@ -318,3 +318,80 @@ extern "C" double emu_mm_iteration(const double *A, double *B, const uint8_t *ma
     for (int q = 0; q < p.ntiles; ++q) s += partial[q];
     return s;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// The fused min/max iteration on z-slabs, all ranks concurrently (streaming halo of NEW values into the
+// downstream rank's ghost plane of B; ghost planes of A = OLD values of the neighbours, as the bulk exchange
+// between iterations leaves them).  A, B: GLOBAL arrays (B a copy of A on entry).  Returns the summed partials.
+extern "C" double emu_mm_iteration_slabs(const double *A, double *B, int nx, int ny, int NZ, int nranks, double dx, double h1,
+                                         int ncta, int order_m)
+{
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    std::vector<SlabGeom> geo(nranks);
+    for (int r = 0; r < nranks; ++r) if (!slab_geom(NZ, nranks, r, geo[r])) return -2.;
+    std::vector<std::vector<double>> lA(nranks), lB(nranks), partial(nranks);
+    std::vector<std::vector<int>> order(nranks);
+    std::vector<std::vector<long long>> progress(nranks);
+    std::vector<SlabSync> sync(nranks);
+    std::vector<MmParams> P(nranks);
+    std::vector<unsigned> ticket(nranks, 0u);
+    std::vector<Ctrl> ctrl(nranks, Ctrl{0, 0, 0, 0, 0});
+    memset(sync.data(), 0, sizeof(SlabSync) * nranks);
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        const size_t n = (size_t)sxy * (g.nzl + 1);
+        lA[r].assign(A + (size_t)g.kbase * sxy, A + (size_t)g.kbase * sxy + n);
+        lB[r].assign(B + (size_t)g.kbase * sxy, B + (size_t)g.kbase * sxy + n);
+    }
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        MmParams &p = P[r];
+        memset(&p, 0, sizeof(p));
+        mm_orient<MCFG>(p, nx, ny, g.nzl, g.kupd_lo, g.kupd_hi);
+        p.A = lA[r].data(); p.B = lB[r].data(); p.mask = nullptr;
+        p.bNB = 4.1 * dx; p.dxx = 1. / (dx * dx); p.h1 = h1;
+        partial[r].assign(p.ntiles, 0.); order[r].resize(p.ntiles); progress[r].assign(p.ntiles, 0);
+        march_fill_order(p.ntb, p.ntc, order[r].data(), order_m);
+        p.partial = partial[r].data(); p.order = order[r].data(); p.progress = progress[r].data();
+        p.ticket = &ticket[r]; p.ctrl = &ctrl[r]; p.epoch = 1;
+        if (r > 0) p.in_progress = sync[r].in_progress;
+        if (r < nranks - 1) {
+            p.push_delta = (lB[r + 1].data() + (long long)(g.kbase - geo[r + 1].kbase) * sxy) - lB[r].data();
+            p.push_progress = sync[r + 1].in_progress;
+        }
+    }
+    const int NT = MCFG::THREADS;
+    std::vector<int> nc(nranks);
+    size_t nthreads = 0;
+    for (int r = 0; r < nranks; ++r) { nc[r] = ncta < P[r].ntiles ? ncta : P[r].ntiles; nthreads += (size_t)nc[r] * NT; }
+    std::vector<std::vector<MSmem>> sm(nranks);
+    std::vector<std::vector<EmuCta>> ctas(nranks);
+    std::vector<MmThreadArg> args(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    for (int r = 0; r < nranks; ++r) {
+        sm[r] = std::vector<MSmem>(nc[r]);
+        ctas[r] = std::vector<EmuCta>(nc[r]);
+        for (int c = 0; c < nc[r]; ++c) pthread_barrier_init(&ctas[r][c].bar, nullptr, NT);
+    }
+    size_t q = 0;
+    for (int r = 0; r < nranks; ++r)
+        for (int c = 0; c < nc[r]; ++c)
+            for (int t = 0; t < NT; ++t, ++q) {
+                MmThreadArg &a = args[q];
+                a.p = &P[r]; a.sm = &sm[r][c]; a.cta = &ctas[r][c]; a.tid = t;
+                if (pthread_create(&th[q], &attr, mm_thread_main, &a) != 0) return -1.;
+            }
+    for (size_t i = 0; i < th.size(); ++i) pthread_join(th[i], nullptr);
+    double s = 0.;
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        for (int c = 0; c < nc[r]; ++c) pthread_barrier_destroy(&ctas[r][c].bar);
+        if (ctrl[r].status != 0) return -3.;
+        memcpy(B + (size_t)g.k0 * sxy, lB[r].data() + (size_t)g.own_lo * sxy, sizeof(double) * (size_t)sxy * (g.k1 - g.k0));
+        for (int i = 0; i < P[r].ntiles; ++i) s += partial[r][i];
+    }
+    return s;
+}

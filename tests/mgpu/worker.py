@@ -81,8 +81,10 @@ def main():
         G.signSearch(g["xLo"], DX, X, E, g["box"])
         sign = G.download()
         rc, n, hist = G.reinit(15, DX, 0.1 * g["dxx"], tol=0.0)
-        return sign, G.download()
-    sign_ref, phi_ref = whole(shape, run_whole2)
+        phi = G.download()
+        rc, n, hist = G.minMaxFlow(13, DX, 0.01 * g["dxx"], tol=0.0)
+        return sign, phi, G.download(), n, hist
+    sign_ref, phi_ref, mm_ref, mm_n, mm_hist = whole(shape, run_whole2)
     SG = ShardedGrid(g["nx"], g["ny"], g["nz"])
     SG.fill(1.0)
     SG.signSearch(g["xLo"], DX, X, E, g["box"])
@@ -93,6 +95,43 @@ def main():
     assert np.array_equal(phi, phi_ref[:, :, SG.k0:SG.k1])
     nb, sb = SG.narrowBand(DX)
     assert np.array_equal(nb, (np.abs(phi) < 4.1 * DX).astype(np.int32))
+    # min/max flow (set3d.f90:394-462) on the slabs: bit-exact, same history
+    rc, n2, hist2 = SG.minMaxFlow(13, DX, 0.01 * g["dxx"], tol=0.0)
+    mm = SG.download()
+    assert n2 == mm_n and np.array_equal(mm, mm_ref[:, :, SG.k0:SG.k1]), \
+        f"rank {rank}: sharded min/max differs, max {np.abs(mm - mm_ref[:, :, SG.k0:SG.k1]).max():.3e}"
+    assert np.allclose(hist2, mm_hist, rtol=1e-12, atol=0) and (nb == 1).any()
+    SG.close()
+    checks += 1
+
+    # min/max on a noisy distance field with a wide band crossing the slab boundaries, tolerance exit
+    shape = (44, 38, 18 * world + 7)
+    from conftest import dist_field
+    p0 = dist_field(shape, seed=21)
+
+    def run_whole3(G):
+        G.upload(p0)
+        rc, n, hist0 = G.minMaxFlow(40, DX, 1.0e-4, tol=0.0)
+        full0 = G.download()
+        tol = 0.5 * (hist0[17] + hist0[18]) if hist0[18] < hist0[:18].min() else 0.0
+        G.upload(p0)
+        rc, n, hist = G.minMaxFlow(40, DX, 1.0e-4, tol=tol)
+        return tol, n, hist, G.download(), hist0, full0
+    tol3, n3, h3, ref3, h0, full0 = whole(shape, run_whole3)
+    SG = ShardedGrid(shape[0] - 1, shape[1] - 1, shape[2] - 1)
+    SG.upload(np.asfortranarray(p0[:, :, SG.k0:SG.k1]))
+    rc, n5, h5 = SG.minMaxFlow(40, DX, 1.0e-4, tol=0.0)
+    got0 = SG.download()
+    bad = np.argwhere(got0 != full0[:, :, SG.k0:SG.k1])
+    assert len(bad) == 0, f"rank {rank}: 40 iterations: {len(bad)} cells differ, first {bad[:5].tolist()}, k0 {SG.k0}, max {np.abs(got0 - full0[:, :, SG.k0:SG.k1]).max():.3e}"
+    assert np.allclose(h0, h5, rtol=1e-12, atol=0), f"rank {rank}: hist {h0[:4]} {h0[16:20]} vs {h5[:4]} {h5[16:20]}"
+    SG.upload(np.asfortranarray(p0[:, :, SG.k0:SG.k1]))
+    rc, n4, h4 = SG.minMaxFlow(40, DX, 1.0e-4, tol=tol3)
+    got = SG.download()
+    bad = np.argwhere(got != ref3[:, :, SG.k0:SG.k1])
+    assert n4 == n3, f"rank {rank}: min/max exit {n4} != {n3} (tol {tol3})"
+    assert len(bad) == 0, f"rank {rank}: {len(bad)} cells differ, first (i,j,k_local) {bad[:5].tolist()}, k0 {SG.k0}, max {np.abs(got - ref3[:, :, SG.k0:SG.k1]).max():.3e}"
+    assert np.allclose(h3, h4, rtol=1e-12, atol=0), f"rank {rank}: hist {h3[:4]} vs {h4[:4]}"
     SG.close()
     checks += 1
 

@@ -28,6 +28,8 @@ def emu():
                                         C.c_int, C.c_int, C.c_int]
     L.emu_march_multi_slabs.restype = C.c_double
     L.emu_march_multi_slabs.argtypes = [dp, dp] + [C.c_int] * 6 + [C.c_double, C.c_double] + [C.c_int] * 4
+    L.emu_mm_iteration_slabs.restype = C.c_double
+    L.emu_mm_iteration_slabs.argtypes = [dp, dp] + [C.c_int] * 4 + [C.c_double, C.c_double, C.c_int, C.c_int]
     L.emu_mm_iteration.restype = C.c_double
     L.emu_mm_iteration.argtypes = [dp, dp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     return L
@@ -119,6 +121,26 @@ def test_minmax_march_iteration_is_bit_exact(emu, oracle, shape, ncta):
     assert np.array_equal(buf[0], a)                     # 6 iterations: result back in buffer 0
     assert np.allclose(sums, hist, rtol=1e-12, atol=0)
     assert (np.abs(p0) < 4.1 * 0.05).sum() > 100         # the band was not empty
+
+
+@pytest.mark.parametrize("shape,nranks,ncta,m", [((22, 21, 40), 2, 2, 1), ((20, 36, 51), 3, 2, 2), ((12, 20, 64), 8, 1, 8)])
+def test_minmax_march_slabs_bit_exact(emu, oracle, shape, nranks, ncta, m):
+    """The fused min/max iteration on z-slabs (streaming NEW-value halo into the downstream rank's ghost
+    plane) against the oracle's literal loop on the whole grid: bit-exact, several iterations."""
+    p0 = dist_field(shape, seed=6)
+    nx, ny, nz = (s - 1 for s in shape)
+    a = p0.copy(order="F")
+    st, n, hist, nbo, sbo = oracle.minmax(a, 4, 0.05, 1.0e-4, tol=1e-30)
+    assert n == 4
+    buf = [p0.copy(order="F"), p0.copy(order="F")]
+    sums = []
+    for it in range(1, 5):
+        A, B = buf[(it - 1) & 1], buf[it & 1]
+        s = emu.emu_mm_iteration_slabs(A.ctypes.data_as(dp), B.ctypes.data_as(dp), nx, ny, nz, nranks, 0.05, 1.0e-4, ncta, m)
+        assert s >= 0
+        sums.append(np.sqrt(s / (nx * ny * nz)))
+    assert np.array_equal(buf[0], a)
+    assert np.allclose(sums, hist, rtol=1e-12, atol=0)
 
 
 def test_minmax_march_given_mask(emu, oracle):
