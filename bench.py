@@ -241,7 +241,7 @@ def run_gpu(args):
 
     # ---- companion measurements on the same resident grid (not part of `value`): min/max flow ----
     mm = None
-    if args.minmax_iters > 0 and world == 1:
+    if args.minmax_iters > 0:
         rc, n_mm, hist_mm = G.minMaxFlow(3, DX, 0.01 * g["dxx"], tol=0.0)          # warm-up
         barrier()
         rc, n_mm, hist_mm = G.minMaxFlow(args.minmax_iters, DX, 0.01 * g["dxx"], tol=0.0)
