@@ -2,6 +2,8 @@
 // cross-check schedule), boundary extrapolation, RMS reduction, loop control, narrow band,
 // min/max flow and the inside/outside sign search.  The production reinit schedule (skewed
 // x-marching column tiles) lives in lsf_march.cu.
+#include <stdlib.h>
+
 #include "lsf_internal.cuh"
 
 namespace lsf {
@@ -447,6 +449,115 @@ k_sign_search(double *__restrict__ phi, Dims dm, double x0, double y0, double z0
     phi[i + dm.sx * j + dm.sxy * (k - kbase)] = __ddiv_rn(pS, den);   // k is the GLOBAL plane (z-slab: local plane k - kbase)
 }
 
+// K1 (production): the same search with exact tile-level culling of the triangle list.
+// A CTA owns a block of SB_I x SB_J x SB_K grid points with centre P and half-diagonal rho.
+//   pass 1: d_min = min over all centroids of |c - P| (cooperative, plain fp64);
+//   pass 2: every point p of the block has its nearest centroid within |c - p| <= d_min + rho, hence
+//           within |c - P| <= d_min + 2 rho: only those triangles can win or tie.  They are streamed
+//           through shared memory in ASCENDING index order (ballot compaction keeps the order), and each
+//           thread runs the reference's loop -- same explicitly rounded arithmetic, strict '<', first index
+//           wins -- over that sub-list.  A relative margin of 1e-9 on the bound covers the rounding of the
+//           filter itself and every candidate that could tie after the rounded sqrt, so the result is
+//           bit-identical to the brute-force loop (tests: against k_sign_search and the oracle).
+// Cost per point drops from nElem to nElem/128 + |candidates| distance evaluations.
+constexpr int SB_I = 8, SB_J = 8, SB_K = 4, SB_THREADS = SB_I * SB_J * SB_K;
+
+__global__ void __launch_bounds__(SB_THREADS)
+k_sign_search_tiled(double *__restrict__ phi, Dims dm, double x0, double y0, double z0, double dx,
+                    const double *__restrict__ surfX, int nNode, const int32_t *__restrict__ surfElem, int nElem,
+                    const double *__restrict__ cen, int im, int jm, int km, int ni, int nj, int nk, int kbase,
+                    int nbi, int nbj)
+{
+    __shared__ double sc[3][SB_THREADS];
+    __shared__ int sidx[SB_THREADS];
+    __shared__ double sred[SB_THREADS / 32];
+    __shared__ int swcnt[SB_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int bi = blockIdx.x % nbi, bj = (blockIdx.x / nbi) % nbj, bk = blockIdx.x / (nbi * nbj);
+    const int li = tid % SB_I, lj = (tid / SB_I) % SB_J, lk = tid / (SB_I * SB_J);
+    const int i = im + bi * SB_I + li, j = jm + bj * SB_J + lj, k = km + bk * SB_K + lk;
+    const bool live = (i < im + ni) && (j < jm + nj) && (k < km + nk);
+    const double gX = __dadd_rn(x0, __dmul_rn((double)i, dx));       // set3d.f90:168-170
+    const double gY = __dadd_rn(y0, __dmul_rn((double)j, dx));
+    const double gZ = __dadd_rn(z0, __dmul_rn((double)k, dx));
+    // block centre and half-diagonal (of the full block: an upper bound for clipped blocks)
+    const double PX = x0 + (im + bi * SB_I + 0.5 * (SB_I - 1)) * dx;
+    const double PY = y0 + (jm + bj * SB_J + 0.5 * (SB_J - 1)) * dx;
+    const double PZ = z0 + (km + bk * SB_K + 0.5 * (SB_K - 1)) * dx;
+    const double rho = 0.5 * dx * sqrt((double)((SB_I - 1) * (SB_I - 1) + (SB_J - 1) * (SB_J - 1) + (SB_K - 1) * (SB_K - 1)));
+    // ---- pass 1: distance of the nearest centroid to the block centre -----------------------------
+    double m2 = __longlong_as_double(0x7ff0000000000000LL);
+    for (int n = tid; n < nElem; n += SB_THREADS) {
+        const double ex = cen[n] - PX, ey = cen[n + (long long)nElem] - PY, ez = cen[n + 2 * (long long)nElem] - PZ;
+        m2 = fmin(m2, ex * ex + ey * ey + ez * ez);
+    }
+    for (int o = 16; o > 0; o >>= 1) m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    if (lane == 0) sred[wid] = m2;
+    __syncthreads();
+    m2 = sred[0];
+    for (int w = 1; w < SB_THREADS / 32; ++w) m2 = fmin(m2, sred[w]);
+    const double bound = (sqrt(m2) + 2.0 * rho) * (1.0 + 1.0e-9);
+    const double bound2 = bound * bound;
+    // ---- pass 2: stream the candidates (ascending index) through shared memory --------------------
+    double minD = 100000., qbest = __longlong_as_double(0x7ff0000000000000LL);
+    int fN = 0;
+    int fill = 0;                                     // entries waiting in the shared buffer
+    for (int base = 0; base < nElem; base += SB_THREADS) {
+        const int n = base + tid;
+        double cx = 0., cy = 0., cz = 0.;
+        bool cand = false;
+        if (n < nElem) {
+            cx = cen[n]; cy = cen[n + (long long)nElem]; cz = cen[n + 2 * (long long)nElem];
+            const double ex = cx - PX, ey = cy - PY, ez = cz - PZ;
+            cand = (ex * ex + ey * ey + ez * ez) <= bound2;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) swcnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int w = 0; w < SB_THREADS / 32; ++w) { const int cw = swcnt[w]; if (w < wid) off += cw; tot += cw; }
+        // flush first if the newcomers do not fit behind what is already buffered
+        if (fill + tot > SB_THREADS) {
+            for (int r = 0; r < fill; ++r) {
+                const double ex = __dsub_rn(sc[0][r], gX), ey = __dsub_rn(sc[1][r], gY), ez = __dsub_rn(sc[2][r], gZ);
+                const double q = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                if (q < qbest) {
+                    const double dis = __dsqrt_rn(q);
+                    if (dis < minD) { minD = dis; qbest = q; fN = sidx[r]; }
+                }
+            }
+            fill = 0;
+            __syncthreads();
+        }
+        if (cand) {
+            const int pos = fill + off + __popc(bal & ((1u << lane) - 1u));
+            sc[0][pos] = cx; sc[1][pos] = cy; sc[2][pos] = cz; sidx[pos] = n;
+        }
+        fill += tot;
+        __syncthreads();
+    }
+    for (int r = 0; r < fill; ++r) {
+        const double ex = __dsub_rn(sc[0][r], gX), ey = __dsub_rn(sc[1][r], gY), ez = __dsub_rn(sc[2][r], gZ);
+        const double q = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+        if (q < qbest) {
+            const double dis = __dsqrt_rn(q);
+            if (dis < minD) { minD = dis; qbest = q; fN = sidx[r]; }
+        }
+    }
+    if (!live) return;
+    const int n1 = surfElem[fN] - 1, n2 = surfElem[fN + nElem] - 1, n3 = surfElem[fN + 2 * (long long)nElem] - 1;
+    const double *X = surfX, *Y = surfX + nNode, *Z = surfX + 2 * (long long)nNode;
+    const double A1 = __dsub_rn(X[n1], gX), A2 = __dsub_rn(Y[n1], gY), A3 = __dsub_rn(Z[n1], gZ);
+    const double B1 = __dsub_rn(X[n2], gX), B2 = __dsub_rn(Y[n2], gY), B3 = __dsub_rn(Z[n2], gZ);
+    const double C1 = __dsub_rn(X[n3], gX), C2 = __dsub_rn(Y[n3], gY), C3 = __dsub_rn(Z[n3], gZ);
+    const double pSx = __dsub_rn(__dmul_rn(A2, B3), __dmul_rn(A3, B2));
+    const double pSy = -__dsub_rn(__dmul_rn(A1, B3), __dmul_rn(B1, A3));
+    const double pSz = __dsub_rn(__dmul_rn(A1, B2), __dmul_rn(B1, A2));
+    const double pS = -__dadd_rn(__dadd_rn(__dmul_rn(pSx, C1), __dmul_rn(pSy, C2)), __dmul_rn(pSz, C3));
+    const double den = __dsqrt_rn(__dadd_rn(__dmul_rn(pS, pS), __dmul_rn(__dmul_rn(dx, dx), 1.)));
+    phi[i + dm.sx * j + dm.sxy * (k - kbase)] = __ddiv_rn(pS, den);
+}
+
 void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode,
                       const int32_t *d_surfElem, int nElem, double *d_cen,
                       int im, int ip, int jm, int jp, int km, int kp)
@@ -459,8 +570,15 @@ void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_s
     if (kp < km) return;
     const int ni = ip - im + 1, nj = jp - jm + 1, nk = kp - km + 1;
     const long long npts = (long long)ni * nj * nk;
-    k_sign_search<<<(unsigned)((npts + SIGN_TILE - 1) / SIGN_TILE), SIGN_TILE, 0, G.stream>>>(
-        g->phi, g->dm, xLo[0], xLo[1], xLo[2], dx, d_surfX, nNode, d_surfElem, nElem, d_cen, im, jm, km, ni, nj, nk, g->sg.kbase);
+    const bool brute = getenv("LSF_SIGN_BRUTE") != nullptr;            // cross-check: the un-culled kernel
+    const long long nbi = (ni + SB_I - 1) / SB_I, nbj = (nj + SB_J - 1) / SB_J, nbk = (nk + SB_K - 1) / SB_K;
+    if (brute || nbi * nbj * nbk > 0x7fffffffLL)
+        k_sign_search<<<(unsigned)((npts + SIGN_TILE - 1) / SIGN_TILE), SIGN_TILE, 0, G.stream>>>(
+            g->phi, g->dm, xLo[0], xLo[1], xLo[2], dx, d_surfX, nNode, d_surfElem, nElem, d_cen, im, jm, km, ni, nj, nk, g->sg.kbase);
+    else
+        k_sign_search_tiled<<<(unsigned)(nbi * nbj * nbk), SB_THREADS, 0, G.stream>>>(
+            g->phi, g->dm, xLo[0], xLo[1], xLo[2], dx, d_surfX, nNode, d_surfElem, nElem, d_cen, im, jm, km, ni, nj, nk, g->sg.kbase,
+            (int)nbi, (int)nbj);
     G.n_launch++;
 }
 

@@ -97,11 +97,14 @@ constexpr long long M_BIAS = 1000;
 constexpr long long M_SPIN_LIMIT = 40000000; // polls before a flag wait gives up (tens of seconds): a lost peer must not hang the GPU
 constexpr int M_ERR_TIMEOUT = -4;            // = LSF_ERR_TIMEOUT (include/lsf_b200.h)
 
-// Tile geometry.  TB x TC rows per CTA (oriented b x c), one thread per row.
-template <int TB_, int TC_>
+// Tile geometry.  TB x TC rows per CTA (oriented b x c), R rows per thread.
+#ifndef LSF_ROWS
+#define LSF_ROWS 1
+#endif
+template <int TB_, int TC_, int R_ = LSF_ROWS>
 struct MarchCfg {
-    static constexpr int TB = TB_, TC = TC_;
-    static constexpr int THREADS = TB * TC;
+    static constexpr int TB = TB_, TC = TC_, R = R_;          // R rows (cells per step) per thread
+    static constexpr int THREADS = TB * TC / R;
     static constexpr int SW = TB + 2 * M_H, SH = TC + 2 * M_H;
     // pitch of one c-row of positions, in doubles; for TB = 8 a warp spans 4 c-rows and the pitch
     // is padded to 8 (mod 16) doubles so that the two rows of a half-warp hit disjoint banks
@@ -223,23 +226,60 @@ inline void march_fill_order(int ntb, int ntc, int *order, int m = 1)
         }
 }
 
+// One cell of row `Sown` at step t: gather the 19 stencil values from the ring (orientation resolved at
+// compile time) and update.  HI: the caller knows the high-order branch applies (compile-time), else `hi`.
+template <class AR, bool FA, bool FB, bool FC, class CFG, bool HI>
+LSF_DEV double march_cell(const double *Sown, int t, double ps, bool hi, const CellConst &cc, bool &sens, double &df2)
+{
+    constexpr int W = M_SLOTW, RP = CFG::RP;
+    const double *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
+    double vx[7], vy[7], vz[7];
+#pragma unroll
+    for (int m = -3; m <= 3; ++m) {
+        vx[FA ? 3 - m : 3 + m] = Wn[3 + m];
+        if (m != 0) {
+            vy[FB ? 3 - m : 3 + m] = Wn[m * W + 3 + m];
+            vz[FC ? 3 - m : 3 + m] = Wn[m * RP + 3 + m];
+        }
+    }
+    vy[3] = vx[3]; vz[3] = vx[3];
+    double g[3], gM;
+    const double pn = reinit_cell<AR>(vx, vy, vz, ps, HI ? true : hi, cc, g, gM, sens);
+    const double df = pn - vx[3];
+    df2 = df * df;
+    return pn;
+}
+
 template <class AR, bool FA, bool FB, bool FC, class CFG>
 LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K)
 {
-    constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP;
+    constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP, R = CFG::R;
     constexpr int W = M_SLOTW;
-    const int tb = tid % TB, tc = tid / TB;
-    const int b = 1 + J * TB + tb, c = p.c_lo + K * TC + tc;
-    const bool rowValid = (b <= p.ny) && (c <= p.c_max);
-    const bool compValid = (b <= p.ny - 1) && (c <= p.c_hi);
-    const bool pushRow = (p.push_delta != 0) && compValid && (c > p.c_hi - M_H);
-    const bool pushUpRow = (p.push_up_delta != 0) && compValid && (c < p.c_lo + M_H);
-    const bool hiBC = (b >= p.lo_b) && (b <= p.hi_b) && (c >= p.lo_c) && (c <= p.hi_c);
-    const int sig = tb + tc + M_H;
-    const long long rowoff = p.off0 + (long long)b * p.sb + (long long)c * p.sc;
-    double *rowp = p.phi + (rowValid ? rowoff : 0);
-    const double *rowS = p.phiS + (rowValid ? rowoff : 0);
-    double *const Sown = sm.S + (tc + M_H) * RP + (tb + M_H) * W;
+    // thread tid owns rows tid, tid + THREADS, ... of the tile (row q: tb = q % TB, tc = q / TB); all rows of a
+    // step lie on one hyperplane, so the R cells a thread updates per step are independent of each other
+    bool rowValid[R], compValid[R], pushRow[R], pushUpRow[R], hiBC[R];
+    int sig[R];
+    double *Sown[R];
+    double *pOut[R];
+    const double *pSgn[R];
+    constexpr long long SA = FA ? -1 : 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int q = tid + r * THREADS;
+        const int tb = q % TB, tc = q / TB;
+        const int b = 1 + J * TB + tb, c = p.c_lo + K * TC + tc;
+        rowValid[r] = (b <= p.ny) && (c <= p.c_max);
+        compValid[r] = (b <= p.ny - 1) && (c <= p.c_hi);
+        pushRow[r] = (p.push_delta != 0) && compValid[r] && (c > p.c_hi - M_H);
+        pushUpRow[r] = (p.push_up_delta != 0) && compValid[r] && (c < p.c_lo + M_H);
+        hiBC[r] = (b >= p.lo_b) && (b <= p.hi_b) && (c >= p.lo_c) && (c <= p.hi_c);
+        sig[r] = tb + tc + M_H;
+        const long long rowoff = rowValid[r] ? p.off0 + (long long)b * p.sb + (long long)c * p.sc : 0;
+        Sown[r] = sm.S + (tc + M_H) * RP + (tb + M_H) * W;
+        // running pointers: cell a of the own row (phi, phiS), advanced by one cell per step (a = 1 + t - sig)
+        pOut[r] = p.phi + rowoff + (long long)(1 - M_LOOK - sig[r]) * SA;
+        pSgn[r] = p.phiS + rowoff + (long long)(1 - M_LOOK - sig[r]) * SA;
+    }
 
     // halo duty: thread q feeds halo rows q, q+THREADS, ... (< NHALO)
     bool hvalid[CFG::HR], hlow[CFG::HR];
@@ -299,17 +339,13 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
     long long dbg_wait = 0, dbg_t0 = 0, dbg_c0 = 0;
     if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); dbg_c0 = clock64(); }
 #endif
-    // running pointers: cell a of the own row (phi, phiS) and cell ah of each halo row, advanced by
-    // one cell per step (a = 1 + t - sig)
-    constexpr long long SA = FA ? -1 : 1;
-    double *pOut = rowp + (long long)(1 - M_LOOK - sig) * SA;
-    const double *pSgn = rowS + (long long)(1 - M_LOOK - sig) * SA;
+    // cell ah of each halo row, advanced by one cell per step
     const double *hp[CFG::HR];
 #pragma unroll
     for (int r = 0; r < CFG::HR; ++r)
         hp[r] = hrow[r] + (long long)(1 - M_LOOK + (hlow[r] ? 0 : M_LOOK) - hsig[r]) * SA;
 
-    for (int t = -M_LOOK; t <= p.tend; ++t, pOut += SA, pSgn += SA) {
+    for (int t = -M_LOOK; t <= p.tend; ++t) {
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
         if (t >= 0 && (t % M_CHUNK) == 0) {
             const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + TB);
@@ -328,15 +364,21 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
 #endif
         }
         p_emu_hook(tid == 0 && t == 6);
-        const int a = 1 + t - sig;
         // ---- (1) issue the global loads of this step --------------------------------------
-        const int a4 = a + M_LOOK;
-        const bool ldLook = rowValid && (a4 >= 0) && (a4 <= p.nx);
-        double la = 0.;
-        if (ldLook) la = p_ldcg(pOut + M_LOOK * SA);
-        const bool active = compValid && (a >= 1) && (a <= p.nx - 1);
-        double ps = 0.;
-        if (active) ps = p_ldcg(pSgn);
+        bool ldLook[R], active[R], hi[R];
+        double la[R], ps[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int a = 1 + t - sig[r];
+            const int a4 = a + M_LOOK;
+            ldLook[r] = rowValid[r] && (a4 >= 0) && (a4 <= p.nx);
+            la[r] = 0.;
+            if (ldLook[r]) la[r] = p_ldcg(pOut[r] + M_LOOK * SA);
+            active[r] = compValid[r] && (a >= 1) && (a <= p.nx - 1);
+            ps[r] = 0.;
+            if (active[r]) ps[r] = p_ldcg(pSgn[r]);
+            hi[r] = hiBC[r] && (a >= p.lo_a) && (a <= p.hi_a);
+        }
         bool hdep[CFG::HR];
         double hv[CFG::HR];
         int hh[CFG::HR];
@@ -350,34 +392,50 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             }
             hp[r] += SA;
         }
-        // ---- (2) cell update ----------------------------------------------------------------
-        double pn = 0.;
-        if (active) {
-            const double *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
-            double vx[7], vy[7], vz[7];
+        // ---- (2) cell updates ---------------------------------------------------------------
+        double pn[R];
+        bool sens = false;
+        bool fused = false;
+        if (R == 2) {
+            // both cells on the high-order branch (the bulk of the grid): one straight-line block, so the two
+            // independent dependence chains interleave on the FP64 pipe
+            if (active[0] && active[R - 1] && hi[0] && hi[R - 1]) {
+                bool s0, s1;
+                double d0, d1;
+                pn[0] = march_cell<AR, FA, FB, FC, CFG, true>(Sown[0], t, ps[0], true, p.cc, s0, d0);
+                pn[R - 1] = march_cell<AR, FA, FB, FC, CFG, true>(Sown[R - 1], t, ps[R - 1], true, p.cc, s1, d1);
+                sens = s0 || s1;
+                acc += d0;
+                acc += d1;
+                fused = true;
+            }
+        }
+        if (!fused) {
 #pragma unroll
-            for (int m = -3; m <= 3; ++m) {
-                vx[FA ? 3 - m : 3 + m] = Wn[3 + m];
-                if (m != 0) {
-                    vy[FB ? 3 - m : 3 + m] = Wn[m * W + 3 + m];
-                    vz[FC ? 3 - m : 3 + m] = Wn[m * RP + 3 + m];
+            for (int r = 0; r < R; ++r) {
+                pn[r] = 0.;
+                if (active[r]) {
+                    bool s0;
+                    double d0;
+                    pn[r] = march_cell<AR, FA, FB, FC, CFG, false>(Sown[r], t, ps[r], hi[r], p.cc, s0, d0);
+                    sens = sens || s0;
+                    acc += d0;
                 }
             }
-            vy[3] = vx[3]; vz[3] = vx[3];
-            const bool hi = hiBC && (a >= p.lo_a) && (a <= p.hi_a);
-            double g[3], gM;
-            bool sens;
-            pn = reinit_cell<AR>(vx, vy, vz, ps, hi, p.cc, g, gM, sens);
-            if (sens) p.ctrl->guard = 1;
-            const double df = pn - vx[3];
-            acc += df * df;
-            p_stcg(pOut, pn);
-            if (pushRow) p_st_peer(pOut + p.push_delta, pn);
-            if (pushUpRow) p_st_peer(pOut + p.push_up_delta, pn);
         }
-        // ---- (3) deposits into the slot ring (each value to slot h&7 and its double) ----------
-        if (active) { double *d = Sown + (t & (M_NSLOT - 1)); d[0] = pn; d[M_NSLOT] = pn; }
-        if (ldLook) { double *d = Sown + ((t + M_LOOK) & (M_NSLOT - 1)); d[0] = la; d[M_NSLOT] = la; }
+        if (sens) p.ctrl->guard = 1;
+        // ---- (3) stores and deposits into the slot ring (each value to slot h&7 and its double) -------
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (active[r]) {
+                p_stcg(pOut[r], pn[r]);
+                if (pushRow[r]) p_st_peer(pOut[r] + p.push_delta, pn[r]);
+                if (pushUpRow[r]) p_st_peer(pOut[r] + p.push_up_delta, pn[r]);
+                double *d = Sown[r] + (t & (M_NSLOT - 1)); d[0] = pn[r]; d[M_NSLOT] = pn[r];
+            }
+            if (ldLook[r]) { double *d = Sown[r] + ((t + M_LOOK) & (M_NSLOT - 1)); d[0] = la[r]; d[M_NSLOT] = la[r]; }
+            pOut[r] += SA; pSgn[r] += SA;
+        }
 #pragma unroll
         for (int r = 0; r < CFG::HR; ++r)
             if (hdep[r]) { double *d = hS[r] + (hh[r] & (M_NSLOT - 1)); d[0] = hv[r]; d[M_NSLOT] = hv[r]; }

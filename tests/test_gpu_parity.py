@@ -55,6 +55,27 @@ def test_sign_search_bit_exact_synthetic(S, oracle):
     assert np.array_equal(a, b) and (a < 0).any() and (a == 1.0).any()
 
 
+def test_sign_search_culling_is_exact_on_a_dense_mesh(S):
+    """The tile-culled search (k_sign_search_tiled) against the brute-force kernel on the 20k-triangle sphere of
+    BASELINE config 3 at reduced grid size: near the centre almost every centroid is a near-tie, so the
+    candidate lists are long and the first-index rule is exercised; must be bit-identical."""
+    import os
+    from levelsetfortran_b200 import stl
+    X, E = stl.dedup_nodes(stl.sphere_config(72, DX))
+    g = stl.grid_from_surface(X, DX)
+    shape = (g["nx"] + 1, g["ny"] + 1, g["nz"] + 1)
+    a = np.ones(shape, order="F")
+    b = np.ones(shape, order="F")
+    S.signSearch(a, g["nx"], g["ny"], g["nz"], g["xLo"], DX, X, E, g["box"])
+    os.environ["LSF_SIGN_BRUTE"] = "1"
+    try:
+        S.signSearch(b, g["nx"], g["ny"], g["nz"], g["xLo"], DX, X, E, g["box"])
+    finally:
+        del os.environ["LSF_SIGN_BRUTE"]
+    assert np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b))
+    assert (a < 0).any() and (a > 0).any() and len(E) > 15000
+
+
 # ------------------------------------------------------------------------------------ reinit
 @pytest.mark.parametrize("plane", [False, True], ids=["march", "plane"])
 @pytest.mark.parametrize("shape", [(22, 21, 23), (40, 38, 36), (19, 50, 33), (35, 18, 70), (6, 5, 7), (3, 3, 3)])

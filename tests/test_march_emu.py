@@ -15,11 +15,20 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 dp = C.POINTER(C.c_double)
 
 
-@pytest.fixture(scope="module")
-def emu():
-    so = os.path.join(EMU_DIR, "libmarch_emu.so")
+def _rows_default():
+    """The R (rows per thread) the GPU library is built with: LSF_ROWS in csrc/Makefile."""
+    import re
+    mk = open(os.path.join(ROOT, "levelsetfortran_b200", "csrc", "Makefile")).read()
+    m = re.search(r"-DLSF_ROWS=(\d+)", mk)
+    return int(m.group(1)) if m else 1
+
+
+@pytest.fixture(scope="module", params=sorted({1, 2, _rows_default()}), ids=lambda r: f"rows{r}")
+def emu(request):
+    so = os.path.join(EMU_DIR, f"libmarch_emu_r{request.param}.so")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                           "-std=c++17", "-Wno-unknown-pragmas", "-o", so, os.path.join(EMU_DIR, "march_emu.cpp")])
+                           "-std=c++17", "-Wno-unknown-pragmas", f"-DLSF_ROWS={request.param}", "-o", so,
+                           os.path.join(EMU_DIR, "march_emu.cpp")])
     L = C.CDLL(so)
     L.emu_march_sweep.restype = C.c_double
     L.emu_march_sweep.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
