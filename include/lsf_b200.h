@@ -49,6 +49,10 @@ extern "C" {
 #define LSF_SCHED_MARCH 0 /* skewed x-marching column tiles, one launch per sweep (default) */
 #define LSF_SCHED_PLANE 1 /* one launch per global hyperplane; simple cross-check path */
 
+/* algorithm of the min/max flow iteration (all are exact re-orderings of set3d.f90:399-431, bit-identical) */
+#define LSF_MINMAX_LIST 0  /* (default) active list of the cells that can still change, order-free speculative update */
+#define LSF_MINMAX_MARCH 1 /* whole-grid skewed march, one fused kernel per iteration; cross-check path */
+
 typedef struct lsf_grid lsf_grid; /* a device-resident phi(0:nx,0:ny,0:nz) plus work arrays */
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -58,6 +62,8 @@ const char *lsf_last_error(void);
 int lsf_set_arith(int arith);      /* LSF_ARITH_*  */
 int lsf_last_arith(void);          /* arithmetic the most recent lsf_*reinit call finished in (FAST or EXACT) */
 int lsf_set_sched(int sched);      /* LSF_SCHED_*  */
+int lsf_set_minmax_algo(int algo); /* LSF_MINMAX_* (used with LSF_SCHED_MARCH) */
+long long lsf_last_minmax_active(void); /* LSF_MINMAX_LIST: cells on the active list of the most recent min/max call (this rank) */
 /* Timing of the kernels of the most recent lsf_*reinit / lsf_*minmax / lsf_*sign_init call,
  * CUDA events on the library's own stream: total ms, number of kernel launches. */
 int lsf_last_timing(double *kernel_ms, int *n_launches);

@@ -21,6 +21,7 @@ LSF_ERR_CUDA, LSF_ERR_ARG, LSF_ERR_BAND_ON_BOUNDARY, LSF_ERR_TIMEOUT = -1, -2, -
 IPC_HANDLE_BYTES = 64
 ARITH_FAST, ARITH_EXACT, ARITH_AUTO = 0, 1, 2
 SCHED_MARCH, SCHED_PLANE = 0, 1
+MINMAX_LIST, MINMAX_MARCH = 0, 1
 
 # every symbol include/lsf_b200.h declares: name -> (restype, argtypes)
 _I, _D, _V = C.c_int, C.c_double, C.c_void_p
@@ -31,6 +32,8 @@ SYMBOLS = {
     "lsf_set_arith": (_I, [_I]),
     "lsf_last_arith": (_I, []),
     "lsf_set_sched": (_I, [_I]),
+    "lsf_set_minmax_algo": (_I, [_I]),
+    "lsf_last_minmax_active": (C.c_longlong, []),
     "lsf_last_timing": (_I, [c_double_p, c_int_p]),
     "lsf_set_profile": (_I, [_I]),
     "lsf_last_sweep_timing": (_I, [c_double_p, c_int_p]),

@@ -321,6 +321,56 @@ static int minmax_core_march(Grid *g, int iter, double dx, double h1, double tol
     return LSF_OK;
 }
 
+// Active-list schedule (production, lsf_mm_list.cuh): the set of cells that can ever change is compacted once,
+// every iteration is an order-free pass over that list plus a (normally empty) settle step.
+static int minmax_core_list(Grid *g, int iter, double dx, double h1, double tol, bool mask_given, Ctrl *hc_out)
+{
+    int rc = mml_prepare(g, mask_given ? g->mask : nullptr, dx);
+    if (rc) return rc;
+    Ctrl hc = {0, 0, 1, 0, 0};
+    if (iter >= 1) {
+        launch_mm_check_boundary(g, mask_given ? g->mask : nullptr, dx, !mask_given || iter >= 2);
+        if (sharded(g)) launch_finalize_slab(g, 0, 1, -1., 1);          // all ranks agree on the verdict -- and have all
+                                                                        // finished setting up phiN before anyone pushes into it
+        rc = read_ctrl(g, &hc);
+        if (rc) return rc;
+        if (hc.status < 0) { *hc_out = hc; return LSF_OK; }
+        if (sharded(g)) {
+            Ctrl init = {0, 0, 1, 0, 0};
+            LSF_CUDA(cudaMemcpyAsync(g->ctrl, &init, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
+        }
+    }
+    const int npart = mml_npart();
+    double *buf[2] = {g->phi, g->phiN};                                 // buf[0] = phi_0, buf[1] = copy of it
+    for (int n = 1; n <= iter; ++n) {                                   // set3d.f90:394
+        const double *A = buf[(n - 1) & 1];
+        double *B = buf[n & 1];
+        launch_minmax_iteration_list(g, A, B, (mask_given && n == 1) ? g->mask : nullptr, dx, h1);   // :399-431
+        if (sharded(g)) {
+            // B's boundary planes -> the neighbours' ghost planes.  No handshake: a neighbour starts iteration n
+            // only after this rank's planes of iteration n-1 have arrived, i.e. it is past everything that read
+            // the buffer being overwritten here.
+            slab_exchange(g, true, B, false);
+            launch_finalize_slab(g, npart, 1, tol, n);                  // :435-458, sum over all ranks
+        } else
+            launch_finalize(g, npart, 1, tol);                          // :435-458
+        if (n % 8 == 0 || n == iter) {
+            rc = read_ctrl(g, &hc);
+            if (rc) return rc;
+            if (hc.done) break;
+        }
+    }
+    const int ne = hc.done ? hc.n_exit : iter;
+    g->phi = buf[ne & 1];
+    g->phiN = buf[(ne & 1) ^ 1];
+    if (hc.done && hc.status == LSF_ERR_ARG) {                          // queue overflow: leave the scratch state clean
+        cudaMemsetAsync(g->mml_unres, 0, (size_t)g->np, G.stream);
+        cudaMemsetAsync(g->mml_work_count, 0, sizeof(int), G.stream);
+    }
+    *hc_out = hc;
+    return LSF_OK;
+}
+
 static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool mask_given,
                        int *n_exit, double *rms_hist, int *converged)
 {
@@ -338,7 +388,8 @@ static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool
     Timer tm;
     tm.start();
     Ctrl hc = init;
-    if (G.sched == LSF_SCHED_MARCH) rc = minmax_core_march(g, iter, dx, h1, tol, mask_given, &hc);
+    if (G.sched == LSF_SCHED_MARCH && G.mm_algo == LSF_MINMAX_LIST) rc = minmax_core_list(g, iter, dx, h1, tol, mask_given, &hc);
+    else if (G.sched == LSF_SCHED_MARCH) rc = minmax_core_march(g, iter, dx, h1, tol, mask_given, &hc);
     else rc = minmax_core_plane(g, iter, dx, h1, tol, mask_given, &hc);
     if (rc) return rc;
     rc = tm.stop();
@@ -346,6 +397,9 @@ static int minmax_core(Grid *g, int iter, double dx, double h1, double tol, bool
     LSF_CUDA(cudaGetLastError());
     if (hc.status == LSF_ERR_BAND_ON_BOUNDARY)
         return set_error(LSF_ERR_BAND_ON_BOUNDARY, "minmax: narrow band touches the grid boundary");
+    if (hc.status == LSF_ERR_ARG)
+        return set_error(LSF_ERR_ARG, "minmax: more than 2^22 undecided cells in one iteration; use LSF_MINMAX_MARCH for this input");
+    if (hc.status == LSF_ERR_TIMEOUT) return set_error(LSF_ERR_TIMEOUT, "minmax: a neighbouring rank stopped answering");
     const int ne = hc.done ? hc.n_exit : iter;
     const bool conv = hc.done && hc.status == 0;
     if (!conv && ne >= 1)      // the reference executed phiN = phi (set3d.f90:454) in the last iteration it ran
@@ -417,6 +471,7 @@ int lsf_init(int device)
     if (const char *a = getenv("LSF_ARITH"))
         G.arith = (strcmp(a, "exact") == 0) ? LSF_ARITH_EXACT : (strcmp(a, "fast") == 0) ? LSF_ARITH_FAST : LSF_ARITH_AUTO;
     if (const char *s = getenv("LSF_SCHED")) G.sched = (strcmp(s, "plane") == 0) ? LSF_SCHED_PLANE : LSF_SCHED_MARCH;
+    if (const char *m = getenv("LSF_MINMAX")) G.mm_algo = (strcmp(m, "march") == 0) ? LSF_MINMAX_MARCH : LSF_MINMAX_LIST;
     G.inited = true;
     return LSF_OK;
 }
@@ -450,6 +505,15 @@ int lsf_set_sched(int sched)
     G.sched = sched;
     return LSF_OK;
 }
+
+int lsf_set_minmax_algo(int algo)
+{
+    if (algo != LSF_MINMAX_LIST && algo != LSF_MINMAX_MARCH) return set_error(LSF_ERR_ARG, "bad minmax algo %d", algo);
+    G.mm_algo = algo;
+    return LSF_OK;
+}
+
+long long lsf_last_minmax_active(void) { return G.mm_active; }
 
 int lsf_set_profile(int on)
 {
@@ -512,6 +576,7 @@ int lsf_grid_destroy(lsf_grid *g)
     cudaFree(g->phiS); cudaFree(g->lap); cudaFree(g->mask);
     cudaFree(g->partial); cudaFree(g->hist); cudaFree(g->ctrl);
     cudaFree(g->march_ticket); cudaFree(g->march_progress);
+    cudaFree(g->mml_list); cudaFree(g->mml_unres); cudaFree(g->mml_work); cudaFree(g->mml_work_count);
     free(g);
     return LSF_OK;
 }

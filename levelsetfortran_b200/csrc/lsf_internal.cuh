@@ -31,6 +31,12 @@ struct lsf_grid {
     long long phase;              // number of ghost-plane exchanges so far (lockstep on all ranks)
     long long sum_seq;            // number of cross-rank reductions so far
     unsigned int *exch_counter;
+    // active-list min/max flow (lsf_mm_list.cu)
+    long long *mml_list;          // linear indices of the cells that can still change, ascending
+    long long mml_n, mml_cap;
+    uint8_t *mml_unres;           // per point: undecided in the current iteration (all zero between iterations)
+    long long *mml_work;          // queue of undecided cells
+    int *mml_work_count;
     bool prev_sweep_valid;        // the previous launch on this grid was a sweep of the same free-running sequence
     long long prev_sweep_epoch;
     int prev_sweep_fb;
@@ -54,6 +60,8 @@ struct Global {
     int arith_run = LSF_ARITH_FAST; // arithmetic the kernels currently use (FAST or EXACT)
     int arith_last = LSF_ARITH_FAST;
     int sched = LSF_SCHED_MARCH;
+    int mm_algo = LSF_MINMAX_LIST;
+    long long mm_active = 0;       // length of the active list of the most recent min/max call (this rank)
     int n_launch = 0;
     double last_ms = 0.;
     bool profile = false;
@@ -92,7 +100,9 @@ inline bool sharded(const Grid *g) { return g->sg.nranks > 1; }
 
 // lsf_slab.cu
 int slab_check_attached(Grid *g);
-void slab_exchange(Grid *g, bool in_loop, double *buf = nullptr);   // ghost-plane refresh of buf (default phi); no-op on one GPU
+// ghost-plane refresh of buf (default phi); no-op on one GPU.  handshake = false: the caller guarantees that
+// the neighbours no longer read the ghost planes being overwritten (lsf_api.cu, active-list min/max)
+void slab_exchange(Grid *g, bool in_loop, double *buf = nullptr, bool handshake = true);
 void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol, int n);
 long long slab_publish_sum(Grid *g, int npart);  // this rank's sum of partials -> every rank (fire and forget); returns its sequence number
 void slab_decide(Grid *g, long long seq_first, int count, int n_first, int hist_off, double tol);   // EXIT / NaN tests of `count` iterations
@@ -111,5 +121,10 @@ const int *march_order();
 int mm_march_prepare(Grid *g);
 void launch_mm_check_boundary(Grid *g, const uint8_t *mask, double dx, bool check_abs);
 void launch_minmax_iteration_march(Grid *g, const double *A, double *B, const uint8_t *mask, double dx, double h1);
+
+// lsf_mm_list.cu
+int mml_prepare(Grid *g, const uint8_t *mask, double dx);
+int mml_npart();
+void launch_minmax_iteration_list(Grid *g, const double *A, double *B, const uint8_t *mask, double dx, double h1);
 
 }  // namespace lsf

@@ -39,18 +39,21 @@ struct ExchArgs {
     unsigned *counter;
     Ctrl *ctrl;
     int in_loop;
+    int handshake;
 };
 
 __global__ void __launch_bounds__(256)
 k_slab_exchange(const ExchArgs a)
 {
     if (a.in_loop && a.ctrl->done) return;
-    if (blockIdx.x == 0 && threadIdx.x < 2 && a.nbr[threadIdx.x]) {
-        p_fence_sys();
-        p_st_release_sys(&a.nbr[threadIdx.x]->phase_done[1 - threadIdx.x], a.phase);
+    if (a.handshake) {
+        if (blockIdx.x == 0 && threadIdx.x < 2 && a.nbr[threadIdx.x]) {
+            p_fence_sys();
+            p_st_release_sys(&a.nbr[threadIdx.x]->phase_done[1 - threadIdx.x], a.phase);
+        }
+        if (threadIdx.x < 2 && a.nbr[threadIdx.x]) wait_ge<true>(&a.self->phase_done[threadIdx.x], a.phase, a.ctrl);
+        __syncthreads();
     }
-    if (threadIdx.x < 2 && a.nbr[threadIdx.x]) wait_ge<true>(&a.self->phase_done[threadIdx.x], a.phase, a.ctrl);
-    __syncthreads();
     const long long n2 = a.n / 2;     // planes are even-sized or not: handle the tail below
     for (int s = 0; s < 2; ++s) {
         if (!a.nbr[s]) continue;
@@ -79,7 +82,7 @@ k_slab_exchange(const ExchArgs a)
     }
 }
 
-void slab_exchange(Grid *g, bool in_loop, double *buf)
+void slab_exchange(Grid *g, bool in_loop, double *buf, bool handshake)
 {
     if (!sharded(g)) return;
     if (!buf) buf = g->phi;
@@ -92,6 +95,7 @@ void slab_exchange(Grid *g, bool in_loop, double *buf)
     a.counter = g->exch_counter;
     a.ctrl = g->ctrl;
     a.in_loop = in_loop ? 1 : 0;
+    a.handshake = handshake ? 1 : 0;
     if (sg.rank > 0) {
         SlabGeom ng;
         slab_geom(sg.NZ, sg.nranks, sg.rank - 1, ng);

@@ -65,6 +65,11 @@ def set_sched(plane: bool):
     check(lib().lsf_set_sched(_lib.SCHED_PLANE if plane else _lib.SCHED_MARCH))
 
 
+def set_minmax_algo(march: bool):
+    """False (default): active-list min/max iteration; True: whole-grid march kernel (cross-check)."""
+    check(lib().lsf_set_minmax_algo(_lib.MINMAX_MARCH if march else _lib.MINMAX_LIST))
+
+
 def reinit(phi, gradPhi, gradPhiMag, nx, ny, nz, iter, dx, h, stop_on_nan=True):
     """SUBROUTINE reinit (subs.f90:717-931).  Returns (n_exit, rms_hist) -- the iteration index at
     which the loop left and the RMS errors the reference prints at subs.f90:923."""

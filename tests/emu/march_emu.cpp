@@ -11,6 +11,7 @@
 #include "../../levelsetfortran_b200/csrc/lsf_march.cuh"
 #include "../../levelsetfortran_b200/csrc/lsf_mm_march.cuh"
 #include "../../levelsetfortran_b200/csrc/lsf_slab.cuh"
+#include "../../levelsetfortran_b200/csrc/lsf_mm_list.cuh"
 
 namespace lsf { thread_local EmuCta *emu_cta = nullptr; int emu_stall_us = 0; }
 extern "C" void emu_set_stall(int us) { lsf::emu_stall_us = us; }
@@ -393,5 +394,37 @@ extern "C" double emu_mm_iteration_slabs(const double *A, double *B, int nx, int
         memcpy(B + (size_t)g.k0 * sxy, lB[r].data() + (size_t)g.own_lo * sxy, sizeof(double) * (size_t)sxy * (g.k1 - g.k0));
         for (int i = 0; i < P[r].ntiles; ++i) s += partial[r][i];
     }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The active-list min/max iteration (lsf_mm_list.cuh) run serially: speculate every band cell from OLD
+// values in an arbitrary (here: descending!) order, then settle the undecided ones in dependence order.
+// B must be a copy of A on entry.  stats[0] = band cells, [1] = cells that needed the exact 8-combination
+// check, [2] = undecided cells.  Returns the sum over band cells of (new-old)^2.
+extern "C" double emu_mm_list_iteration(const double *A, double *B, const unsigned char *mask, int nx, int ny, int nz,
+                                        double dx, double h1, long long *stats)
+{
+    MmListConst c;
+    c.sx = nx + 1; c.sxy = c.sx * (ny + 1); c.nx = nx; c.ny = ny; c.k_lo = 1; c.k_hi = nz - 1;
+    c.bNB = 4.1 * dx; c.dxx = 1. / (dx * dx); c.h1 = h1;
+    std::vector<long long> work;
+    double s = 0.;
+    long long nband = 0, ncomb = 0;
+    for (int k = nz - 1; k >= 1; --k)
+        for (int j = ny - 1; j >= 1; --j)
+            for (int i = nx - 1; i >= 1; --i) {
+                const long long q = i + c.sx * j + c.sxy * k;
+                if (!mm_inband(c, A, mask, q)) { B[q] = A[q]; continue; }
+                ++nband;
+                double pn;
+                bool comb = false;
+                if (mm_cell_speculate(c, A, mask, q, i, j, k, pn, &comb)) { B[q] = pn; const double d = pn - A[q]; s += d * d; }
+                else work.push_back(q);
+                ncomb += comb ? 1 : 0;
+            }
+    std::vector<long long> w(work.rbegin(), work.rend());        // ascending q = a topological order
+    for (long long q : w) { B[q] = mm_cell_settle(c, A, B, q); const double d = B[q] - A[q]; s += d * d; }
+    if (stats) { stats[0] = nband; stats[1] = ncomb; stats[2] = (long long)w.size(); }
     return s;
 }

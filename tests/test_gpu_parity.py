@@ -23,11 +23,16 @@ def S(lsf):
     yield set_subs
     set_subs.set_arith(None)
     set_subs.set_sched(False)
+    set_subs.set_minmax_algo(False)
 
 
-def _mode(S, exact, plane):
+def _mode(S, exact, plane, mm_march=False):
     S.set_arith(exact)
     S.set_sched(plane)
+    S.set_minmax_algo(mm_march)
+
+
+MM_ALGOS = {"list": (False, False), "march": (False, True), "plane": (True, False)}     # -> (plane, mm_march)
 
 
 # ------------------------------------------------------------------------------------ sign search
@@ -207,10 +212,10 @@ def test_cube40_minmax_full_parity_bit_exact(S):
     assert np.array_equal(nb, gold["phiNB"].astype(np.int32)) and np.array_equal(sb, gold["phiSB"].astype(np.int32))
 
 
-@pytest.mark.parametrize("plane", [False, True], ids=["march", "plane"])
+@pytest.mark.parametrize("algo", ["list", "march", "plane"])
 @pytest.mark.parametrize("shape", [(30, 28, 26), (45, 20, 37), (19, 50, 33), (6, 5, 7)])
-def test_minmax_small_vs_oracle_iteration_limit(S, oracle, shape, plane):
-    _mode(S, False, plane)
+def test_minmax_small_vs_oracle_iteration_limit(S, oracle, shape, algo):
+    _mode(S, False, *MM_ALGOS[algo])
     p0 = dist_field(shape, seed=11)
     a, b = p0.copy(order="F"), p0.copy(order="F")
     st, n, hist, nbo, sbo = oracle.minmax(a, 12, DX, 1.0e-4, tol=1e-30)
@@ -236,8 +241,8 @@ def test_minmax_given_mask_first_iteration(S, oracle):
     nb0 = np.zeros(shape, dtype=np.int32, order="F")
     nb0[2:-2, 2:-2, 2:-2] = rng.random((shape[0] - 4, shape[1] - 4, shape[2] - 4)) < 0.3
     dp = ctypes.POINTER(ctypes.c_double)
-    for plane in (False, True):
-        _mode(S, False, plane)
+    for algo in MM_ALGOS.values():
+        _mode(S, False, *algo)
         a, an, nba, sba = p0.copy(order="F"), p0.copy(order="F"), nb0.copy(order="F"), np.zeros(shape, dtype=np.int32, order="F")
         hist = np.zeros(3)
         ne = ctypes.c_int(0)
@@ -258,8 +263,8 @@ def test_minmax_band_on_boundary_is_an_error(S):
     phi = np.full(shape, 0.01, order="F")              # every cell, including the boundary, is in the band
     nb = np.ones(shape, dtype=np.int32, order="F")
     sb = np.ones(shape, dtype=np.int32, order="F")
-    for plane in (False, True):
-        _mode(S, False, plane)
+    for algo in MM_ALGOS.values():
+        _mode(S, False, *algo)
         with pytest.raises(LsfError) as e:
             S.minMaxFlow(phi.copy(order="F"), phi.copy(order="F"), nb, sb, 11, 11, 11, 2, DX, 1.0e-4)
         assert e.value.code == LSF_ERR_BAND_ON_BOUNDARY
@@ -273,19 +278,45 @@ def test_minmax_march_equals_plane_schedule_at_size(S, shape):
     p0 = dist_field(shape, seed=15)
     nx, ny, nz = (q - 1 for q in shape)
     out = []
-    for plane in (True, False):
-        _mode(S, False, plane)
+    for algo in ("plane", "march", "list"):
+        _mode(S, False, *MM_ALGOS[algo])
         b, bn = p0.copy(order="F"), p0.copy(order="F")
         nb = np.zeros(shape, dtype=np.int32, order="F")
         sb = np.zeros(shape, dtype=np.int32, order="F")
         S.narrowBand(nx, ny, nz, DX, b, nb, sb)
         n, hist = S.minMaxFlow(b, bn, nb, sb, nx, ny, nz, 5, DX, 1.0e-4, tol=1e-30)
         out.append((n, b, bn, nb, sb, hist))
-    assert out[0][0] == out[1][0] == 5
-    for q in range(1, 5):
-        assert np.array_equal(out[0][q], out[1][q])
-    assert np.allclose(out[0][5], out[1][5], rtol=1e-12, atol=0)
+    assert out[0][0] == out[1][0] == out[2][0] == 5
+    for other in (1, 2):
+        for q in range(1, 5):
+            assert np.array_equal(out[0][q], out[other][q])
+        assert np.allclose(out[0][5], out[other][5], rtol=1e-11, atol=0)
     assert not np.array_equal(out[0][1], p0)
+    _mode(S, False, False)
+
+
+@pytest.mark.parametrize("h1,scale", [(2.0e-3, 1.0), (1.0e-3, 1.0e-2)])
+def test_minmax_active_list_settle_path_on_gpu(S, oracle, h1, scale):
+    """Large h1 / small amplitude: pAve hovers around zero, the 8-combination check and the settle queue of the
+    active-list kernel really run (CPU twin: tests/test_march_emu.py); bit-exact against the oracle."""
+    _mode(S, False, False)
+    shape = (40, 36, 34)
+    p0 = np.asfortranarray(dist_field(shape, seed=9) * scale)
+    if scale != 1.0:
+        edge = np.ones(shape, dtype=bool)
+        edge[1:-1, 1:-1, 1:-1] = False
+        p0[edge] = 1.0
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    st, n, hist, nbo, sbo = oracle.minmax(a, 12, DX, h1, tol=1e-300)
+    assert n == 12
+    nx, ny, nz = (q - 1 for q in shape)
+    phiN = b.copy(order="F")
+    nb = np.zeros(shape, dtype=np.int32, order="F")
+    sb = np.zeros(shape, dtype=np.int32, order="F")
+    S.narrowBand(nx, ny, nz, DX, b, nb, sb)
+    n2, hist2 = S.minMaxFlow(b, phiN, nb, sb, nx, ny, nz, 12, DX, h1, tol=1e-300)
+    assert n2 == 12 and np.array_equal(a, b)
+    assert np.allclose(hist, hist2, rtol=1e-11, atol=0)
 
 
 # ------------------------------------------------------------------------------------ device-resident pipeline + larger sizes

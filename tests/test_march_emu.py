@@ -39,6 +39,8 @@ def emu(request):
     L.emu_march_multi_slabs.argtypes = [dp, dp] + [C.c_int] * 6 + [C.c_double, C.c_double] + [C.c_int] * 4
     L.emu_mm_iteration_slabs.restype = C.c_double
     L.emu_mm_iteration_slabs.argtypes = [dp, dp] + [C.c_int] * 4 + [C.c_double, C.c_double, C.c_int, C.c_int]
+    L.emu_mm_list_iteration.restype = C.c_double
+    L.emu_mm_list_iteration.argtypes = [dp, dp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_longlong)]
     L.emu_mm_iteration.restype = C.c_double
     L.emu_mm_iteration.argtypes = [dp, dp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     return L
@@ -150,6 +152,38 @@ def test_minmax_march_slabs_bit_exact(emu, oracle, shape, nranks, ncta, m):
         sums.append(np.sqrt(s / (nx * ny * nz)))
     assert np.array_equal(buf[0], a)
     assert np.allclose(sums, hist, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("shape,h1,scale", [((24, 22, 23), 1.0e-4, 1.0), ((30, 26, 28), 2.0e-3, 1.0), ((26, 30, 24), 1.0e-3, 1.0e-2)])
+def test_minmax_active_list_speculation_is_bit_exact(emu, oracle, shape, h1, scale):
+    """The active-list formulation of the min/max iteration (lsf_mm_list.cuh): every band cell is decided
+    from OLD values alone when all outcomes of its three upstream neighbours give the same sign of pAve,
+    the rest are settled afterwards.  Against the oracle's literal in-place loop, 12 iterations, bit-exact;
+    the large-h1 / small-amplitude cases force the 8-combination check and the settle path to run."""
+    p0 = np.asfortranarray(dist_field(shape, seed=9) * scale) if scale != 1.0 else dist_field(shape, seed=9)
+    if scale != 1.0:      # small amplitude: everything is in the band and pAve hovers around zero
+        edge = np.ones(shape, dtype=bool); edge[1:-1, 1:-1, 1:-1] = False
+        p0[edge] = 1.0
+    nx, ny, nz = (s - 1 for s in shape)
+    a = p0.copy(order="F")
+    st, n, hist, nbo, sbo = oracle.minmax(a, 12, 0.05, h1, tol=1e-300)
+    assert n == 12
+    buf = [p0.copy(order="F"), p0.copy(order="F")]
+    tot = np.zeros(3, dtype=np.int64)
+    sums = []
+    for it in range(1, 13):
+        A, B = buf[(it - 1) & 1], buf[it & 1]
+        stats = (C.c_longlong * 3)()
+        s = emu.emu_mm_list_iteration(A.ctypes.data_as(dp), B.ctypes.data_as(dp), None, nx, ny, nz, 0.05, h1, stats)
+        tot += np.array(list(stats))
+        sums.append(np.sqrt(s / (nx * ny * nz)))
+    assert np.array_equal(buf[0], a)
+    assert np.allclose(sums, hist, rtol=1e-11, atol=0)
+    assert tot[0] > 1000
+    if h1 >= 2.0e-3:
+        assert tot[1] > 0, "the exact combination check never ran"
+    if scale != 1.0:
+        assert tot[2] > 0, "no cell ever went through the settle path"
 
 
 def test_minmax_march_given_mask(emu, oracle):
