@@ -145,7 +145,8 @@ k_rank_publish(const double *__restrict__ partial, int npart, Ctrl *ctrl, PeerSy
     const int slot = (int)(seq % SLAB_SUM_SLOTS);
     if (threadIdx.x < nranks) {
         const int st = *(volatile int *)&ctrl->status;
-        const int flags = (ctrl->guard ? 1 : 0) | (st == LSF_ERR_BAND_ON_BOUNDARY ? 2 : 0) | (st == LSF_ERR_TIMEOUT ? 4 : 0);
+        const int flags = (ctrl->guard ? 1 : 0) | (st == LSF_ERR_BAND_ON_BOUNDARY ? 2 : 0) | (st == LSF_ERR_TIMEOUT ? 4 : 0) |
+                          ((st < 0 && st != LSF_ERR_BAND_ON_BOUNDARY && st != LSF_ERR_TIMEOUT) ? 8 : 0);
         SlabSync *q = peers.s[threadIdx.x];
         *(volatile double *)&q->rank_sum[slot][rank] = sh[0];
         *(volatile int *)&q->rank_flag[slot][rank] = flags;
@@ -176,8 +177,8 @@ k_decide_slab(Ctrl *ctrl, double *__restrict__ hist, int hist_off, double denom,
             flags |= *(volatile int *)&self->rank_flag[slot][r];
         }
         if (flags & 1) ctrl->guard = 1;
-        if (flags & 6) {
-            ctrl->status = (flags & 4) ? LSF_ERR_TIMEOUT : LSF_ERR_BAND_ON_BOUNDARY;
+        if (flags & 14) {
+            ctrl->status = (flags & 4) ? LSF_ERR_TIMEOUT : (flags & 2) ? LSF_ERR_BAND_ON_BOUNDARY : LSF_ERR_ARG;
             ctrl->done = 1; ctrl->n_exit = n; ctrl->n = n;
             return;
         }

@@ -66,7 +66,7 @@ struct SlabSync {
     long long phase_done[2];                 // same sides: "I have finished compute phase e" (I no longer read my ghost planes)
     long long sum_seq[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];   // per slot and source rank: sequence number of the contribution held there
     double rank_sum[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];     // per-rank partial sums of the RMS test, slot = sequence number mod SLOTS
-    int rank_flag[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];       // flags travelling with the sums (bit 0 guard, bit 1 band-on-boundary, bit 2 timeout)
+    int rank_flag[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];       // flags travelling with the sums (bit 0 guard, bit 1 band-on-boundary, bit 2 timeout, bit 3 other error)
     long long in_progress[SLAB_MAX_NTB];     // streaming-halo progress of the upstream rank's last tile row
     long long edge_done[2][SLAB_MAX_NTB];    // [side][J]: epoch of the last sweep in which that neighbour's tile J adjacent to this rank completed
 };

@@ -135,6 +135,31 @@ def main():
     SG.close()
     checks += 1
 
+    # active-list min/max with undecided cells at and across the slab boundaries (large h1, small amplitude)
+    shape = (30, 28, 12 * world + 9)
+    p0 = np.asfortranarray(dist_field(shape, seed=9) * 1.0e-2)
+    edge = np.ones(shape, dtype=bool)
+    edge[1:-1, 1:-1, 1:-1] = False
+    p0[edge] = 1.0
+    for march in (False, True):
+        S.set_minmax_algo(march)
+
+        def run_whole4(G):
+            G.upload(p0)
+            rc, n, hist = G.minMaxFlow(10, DX, 1.0e-3, tol=0.0)
+            return n, hist, G.download()
+        n6, h6, ref6 = whole(shape, run_whole4)
+        SG = ShardedGrid(shape[0] - 1, shape[1] - 1, shape[2] - 1)
+        SG.upload(np.asfortranarray(p0[:, :, SG.k0:SG.k1]))
+        rc, n7, h7 = SG.minMaxFlow(10, DX, 1.0e-3, tol=0.0)
+        got = SG.download()
+        assert n7 == n6 and np.array_equal(got, ref6[:, :, SG.k0:SG.k1]), \
+            f"rank {rank} march={march}: settle-path case differs, max {np.abs(got - ref6[:, :, SG.k0:SG.k1]).max():.3e}"
+        assert np.allclose(h6, h7, rtol=1e-11, atol=0)
+        SG.close()
+        checks += 1
+    S.set_minmax_algo(False)
+
     dist.barrier()
     if rank == 0:
         print(f"MGPU_OK {checks} checks on {world} GPUs", flush=True)
