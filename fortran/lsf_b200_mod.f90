@@ -28,7 +28,8 @@ USE, INTRINSIC :: ISO_C_BINDING
 IMPLICIT NONE
 PRIVATE
 
-PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched
+PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched, lsf_set_minmax_algo
+PUBLIC :: lsf_slab_range, lsf_sgrid_create, lsf_sgrid_ipc_handle, lsf_sgrid_attach, lsf_grid_destroy
 PUBLIC :: signSearch_b200, reinit_b200, narrowBand_b200, minMaxFlow_b200
 PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT, LSF_ARITH_AUTO
 
@@ -59,6 +60,47 @@ INTERFACE
       INTEGER(c_int), VALUE :: sched
       INTEGER(c_int) :: rc
    END FUNCTION lsf_set_sched
+
+   FUNCTION lsf_set_minmax_algo(algo) BIND(C, NAME='lsf_set_minmax_algo') RESULT(rc)
+      IMPORT :: c_int
+      INTEGER(c_int), VALUE :: algo          ! 0 = active list (default), 1 = whole-grid march
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_set_minmax_algo
+
+   ! ---- z-slab sharding, one MPI rank per GPU (include/lsf_b200.h; calling sequence: INTEGRATION.md) ----
+   FUNCTION lsf_slab_range(nz,nranks,rank,k0,k1) BIND(C, NAME='lsf_slab_range') RESULT(rc)
+      IMPORT :: c_int
+      INTEGER(c_int), VALUE :: nz,nranks,rank
+      INTEGER(c_int) :: k0,k1                ! this rank owns planes k0 .. k1-1 of phi(0:nx,0:ny,0:nz)
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_slab_range
+
+   FUNCTION lsf_sgrid_create(g,nx,ny,nz,rank,nranks) BIND(C, NAME='lsf_sgrid_create') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr) :: g                        ! lsf_grid**
+      INTEGER(c_int), VALUE :: nx,ny,nz,rank,nranks
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_sgrid_create
+
+   FUNCTION lsf_sgrid_ipc_handle(g,handle) BIND(C, NAME='lsf_sgrid_ipc_handle') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_char
+      TYPE(c_ptr), VALUE :: g
+      CHARACTER(KIND=c_char) :: handle(64)    ! LSF_IPC_HANDLE_BYTES; MPI_Allgather these as MPI_BYTE
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_sgrid_ipc_handle
+
+   FUNCTION lsf_sgrid_attach(g,handles) BIND(C, NAME='lsf_sgrid_attach') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_char
+      TYPE(c_ptr), VALUE :: g
+      CHARACTER(KIND=c_char) :: handles(*)    ! nranks*64 bytes, rank order
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_sgrid_attach
+
+   FUNCTION lsf_grid_destroy(g) BIND(C, NAME='lsf_grid_destroy') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr), VALUE :: g
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_destroy
 
    FUNCTION lsf_last_error() BIND(C, NAME='lsf_last_error') RESULT(msg)
       IMPORT :: c_ptr
