@@ -136,6 +136,20 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(grid):
+    """DRAM bytes (read + write) of ONE sweep-kernel launch from the committed `ncu --set full` capture of this
+    kernel at the same grid size (profiles/r1g_march_<grid>_full.txt), or None if there is no capture."""
+    path = os.path.join(ROOT, "profiles", f"r1g_march_{grid}_full.txt")
+    if not os.path.exists(path):
+        return None
+    tot = 0.0
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+    return tot or None
+
+
 # ----------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -330,7 +344,9 @@ def run_gpu(args):
                            "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
                            "last_rms": float(hist[-1]) if hist is not None else None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak if achieved else None, "traffic": None,
+                             "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(n),
+                             "traffic_note": "DRAM read+write bytes of one launch, ncu --set full (profiles/r1g_march_%d_full.txt); "
+                                             "algorithmic bytes per launch: %.4g" % (n, BYTES_PER_UPDATE * cells_per_launch),
                              "kernel": "k_reinit_march" if args.sched == "march" else "k_reinit_plane",
                              "launch_ms": launch_ms, "peak_source": peak_src,
                              "fp64_pipe_frac": (FP64_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3)) / FP64_PIPE_PEAK if launch_ms > 0 else None,

@@ -443,6 +443,32 @@ static int sign_core(Grid *g, const double xLo[3], double dx, const double *surf
 
 using namespace lsf;
 
+// The host-buffer entry points (the Fortran drop-in calls) run on a library-owned device grid.  Allocating
+// and freeing three fields per call costs ~0.1 s at 1024^3, so the grid of the most recent call is kept and
+// reused when the next call has the same extents (set3d.f90 calls sign search, reinit, narrowBand and the
+// min/max loop on the same grid).  It is released by lsf_finalize, by a call with other extents, or never kept
+// at all with LSF_NO_GRID_CACHE=1.
+static lsf_grid *g_cached = nullptr;
+
+static int host_grid_acquire(lsf_grid **out, int nx, int ny, int nz)
+{
+    if (g_cached && g_cached->dm.nx == nx && g_cached->dm.ny == ny && g_cached->dm.nz == nz && !sharded(g_cached)) {
+        *out = g_cached;
+        g_cached = nullptr;
+        return LSF_OK;
+    }
+    if (g_cached) { lsf_grid_destroy(g_cached); g_cached = nullptr; }
+    return lsf_grid_create(out, nx, ny, nz);
+}
+
+static void host_grid_release(lsf_grid *g)
+{
+    if (!g) return;
+    static const bool no_cache = getenv("LSF_NO_GRID_CACHE") != nullptr;
+    if (no_cache || g_cached) { lsf_grid_destroy(g); return; }
+    g_cached = g;
+}
+
 // =============================================================================================
 extern "C" {
 
@@ -479,6 +505,7 @@ int lsf_init(int device)
 int lsf_finalize(void)
 {
     if (!G.inited) return LSF_OK;
+    if (g_cached) { lsf_grid_destroy(g_cached); g_cached = nullptr; }
     cudaStreamSynchronize(G.stream);
     cudaEventDestroy(G.ev0);
     cudaEventDestroy(G.ev1);
@@ -673,12 +700,12 @@ int lsf_sign_init(double *phi, int nx, int ny, int nz, const double xLo[3], doub
 {
     if (!phi || !xLo || !surfX || !surfElem) return set_error(LSF_ERR_ARG, "null argument");
     lsf_grid *g = nullptr;
-    int rc = lsf_grid_create(&g, nx, ny, nz);
+    int rc = host_grid_acquire(&g, nx, ny, nz);
     if (rc) return rc;
     rc = lsf_grid_upload(g, phi);
     if (!rc) rc = sign_core(g, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
     if (!rc) rc = lsf_grid_download(g, phi);
-    lsf_grid_destroy(g);
+    host_grid_release(g);
     return rc;
 }
 
@@ -687,7 +714,7 @@ int lsf_reinit(double *phi, double *gradPhi, double *gradPhiMag, int nx, int ny,
 {
     if (!phi) return set_error(LSF_ERR_ARG, "null phi");
     lsf_grid *g = nullptr;
-    int rc = lsf_grid_create(&g, nx, ny, nz);
+    int rc = host_grid_acquire(&g, nx, ny, nz);
     if (rc) return rc;
     double *d_g = nullptr, *d_gm = nullptr;
     const size_t bytes = sizeof(double) * (size_t)g->np;
@@ -705,7 +732,7 @@ int lsf_reinit(double *phi, double *gradPhi, double *gradPhiMag, int nx, int ny,
     if (!rc && d_g && cudaMemcpy(gradPhi, d_g, 3 * bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error(LSF_ERR_CUDA, "reinit: D2H gradPhi");
     if (!rc && d_gm && cudaMemcpy(gradPhiMag, d_gm, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error(LSF_ERR_CUDA, "reinit: D2H gradPhiMag");
     cudaFree(d_g); cudaFree(d_gm);
-    lsf_grid_destroy(g);
+    host_grid_release(g);
     return rc ? rc : st;
 }
 
@@ -713,11 +740,11 @@ int lsf_narrowband(int nx, int ny, int nz, double dx, const double *phi, int32_t
 {
     if (!phi || !phiNB || !phiSB) return set_error(LSF_ERR_ARG, "null argument");
     lsf_grid *g = nullptr;
-    int rc = lsf_grid_create(&g, nx, ny, nz);
+    int rc = host_grid_acquire(&g, nx, ny, nz);
     if (rc) return rc;
     rc = lsf_grid_upload(g, phi);
     if (!rc) rc = narrowband_to_host(g, g->phi, dx, phiNB, phiSB);
-    lsf_grid_destroy(g);
+    host_grid_release(g);
     return rc;
 }
 
@@ -726,7 +753,7 @@ int lsf_minmax(double *phi, double *phiN, int32_t *phiNB, int32_t *phiSB, int nx
 {
     if (!phi || !phiN || !phiNB || !phiSB) return set_error(LSF_ERR_ARG, "null argument");
     lsf_grid *g = nullptr;
-    int rc = lsf_grid_create(&g, nx, ny, nz);
+    int rc = host_grid_acquire(&g, nx, ny, nz);
     if (rc) return rc;
     int st = LSF_OK, conv = 0, ne = 0;
     const size_t bytes = sizeof(double) * (size_t)g->np;
@@ -753,7 +780,7 @@ int lsf_minmax(double *phi, double *phiN, int32_t *phiNB, int32_t *phiSB, int nx
             rc = narrowband_to_host(g, conv ? g->phiN : g->phi, dx, phiNB, phiSB);
     } while (0);
     cudaFree(d_nb);
-    lsf_grid_destroy(g);
+    host_grid_release(g);
     return rc ? rc : st;
 }
 

@@ -23,7 +23,7 @@ def _rows_default():
     return int(m.group(1)) if m else 1
 
 
-@pytest.fixture(scope="module", params=sorted({1, 2, _rows_default()}), ids=lambda r: f"rows{r}")
+@pytest.fixture(scope="module", params=[_rows_default()], ids=lambda r: f"rows{r}")
 def emu(request):
     so = os.path.join(EMU_DIR, f"libmarch_emu_r{request.param}.so")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
@@ -103,7 +103,7 @@ def test_march_slab_pipeline_free_running_sweeps(emu, oracle, shape, nranks, nct
         before = a.copy(order="F")
         oracle.reinit_sweep(a, pS, 0.05, 0.0014, (first - 1 + n) % 8 + 1)
         ref += float(((a - before)[1:-1, 1:-1, 1:-1] ** 2).sum())
-    emu.emu_set_stall(300000 if skew else 0)     # every tile stalls 0.3 s shortly before its end: ranks run ahead where allowed
+    emu.emu_set_stall(20000 if skew else 0)      # every tile stalls 20 ms shortly before its end: ranks run ahead where allowed
     try:
         s = emu.emu_march_multi_slabs(b.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, nranks, nsweeps, first,
                                       0.05, 0.0014, 1, ncta, m, skew)
