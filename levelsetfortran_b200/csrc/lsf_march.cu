@@ -18,30 +18,37 @@ namespace lsf {
 #endif
 typedef MarchCfg<LSF_TB, LSF_TC> CFG;
 
-template <class AR, bool FA, bool FB, bool FC>
+// MG: z-slab variant (peer stores / peer flags compiled in)
+template <class AR, bool FA, bool FB, bool FC, bool MG>
 __global__ void __launch_bounds__(CFG::THREADS, LSF_OCC)
 k_reinit_march(const MarchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MarchSmem<CFG> &sm = *reinterpret_cast<MarchSmem<CFG> *>(smem_raw);
-    march_cta<AR, FA, FB, FC, CFG>(p, sm, threadIdx.x);
+    march_cta<AR, FA, FB, FC, CFG, MG>(p, sm, threadIdx.x);
 }
 
 typedef void (*MarchKernel)(const MarchParams);
 
-template <class AR>
-static MarchKernel march_kernel(int fa, int fb, int fc)
+template <class AR, bool MG>
+static MarchKernel march_kernel_mg(int fa, int fb, int fc)
 {
     switch ((fa ? 1 : 0) | (fb ? 2 : 0) | (fc ? 4 : 0)) {
-    case 0: return k_reinit_march<AR, false, false, false>;
-    case 1: return k_reinit_march<AR, true, false, false>;
-    case 2: return k_reinit_march<AR, false, true, false>;
-    case 3: return k_reinit_march<AR, true, true, false>;
-    case 4: return k_reinit_march<AR, false, false, true>;
-    case 5: return k_reinit_march<AR, true, false, true>;
-    case 6: return k_reinit_march<AR, false, true, true>;
-    default: return k_reinit_march<AR, true, true, true>;
+    case 0: return k_reinit_march<AR, false, false, false, MG>;
+    case 1: return k_reinit_march<AR, true, false, false, MG>;
+    case 2: return k_reinit_march<AR, false, true, false, MG>;
+    case 3: return k_reinit_march<AR, true, true, false, MG>;
+    case 4: return k_reinit_march<AR, false, false, true, MG>;
+    case 5: return k_reinit_march<AR, true, false, true, MG>;
+    case 6: return k_reinit_march<AR, false, true, true, MG>;
+    default: return k_reinit_march<AR, true, true, true, MG>;
     }
+}
+
+template <class AR>
+static MarchKernel march_kernel(int fa, int fb, int fc, bool mg = false)
+{
+    return mg ? march_kernel_mg<AR, true>(fa, fb, fc) : march_kernel_mg<AR, false>(fa, fb, fc);
 }
 
 struct MarchHost {
@@ -99,9 +106,9 @@ int march_prepare(Grid *g)
     }
     static bool attr_done = false;
     if (!attr_done) {
-        for (int o = 0; o < 8; ++o) {
-            LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
-            LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+        for (int o = 0; o < 16; ++o) {
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
         }
         attr_done = true;
     }
@@ -158,8 +165,8 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
 #endif
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     const int ncta = p.ntiles < LSF_OCC * G.num_sms ? p.ntiles : LSF_OCC * G.num_sms;
-    MarchKernel kern = (G.arith_run == LSF_ARITH_EXACT) ? march_kernel<ExactArith>(p.fa, p.fb, p.fc)
-                                                    : march_kernel<FastArith>(p.fa, p.fb, p.fc);
+    MarchKernel kern = (G.arith_run == LSF_ARITH_EXACT) ? march_kernel<ExactArith>(p.fa, p.fb, p.fc, sharded(g))
+                                                    : march_kernel<FastArith>(p.fa, p.fb, p.fc, sharded(g));
     kern<<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(p);
     G.n_launch++;
 #if defined(LSF_EXP_TIMING)

@@ -250,7 +250,8 @@ LSF_DEV double march_cell(const double *Sown, int t, double ps, bool hi, const C
     return pn;
 }
 
-template <class AR, bool FA, bool FB, bool FC, class CFG>
+// MG = false compiles the z-slab hooks (peer stores, peer flags) out of the single-GPU kernel.
+template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true>
 LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K)
 {
     constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP, R = CFG::R;
@@ -270,8 +271,8 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
         const int b = 1 + J * TB + tb, c = p.c_lo + K * TC + tc;
         rowValid[r] = (b <= p.ny) && (c <= p.c_max);
         compValid[r] = (b <= p.ny - 1) && (c <= p.c_hi);
-        pushRow[r] = (p.push_delta != 0) && compValid[r] && (c > p.c_hi - M_H);
-        pushUpRow[r] = (p.push_up_delta != 0) && compValid[r] && (c < p.c_lo + M_H);
+        pushRow[r] = MG && (p.push_delta != 0) && compValid[r] && (c > p.c_hi - M_H);
+        pushUpRow[r] = MG && (p.push_up_delta != 0) && compValid[r] && (c < p.c_lo + M_H);
         hiBC[r] = (b >= p.lo_b) && (b <= p.hi_b) && (c >= p.lo_c) && (c <= p.hi_c);
         sig[r] = tb + tc + M_H;
         const long long rowoff = rowValid[r] ? p.off0 + (long long)b * p.sb + (long long)c * p.sc : 0;
@@ -314,17 +315,17 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
 
     const long long ebase = p.epoch << 32;
     const long long *predB = (J > 0) ? p.progress + ((J - 1) + p.ntb * K) : nullptr;
-    const bool predCpeer = (K == 0) && p.in_progress;       // predecessor in c lives on the upstream rank
+    const bool predCpeer = MG && (K == 0) && p.in_progress;       // predecessor in c lives on the upstream rank
     const long long *predC = (K > 0) ? p.progress + (J + p.ntb * (K - 1)) : (predCpeer ? p.in_progress + J : nullptr);
     long long *mine = p.progress + (J + p.ntb * K);
-    long long *minePeer = (K == p.ntc - 1 && p.push_progress) ? p.push_progress + J : nullptr;
+    long long *minePeer = (MG && K == p.ntc - 1 && p.push_progress) ? p.push_progress + J : nullptr;
 
     // z-slabs: before a tile of the last row touches the downstream rank's planes (reads them as OLD values,
     // streams NEW values into its ghost planes) that rank's adjacent tiles of the PREVIOUS sweep covering the
     // same physical j range must be complete (they may have used a different b orientation).
     // (a short last tile row leaves some of the three boundary planes to the row before it: any tile whose
     // rows or +c halo reach beyond c_hi is concerned)
-    if (p.edge_wait && p.c_lo + (K + 1) * TC + M_H - 1 > p.c_hi) {
+    if (MG && p.edge_wait && p.c_lo + (K + 1) * TC + M_H - 1 > p.c_hi) {
         if (tid < 2) {
             const int bq = 1 + J * TB + (tid ? TB - 1 : 0);
             const int be = bq < p.ny - 1 ? bq : p.ny - 1;                       // clamp to the updated range
@@ -459,8 +460,8 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
     if (tid == 0) {
         p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN);
         if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + M_FIN); }
-        if (K == 0 && p.edge_pub[0]) { p_fence_sys(); p_st_release_sys(p.edge_pub[0] + J, p.epoch); }
-        if (K == p.ntc - 1 && p.edge_pub[1]) { p_fence_sys(); p_st_release_sys(p.edge_pub[1] + J, p.epoch); }
+        if (MG && K == 0 && p.edge_pub[0]) { p_fence_sys(); p_st_release_sys(p.edge_pub[0] + J, p.epoch); }
+        if (MG && K == p.ntc - 1 && p.edge_pub[1]) { p_fence_sys(); p_st_release_sys(p.edge_pub[1] + J, p.epoch); }
     }
     for (int wdt = THREADS / 2; wdt > 0; wdt >>= 1) {
         if (tid < wdt) sm.red[tid] = sm.red[tid] + sm.red[tid + wdt];
@@ -480,11 +481,11 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
 }
 
 // Persistent CTA: take tickets until the tile list is exhausted.
-template <class AR, bool FA, bool FB, bool FC, class CFG>
+template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true>
 LSF_DEV void march_cta(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
 {
     if (p.ctrl->done) return;
-    if (p.halo_seq) {          // z-slab: both neighbours must have refreshed this rank's ghost planes
+    if (MG && p.halo_seq) {          // z-slab: both neighbours must have refreshed this rank's ghost planes
         if (tid == 0) {
             if (p.halo_need[0]) wait_ge<true>(p.halo_seq + 0, p.halo_need[0], p.ctrl);
             if (p.halo_need[1]) wait_ge<true>(p.halo_seq + 1, p.halo_need[1], p.ctrl);
@@ -498,7 +499,7 @@ LSF_DEV void march_cta(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
         p_sync();
         if (tk >= p.ntiles) break;
         const int jk = p.order[tk];
-        march_tile<AR, FA, FB, FC, CFG>(p, sm, tid, jk & 0xffff, jk >> 16);
+        march_tile<AR, FA, FB, FC, CFG, MG>(p, sm, tid, jk & 0xffff, jk >> 16);
     }
 }
 
