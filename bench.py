@@ -212,11 +212,15 @@ def run_gpu(args):
     h = 0.1 * g["dxx"]                                         # CFL = .1, set3d.f90:304-305
     cells_per_step = (nx - 1) * (ny - 1) * (nz - 1) * SWEEPS_PER_STEP     # whole job
 
+    f32 = bool(args.f32)
+    if f32 and world > 1:
+        raise SystemExit("bench.py: the fp32 mode is single-GPU (sharded fp32 grids are not built)")
+    bytes_per_update = 12.0 if f32 else BYTES_PER_UPDATE
     if world > 1:
         G = ShardedGrid(nx, ny, nz)
         k_upd = min(G.k1 - 1, nz - 1) - max(G.k0, 1) + 1      # planes this rank's sweeps update
     else:
-        G = DeviceGrid(nx, ny, nz)
+        G = DeviceGrid(nx, ny, nz, f32=f32)
         k_upd = nz - 1
     G.fill(1.0)
     t0 = time.perf_counter()
@@ -255,7 +259,7 @@ def run_gpu(args):
 
     # ---- companion measurements on the same resident grid (not part of `value`): min/max flow ----
     mm = None
-    if args.minmax_iters > 0:
+    if args.minmax_iters > 0 and not f32:
         rc, n_mm, hist_mm = G.minMaxFlow(3, DX, 0.01 * g["dxx"], tol=0.0)          # warm-up
         barrier()
         rc, n_mm, hist_mm = G.minMaxFlow(args.minmax_iters, DX, 0.01 * g["dxx"], tol=0.0)
@@ -276,6 +280,33 @@ def run_gpu(args):
                            "dense_equivalent_GBs": 16.0 * mm_rate},
               "last_rms": float(hist_mm[-1]) if len(hist_mm) else None}
 
+    # ---- companion: the optional fp32 mode on the same geometry (single GPU; not part of `value`) ----
+    fp32 = None
+    if world == 1 and not f32 and not args.no_f32:
+        G32 = DeviceGrid(nx, ny, nz, f32=True)
+        G32.fill(1.0)
+        G32.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
+        for _ in range(2):
+            G32.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)
+        barrier()
+        ms32 = sw32 = 0.0
+        ns32 = 0
+        k32 = max(1, min(args.steps, 3))
+        for _ in range(k32):
+            rc, n_exit, hist32 = G32.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)
+            assert rc == 0 and n_exit == SWEEPS_PER_STEP - 1
+            ms, _nl = _lib.last_timing()
+            sm, ns = _lib.last_sweep_timing()
+            ms32 += ms; sw32 += sm; ns32 += ns
+        G32.close()
+        l32 = sw32 / max(ns32, 1)
+        a32 = 12.0 * (nx - 1) * (ny - 1) * (nz - 1) / (l32 * 1e-3) / 1e9 if l32 > 0 else None
+        fp32 = {"metric": METRIC + " (fp32 mode)", "value": cells_per_step * k32 / (ms32 * 1e-3) / 1e9, "unit": UNIT, "dtype": "f32",
+                "steps": k32, "ms_per_step": ms32 / k32,
+                "roofline": {"bound": "hbm", "bytes_per_update": 12.0, "achieved": a32, "peak": measured_peak()[0], "unit": "GB/s",
+                             "frac": a32 / measured_peak()[0] if a32 else None, "launch_ms": l32, "kernel": "k_reinit_march_f32"},
+                "last_rms": float(hist32[-1]), "last_rms_fp64": float(hist[-1]) if hist is not None else None}
+
     # ---- e2e: the host-buffer drop-in call, pinned host memory, H2D + compute + D2H timed ------
     e2e = None
     if not args.no_e2e:
@@ -286,6 +317,9 @@ def run_gpu(args):
         import ctypes as C
         n_exit = C.c_int(0)
         if world == 1:
+            if f32:
+                _lib.check(L.lsf_set_precision(_lib.PREC_F32))
+
             def e2e_step():
                 rc = L.lsf_reinit(C.cast(host.data_ptr(), _lib.c_double_p), None, None, nx, ny, nz, SWEEPS_PER_STEP - 1,
                                   DX, h, C.byref(n_exit), hist_buf.ctypes.data_as(_lib.c_double_p))
@@ -321,7 +355,7 @@ def run_gpu(args):
         peak, peak_src = measured_peak()
         launch_ms = sweep_ms / max(n_sweeps, 1)
         cells_per_launch = (nx - 1) * (ny - 1) * k_upd          # rank 0's sweep kernel
-        achieved = BYTES_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
+        achieved = bytes_per_update * cells_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
         cpu = None
         if not args.no_cpu:
             v, desc = cpu_sample(n, args.ref_slab, 1)
@@ -330,9 +364,9 @@ def run_gpu(args):
                                     "compiler in the image)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
+                "dtype": "f32" if f32 else "f64", "data": "synthetic",
                 "config": {"workload": f"BASELINE config {'4' if world == 1 else '5'}: synthetic torus+cube STL ({len(surfElem)} triangles) on "
-                                       f"ONE {n}x{n}x{n * world} fp64 grid ({n}^3 points per GPU), reinit-only, one step = "
+                                       f"ONE {n}x{n}x{n * world} {'fp32-mode' if f32 else 'fp64'} grid ({n}^3 points per GPU), reinit-only, one step = "
                                        f"{SWEEPS_PER_STEP} Gauss-Seidel raster sweeps (+BC+RMS each)",
                            "global_grid": [n, n, n * world],
                            "grid_per_gpu": list(shape_pts), "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX, "h": h,
@@ -344,12 +378,12 @@ def run_gpu(args):
                            "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
                            "last_rms": float(hist[-1]) if hist is not None else None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(n),
+                             "frac": achieved / peak if achieved else None, "traffic": None if f32 else ncu_traffic(n),
                              "traffic_note": "DRAM read+write bytes of one launch, ncu --set full (profiles/r1g_march_%d_full.txt); "
-                                             "algorithmic bytes per launch: %.4g" % (n, BYTES_PER_UPDATE * cells_per_launch),
-                             "kernel": "k_reinit_march" if args.sched == "march" else "k_reinit_plane",
+                                             "algorithmic bytes per launch: %.4g" % (n, bytes_per_update * cells_per_launch),
+                             "kernel": ("k_reinit_march_f32" if f32 else "k_reinit_march") if args.sched == "march" else "k_reinit_plane",
                              "launch_ms": launch_ms, "peak_source": peak_src,
-                             "fp64_pipe_frac": (FP64_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3)) / FP64_PIPE_PEAK if launch_ms > 0 else None,
+                             "fp64_pipe_frac": (FP64_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3)) / FP64_PIPE_PEAK if launch_ms > 0 and not f32 else None,
                              "fp64_pipe_note": "second roof: %d FP64-pipe instructions per cell update (SASS) vs %.1f T lane-ops/s "
                                                "(148 SM x 64 lanes x 1.965 GHz; micro-benchmarked 18.4 T, profiles/r1_fp64_pipe_ubench.txt)"
                                                % (FP64_PER_UPDATE, FP64_PIPE_PEAK / 1e12),
@@ -360,6 +394,7 @@ def run_gpu(args):
                          "api": "lsf_reinit (host-buffer drop-in)" if world == 1 else
                                 "lsf_grid_upload + lsf_grid_reinit + lsf_grid_download on each rank's slab"} if e2e else None),
                 "minmax_flow": mm,
+                "fp32_mode": fp32,
                 "sign_search": {"ms": sign_ms, "points": int(np.prod([g["box"][1] - g["box"][0] + 1, g["box"][3] - g["box"][2] + 1,
                                                                       g["box"][5] - g["box"][4] + 1])),
                                 "triangles": int(len(surfElem))},
@@ -381,6 +416,8 @@ def main():
     ap.add_argument("--ref-slab", type=int, default=32, help="z thickness of the CPU sample slab")
     ap.add_argument("--minmax-iters", type=int, default=64, help="min/max iterations of the companion measurement (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--f32", action="store_true", help="measure the optional fp32 mode as the main line (single GPU)")
+    ap.add_argument("--no-f32", action="store_true", help="skip the fp32-mode companion measurement")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

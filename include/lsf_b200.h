@@ -37,6 +37,7 @@ extern "C" {
 #define LSF_ERR_BAND_ON_BOUNDARY (-3) /* a narrow-band cell lies on the grid boundary: the
                                          reference would read phi(-1,..) (set3d.f90:402-403) */
 #define LSF_ERR_TIMEOUT (-4)          /* sharded grid: a neighbouring rank stopped answering */
+#define LSF_ERR_NODE_OFF_GRID (-5)    /* surface-node projection: a node left the grid (out-of-bounds read in the reference) */
 #define LSF_IPC_HANDLE_BYTES 64       /* size of the opaque per-rank handle of lsf_sgrid_ipc_handle */
 
 /* arithmetic of the WENO5 cell update */
@@ -53,6 +54,11 @@ extern "C" {
 #define LSF_MINMAX_LIST 0  /* (default) active list of the cells that can still change, order-free speculative update */
 #define LSF_MINMAX_MARCH 1 /* whole-grid skewed march, one fused kernel per iteration; cross-check path */
 
+/* storage / arithmetic precision of the device fields (host arrays are REAL(8) in either mode) */
+#define LSF_PREC_F64 0 /* (default) the reference's REAL(8): phi within 1e-10 of the reference, bit-exact in EXACT arithmetic */
+#define LSF_PREC_F32 1 /* optional single-precision mode: 12 B per cell update, WENO5 sweep on the FP32 pipe;
+                          contract max|phi - phi_ref| <= 1e-4 * max|phi_ref| */
+
 typedef struct lsf_grid lsf_grid; /* a device-resident phi(0:nx,0:ny,0:nz) plus work arrays */
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -63,6 +69,7 @@ int lsf_set_arith(int arith);      /* LSF_ARITH_*  */
 int lsf_last_arith(void);          /* arithmetic the most recent lsf_*reinit call finished in (FAST or EXACT) */
 int lsf_set_sched(int sched);      /* LSF_SCHED_*  */
 int lsf_set_minmax_algo(int algo); /* LSF_MINMAX_* (used with LSF_SCHED_MARCH) */
+int lsf_set_precision(int prec);   /* LSF_PREC_*: precision lsf_reinit (host-buffer entry point) runs in; env LSF_PRECISION=f32 */
 long long lsf_last_minmax_active(void); /* LSF_MINMAX_LIST: cells on the active list of the most recent min/max call (this rank) */
 /* Timing of the kernels of the most recent lsf_*reinit / lsf_*minmax / lsf_*sign_init call,
  * CUDA events on the library's own stream: total ms, number of kernel launches. */
@@ -103,8 +110,25 @@ int lsf_minmax(double *phi, double *phiN, int32_t *phiNB, int32_t *phiSB,
                int nx, int ny, int nz, int iter, double dx, double h1, double tol,
                int *n_exit, double *rms_hist);
 
+/* Surface-node projection ("Advect Nodes"), set3d.f90:465-501: gradPhi = firstDeriv(order 8) (subs.f90:311-347,
+ * including the jp1 typo of :346) on the stencil band phiSB == 1 and 0 elsewhere (set3d.f90:372), setPhiSurf
+ * (subs.f90:1057-1170), then `iter` (reference: 1000) passes in which every node with phiSurf > 1E-13 moves by
+ * phiSurf*gradPhiSurf and is re-interpolated.  surfXX (nSurfNode,3): surfX on entry (set3d.f90:485), the moved
+ * nodes on exit; phiSurf (nSurfNode) and gradPhiSurf (nSurfNode,3) as the reference leaves them.  Bit-identical to
+ * the reference loop (which re-interpolates ALL nodes after every move: O(iter*nSurfNode^2)).
+ * n_moves (may be NULL): node moves executed.  LSF_ERR_NODE_OFF_GRID / LSF_ERR_BAND_ON_BOUNDARY where the reference
+ * would read out of bounds. */
+int lsf_advect_nodes(const double *phi, const int32_t *phiSB, int nx, int ny, int nz, const double xLo[3], double dx,
+                     double *surfXX, int nSurfNode, double *phiSurf, double *gradPhiSurf, int iter, long long *n_moves);
+
 /* ---- device-resident pipeline (no host round trip between stages) ------- */
 int lsf_grid_create(lsf_grid **g, int nx, int ny, int nz);
+/* fp32 mode: phi is stored as float on the device; the same lsf_grid_* calls apply (upload / download convert
+ * from / to the caller's REAL(8) arrays).  reinit runs natively in fp32; sign search and min/max flow -- a
+ * negligible share of a run -- execute the fp64 kernels on a transient fp64 copy and round the result.
+ * Not available: sharded grids, lsf_grid_download_phiN. */
+int lsf_grid_create_f32(lsf_grid **g, int nx, int ny, int nz);
+int lsf_grid_is_f32(lsf_grid *g);
 int lsf_grid_destroy(lsf_grid *g);
 int lsf_grid_fill(lsf_grid *g, double value);                       /* phi = value, set3d.f90:161 */
 int lsf_grid_upload(lsf_grid *g, const double *phi_host);           /* H2D, dense Fortran layout */
@@ -119,6 +143,10 @@ int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol,
 int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *phiSB_host);
 int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol,
                     int *n_exit, double *rms_hist);
+/* lsf_advect_nodes on the resident phi; phiSB is the band the reference holds at that point: that of the field the
+ * last narrowBand call saw (phi, or the previous iterate after a tolerance EXIT of lsf_grid_minmax). */
+int lsf_grid_advect_nodes(lsf_grid *g, const double xLo[3], double dx, double *surfXX, int nSurfNode,
+                          double *phiSurf, double *gradPhiSurf, int iter, long long *n_moves);
 
 /* ---- z-slab sharding over the GPUs of one node -----------------------------------
  * The reference is serial ("Parallel version is in the works", README.md:17).  Here phi(0:nx,0:ny,0:nz) is

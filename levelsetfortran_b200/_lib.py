@@ -17,11 +17,12 @@ c_i32_p = C.POINTER(C.c_int32)
 c_int_p = C.POINTER(C.c_int)
 
 LSF_OK, LSF_NAN = 0, 1
-LSF_ERR_CUDA, LSF_ERR_ARG, LSF_ERR_BAND_ON_BOUNDARY, LSF_ERR_TIMEOUT = -1, -2, -3, -4
+LSF_ERR_CUDA, LSF_ERR_ARG, LSF_ERR_BAND_ON_BOUNDARY, LSF_ERR_TIMEOUT, LSF_ERR_NODE_OFF_GRID = -1, -2, -3, -4, -5
 IPC_HANDLE_BYTES = 64
 ARITH_FAST, ARITH_EXACT, ARITH_AUTO = 0, 1, 2
 SCHED_MARCH, SCHED_PLANE = 0, 1
 MINMAX_LIST, MINMAX_MARCH = 0, 1
+PREC_F64, PREC_F32 = 0, 1
 
 # every symbol include/lsf_b200.h declares: name -> (restype, argtypes)
 _I, _D, _V = C.c_int, C.c_double, C.c_void_p
@@ -34,6 +35,7 @@ SYMBOLS = {
     "lsf_set_sched": (_I, [_I]),
     "lsf_set_minmax_algo": (_I, [_I]),
     "lsf_last_minmax_active": (C.c_longlong, []),
+    "lsf_set_precision": (_I, [_I]),
     "lsf_last_timing": (_I, [c_double_p, c_int_p]),
     "lsf_set_profile": (_I, [_I]),
     "lsf_last_sweep_timing": (_I, [c_double_p, c_int_p]),
@@ -41,7 +43,12 @@ SYMBOLS = {
     "lsf_reinit": (_I, [c_double_p, c_double_p, c_double_p, _I, _I, _I, _I, _D, _D, c_int_p, c_double_p]),
     "lsf_narrowband": (_I, [_I, _I, _I, _D, c_double_p, c_i32_p, c_i32_p]),
     "lsf_minmax": (_I, [c_double_p, c_double_p, c_i32_p, c_i32_p, _I, _I, _I, _I, _D, _D, _D, c_int_p, c_double_p]),
+    "lsf_advect_nodes": (_I, [c_double_p, c_i32_p, _I, _I, _I, c_double_p, _D, c_double_p, _I, c_double_p, c_double_p, _I,
+                              C.POINTER(C.c_longlong)]),
+    "lsf_grid_advect_nodes": (_I, [_V, c_double_p, _D, c_double_p, _I, c_double_p, c_double_p, _I, C.POINTER(C.c_longlong)]),
     "lsf_grid_create": (_I, [C.POINTER(_V), _I, _I, _I]),
+    "lsf_grid_create_f32": (_I, [C.POINTER(_V), _I, _I, _I]),
+    "lsf_grid_is_f32": (_I, [_V]),
     "lsf_grid_destroy": (_I, [_V]),
     "lsf_grid_fill": (_I, [_V, _D]),
     "lsf_grid_upload": (_I, [_V, _V]),

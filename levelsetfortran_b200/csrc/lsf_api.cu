@@ -450,15 +450,16 @@ using namespace lsf;
 // at all with LSF_NO_GRID_CACHE=1.
 static lsf_grid *g_cached = nullptr;
 
-static int host_grid_acquire(lsf_grid **out, int nx, int ny, int nz)
+static int host_grid_acquire(lsf_grid **out, int nx, int ny, int nz, bool f32 = false)
 {
-    if (g_cached && g_cached->dm.nx == nx && g_cached->dm.ny == ny && g_cached->dm.nz == nz && !sharded(g_cached)) {
+    if (g_cached && g_cached->dm.nx == nx && g_cached->dm.ny == ny && g_cached->dm.nz == nz && !sharded(g_cached) &&
+        (g_cached->f32 != 0) == f32) {
         *out = g_cached;
         g_cached = nullptr;
         return LSF_OK;
     }
     if (g_cached) { lsf_grid_destroy(g_cached); g_cached = nullptr; }
-    return lsf_grid_create(out, nx, ny, nz);
+    return f32 ? lsf_grid_create_f32(out, nx, ny, nz) : lsf_grid_create(out, nx, ny, nz);
 }
 
 static void host_grid_release(lsf_grid *g)
@@ -498,6 +499,7 @@ int lsf_init(int device)
         G.arith = (strcmp(a, "exact") == 0) ? LSF_ARITH_EXACT : (strcmp(a, "fast") == 0) ? LSF_ARITH_FAST : LSF_ARITH_AUTO;
     if (const char *s = getenv("LSF_SCHED")) G.sched = (strcmp(s, "plane") == 0) ? LSF_SCHED_PLANE : LSF_SCHED_MARCH;
     if (const char *m = getenv("LSF_MINMAX")) G.mm_algo = (strcmp(m, "march") == 0) ? LSF_MINMAX_MARCH : LSF_MINMAX_LIST;
+    if (const char *q = getenv("LSF_PRECISION")) G.prec = (strcmp(q, "f32") == 0) ? LSF_PREC_F32 : LSF_PREC_F64;
     G.inited = true;
     return LSF_OK;
 }
@@ -541,6 +543,13 @@ int lsf_set_minmax_algo(int algo)
 }
 
 long long lsf_last_minmax_active(void) { return G.mm_active; }
+
+int lsf_set_precision(int prec)
+{
+    if (prec != LSF_PREC_F64 && prec != LSF_PREC_F32) return set_error(LSF_ERR_ARG, "bad precision %d", prec);
+    G.prec = prec;
+    return LSF_OK;
+}
 
 int lsf_set_profile(int on)
 {
@@ -600,6 +609,7 @@ int lsf_grid_destroy(lsf_grid *g)
         cudaFree(g->shared_base);
         cudaFree(g->exch_counter);
     } else { cudaFree(g->phi); cudaFree(g->phiN); }
+    cudaFree(g->phi_f); cudaFree(g->phiS_f); cudaFree(g->phiN_f);
     cudaFree(g->phiS); cudaFree(g->lap); cudaFree(g->mask);
     cudaFree(g->partial); cudaFree(g->hist); cudaFree(g->ctrl);
     cudaFree(g->march_ticket); cudaFree(g->march_progress);
@@ -611,6 +621,7 @@ int lsf_grid_destroy(lsf_grid *g)
 int lsf_grid_fill(lsf_grid *g, double value)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    if (g->f32) return f32_fill(g, value);
     launch_fill(g, g->phi, value);                                      // ghost planes included: consistent on all ranks
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
@@ -619,6 +630,8 @@ int lsf_grid_fill(lsf_grid *g, double value)
 int lsf_grid_upload(lsf_grid *g, const double *phi_host)
 {
     if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
+    if (g->f32) return f32_upload(g, phi_host, g->phi_f);
+    g->sb_from_phiN = false;
     int rc = slab_check_attached(g);
     if (rc) return rc;
     // z-slab: the host array holds this rank's owned planes k0..k1-1 (a contiguous range of the global array)
@@ -631,6 +644,7 @@ int lsf_grid_upload(lsf_grid *g, const double *phi_host)
 int lsf_grid_download(lsf_grid *g, double *phi_host)
 {
     if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
+    if (g->f32) return f32_download(g, g->phi_f, phi_host);
     LSF_CUDA(cudaMemcpyAsync(phi_host, g->phi + owned_off(g), sizeof(double) * owned_elems(g), cudaMemcpyDeviceToHost, G.stream));
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
@@ -639,23 +653,36 @@ int lsf_grid_download(lsf_grid *g, double *phi_host)
 int lsf_grid_download_phiN(lsf_grid *g, double *phiN_host)
 {
     if (!g || !phiN_host) return set_error(LSF_ERR_ARG, "null argument");
+    if (g->f32) return set_error(LSF_ERR_ARG, "download_phiN: an fp32 grid keeps no phiN");
     LSF_CUDA(cudaMemcpyAsync(phiN_host, g->phiN + owned_off(g), sizeof(double) * owned_elems(g), cudaMemcpyDeviceToHost, G.stream));
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
 }
 
-void *lsf_grid_device_ptr(lsf_grid *g) { return g ? (void *)g->phi : nullptr; }
+void *lsf_grid_device_ptr(lsf_grid *g) { return g ? (g->f32 ? (void *)g->phi_f : (void *)g->phi) : nullptr; }
+
+int lsf_grid_is_f32(lsf_grid *g) { return g && g->f32 ? 1 : 0; }
 
 int lsf_grid_sign_init(lsf_grid *g, const double xLo[3], double dx, const double *surfX, int nSurfNode,
                        const int32_t *surfElem, int nSurfElem, int im, int ip, int jm, int jp, int km, int kp)
 {
     if (!g || !xLo || !surfX || !surfElem) return set_error(LSF_ERR_ARG, "null argument");
+    if (g->f32) {                                                       // fp64 search on a transient shadow, rounded to fp32
+        lsf_grid *sh = nullptr;
+        int rc = f32_shadow_open(g, &sh);
+        if (rc) return rc;
+        rc = sign_core(sh, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
+        const int rc2 = f32_shadow_close(g, sh, rc == LSF_OK);
+        return rc ? rc : rc2;
+    }
     return sign_core(g, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
 }
 
 int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    if (g->f32) return f32_reinit(g, iter, dx, h, tol, n_exit, rms_hist);
+    g->sb_from_phiN = false;
     return reinit_core(g, iter, dx, h, tol, nullptr, nullptr, n_exit, rms_hist);
 }
 
@@ -666,7 +693,8 @@ static int narrowband_to_host(Grid *g, const double *d_phi, double dx, int32_t *
     LSF_CUDA(cudaMalloc(&d_nb, bytes));
     cudaError_t e = cudaMalloc(&d_sb, bytes);
     if (e != cudaSuccess) { cudaFree(d_nb); return set_error(LSF_ERR_CUDA, "narrowband: %s", cudaGetErrorString(e)); }
-    launch_narrowband(g, d_phi, dx, d_nb, d_sb);
+    if (g->f32) f32_narrowband(g, dx, d_nb, d_sb);
+    else launch_narrowband(g, d_phi, dx, d_nb, d_sb);
     const size_t obytes = sizeof(int32_t) * owned_elems(g);
     if (nb_host) cudaMemcpyAsync(nb_host, d_nb + owned_off(g), obytes, cudaMemcpyDeviceToHost, G.stream);
     if (sb_host) cudaMemcpyAsync(sb_host, d_sb + owned_off(g), obytes, cudaMemcpyDeviceToHost, G.stream);
@@ -685,9 +713,19 @@ int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *ph
 int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol, int *n_exit, double *rms_hist)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    if (g->f32) {                                                       // fp64 flow on a transient shadow, rounded to fp32
+        lsf_grid *sh = nullptr;
+        int rc = f32_shadow_open(g, &sh);
+        if (rc) return rc;
+        const int st = lsf_grid_minmax(sh, iter, dx, h1, tol, n_exit, rms_hist);
+        rc = f32_shadow_close(g, sh, st >= 0);
+        return st ? st : rc;
+    }
     slab_exchange(g, false);                                            // z-slabs: phi's ghost planes current before they are copied
     LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, sizeof(double) * (size_t)g->np, cudaMemcpyDeviceToDevice, G.stream)); // set3d.f90:377
-    const int st = minmax_core(g, iter, dx, h1, tol, false, n_exit, rms_hist, nullptr);
+    int conv = 0;
+    const int st = minmax_core(g, iter, dx, h1, tol, false, n_exit, rms_hist, &conv);
+    g->sb_from_phiN = st >= 0 && conv;
     if (st >= 0) slab_exchange(g, false);
     return st;
 }
@@ -714,6 +752,18 @@ int lsf_reinit(double *phi, double *gradPhi, double *gradPhiMag, int nx, int ny,
 {
     if (!phi) return set_error(LSF_ERR_ARG, "null phi");
     lsf_grid *g = nullptr;
+    if (G.prec == LSF_PREC_F32) {
+        // fp32 mode (lsf_set_precision): host arrays stay REAL(8); gradPhi / gradPhiMag (dead downstream,
+        // set3d.f90:372-375) are not written
+        int rc = host_grid_acquire(&g, nx, ny, nz, true);
+        if (rc) return rc;
+        rc = lsf_grid_upload(g, phi);
+        int st = LSF_OK;
+        if (!rc) { st = f32_reinit(g, iter, dx, h, 1.E-5, n_exit, rms_hist); if (st < 0) rc = st; }
+        if (!rc) rc = lsf_grid_download(g, phi);
+        host_grid_release(g);
+        return rc ? rc : st;
+    }
     int rc = host_grid_acquire(&g, nx, ny, nz);
     if (rc) return rc;
     double *d_g = nullptr, *d_gm = nullptr;

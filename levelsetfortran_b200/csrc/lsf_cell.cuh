@@ -30,16 +30,19 @@ namespace lsf {
 LSF_HD double fmax_f(double a, double b) { return (b > a || a != a) ? b : a; }
 LSF_HD double fmin_f(double a, double b) { return (b < a || a != a) ? b : a; }
 
-struct CellConst {
-    double dx;       // grid spacing
-    double inv_dx;   // 1/dx
-    double k12;      // 1/(12 dx)
-    double dx2;      // dx*dx            (phiSign: dxx*dxx, subs.f90:169)
-    double h;        // pseudo-time step (subs.f90:750)
+template <class T>
+struct CellConstT {
+    T dx;       // grid spacing
+    T inv_dx;   // 1/dx
+    T k12;      // 1/(12 dx)
+    T dx2;      // dx*dx            (phiSign: dxx*dxx, subs.f90:169)
+    T h;        // pseudo-time step (subs.f90:750)
 };
+typedef CellConstT<double> CellConst;
 
 // ------------------------------------------------------------------------------------------
 struct ExactArith {
+    typedef double real;
 #if defined(__CUDA_ARCH__)
     static LSF_HD double mul(double a, double b) { return __dmul_rn(a, b); }
     static LSF_HD double add(double a, double b) { return __dadd_rn(a, b); }
@@ -141,6 +144,7 @@ struct ExactArith {
 
 // ------------------------------------------------------------------------------------------
 struct FastArith {
+    typedef double real;
     // ---- select-style helpers that stay off the FP64 pipe ---------------------------------------
     // (a double fmax/fmin costs a DSETP on the FP64 pipe plus ~6 integer instructions of NaN
     // fix-up; here the operands are known to be sign-definite, so integer compares on the bit
@@ -265,13 +269,107 @@ struct FastArith {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// F32Arith: the optional single-precision mode (fp32 storage, 12 B per cell update,
+// contract 1e-4 relative to the fp64 reference).  Same algebra as FastArith -- unscaled differences,
+// one reciprocal per side for the Jiang-Shu weights -- with two changes forced by the fp32 exponent
+// range: (1) the three E_k = eps + IS_k of a side are normalised by their sum before they are squared
+// and multiplied pairwise (eps >= 1e-6 max(e^2) bounds E_k / sum(E) from below by ~1e-9, so no product
+// of two squares leaves the normal range), (2) the 1.E-99 floor of subs.f90:533 becomes 1.E-30.
+// max/abs/select are native single instructions in fp32, so none of FastArith's integer tricks.
+struct F32Arith {
+    typedef float real;
+#if defined(__CUDA_ARCH__)
+    // MUFU approximations (1-2 ulp), flush-to-zero: no denormal fix-up code around them
+    static LSF_HD float rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    static LSF_HD float rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    static LSF_HD float sqr(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+    static LSF_HD float rcp(float x) { return 1.0f / x; }
+    static LSF_HD float rsq(float x) { return 1.0f / sqrtf(x); }
+    static LSF_HD float sqr(float x) { return sqrtf(x); }
+#endif
+    static LSF_HD void weights(float E0, float E1, float E2, float &w0x2, float &w2mh)
+    {
+        const float rs = rcp((E0 + E1) + E2);
+        const float n0e = E0 * rs, n1e = E1 * rs, n2e = E2 * rs;
+        const float q0 = n0e * n0e, q1 = n1e * n1e, q2 = n2e * n2e;
+        const float n0 = q1 * q2, x = q0 * q2, y3 = 3.0f * (q0 * q1);
+        const float D = fmaf(6.0f, x, y3 + n0);
+        const float r = rcp(D);
+        w0x2 = (n0 + n0) * r;
+        w2mh = fmaf(y3, r, -0.5f);
+    }
+
+    template <bool YQ>
+    static LSF_HD void weno_dir(const float v[7], const CellConstT<float> &cc, float &dminus, float &dplus)
+    {
+        const float e0 = v[1] - v[0], e1 = v[2] - v[1], e2 = v[3] - v[2];
+        const float e3 = v[4] - v[3], e4 = v[5] - v[4], e5 = v[6] - v[5];
+        const float am = e1 - e0, bm = e2 - e1, c = e3 - e2, bp = e4 - e3, ap = e5 - e4;
+        const float tpa = ap - bp, tpb = bp - c, tmc = c - bm, tma = am - bm;
+        const float mc = fmaxf(fmaxf(fabsf(e1), fabsf(e2)), fmaxf(fabsf(e3), fabsf(e4)));
+        const float mp = YQ ? mc : fmaxf(mc, fabsf(e5));          // subs.f90:576: p5 == 0 in y
+        const float mm = fmaxf(mc, fabsf(e0));
+        const float tiny = 1.0e-30f;
+        const float epsp = fmaf(1.0e-6f * mp, mp, tiny);
+        const float epsm = fmaf(1.0e-6f * mm, mm, tiny);
+        const float s13b = (13.0f * tpb) * tpb, s13c = (13.0f * tmc) * tmc;
+        float t;
+        t = fmaf(-3.0f, bp, ap); const float E0p = fmaf(13.0f * tpa, tpa, fmaf(3.0f * t, t, epsp));
+        t = bp + c;              const float E1p = fmaf(3.0f * t, t, s13b + epsp);
+        t = fmaf(3.0f, c, -bm);  const float E2p = fmaf(3.0f * t, t, s13c + epsp);
+        t = fmaf(-3.0f, bm, am); const float E0m = fmaf(13.0f * tma, tma, fmaf(3.0f * t, t, epsm));
+        t = bm + c;              const float E1m = fmaf(3.0f * t, t, s13c + epsm);
+        t = fmaf(3.0f, c, -bp);  const float E2m = fmaf(3.0f * t, t, s13b + epsm);
+        float w0p2, w2ph, w0m2, w2mh;
+        weights(E0p, E1p, E2p, w0p2, w2ph);
+        weights(E0m, E1m, E2m, w0m2, w2mh);
+        const float s = tpb - tmc;
+        const float Yp = fmaf(w0p2, tpa - tpb, w2ph * s);
+        const float Ym = fmaf(w0m2, tma + tmc, w2mh * s);
+        const float cen = fmaf(7.0f, e2 + e3, -(e1 + e4));
+        dminus = cc.k12 * fmaf(-2.0f, Ym, cen);
+        dplus = cc.k12 * fmaf(2.0f, Yp, cen);
+    }
+
+    static LSF_HD void lo_dir(float vm, float vc, float vp, const CellConstT<float> &cc, float &dminus, float &dplus)
+    {
+        dminus = (vc - vm) * cc.inv_dx;
+        dplus = (vp - vc) * cc.inv_dx;
+    }
+
+    static LSF_HD float godunov(float phic, float a, float b, float c, float d, float e, float f, float g[3])
+    {
+        const bool pos = phic > 0.f;
+        const float x1 = fmaxf(pos ? a : b, 0.f), x2 = fminf(pos ? b : a, 0.f);
+        const float y1 = fmaxf(pos ? c : d, 0.f), y2 = fminf(pos ? d : c, 0.f);
+        const float z1 = fmaxf(pos ? e : f, 0.f), z2 = fminf(pos ? f : e, 0.f);
+        g[0] = fmaxf(x1 * x1, x2 * x2);
+        g[1] = fmaxf(y1 * y1, y2 * y2);
+        g[2] = fmaxf(z1 * z1, z2 * z2);
+        return sqr(g[0] + g[1] + g[2]);
+    }
+
+    // no conditioning guard in fp32 mode: the 1e-4 contract is far above the amplification FastArith guards against
+    static LSF_HD float update(float phic, float phiS, float gM, const CellConstT<float> &cc, bool &sens)
+    {
+        sens = false;
+        const float r = rsq(fmaf(phiS, phiS, cc.dx2 * gM));     // 0 * rsqrt(0) = NaN: the reference's 0/0 (subs.f90:169)
+        const float k1 = (phiS * r) * (1.0f - gM);
+        return fmaf(cc.h, k1, phic);
+    }
+};
+
 // Full cell update from the three 7-point lines (physical orientation, index 3 = centre).
 // hi = high-order branch condition of subs.f90:506.  Returns the new phi; g[3]/gM as in weno.
 template <class AR>
-LSF_HD double reinit_cell(const double vx[7], const double vy[7], const double vz[7], double phiS, bool hi,
-                          const CellConst &cc, double g[3], double &gM, bool &sens)
+LSF_HD typename AR::real reinit_cell(const typename AR::real vx[7], const typename AR::real vy[7],
+                                     const typename AR::real vz[7], typename AR::real phiS, bool hi,
+                                     const CellConstT<typename AR::real> &cc, typename AR::real g[3],
+                                     typename AR::real &gM, bool &sens)
 {
-    double a, b, c, d, e, f;
+    typename AR::real a, b, c, d, e, f;
     if (hi) {
         AR::template weno_dir<false>(vx, cc, a, b);
         AR::template weno_dir<true>(vy, cc, c, d);

@@ -37,6 +37,12 @@ struct lsf_grid {
     uint8_t *mml_unres;           // per point: undecided in the current iteration (all zero between iterations)
     long long *mml_work;          // queue of undecided cells
     int *mml_work_count;
+    // fp32 mode (lsf_f32.cu): f32 != 0 -> the fields live in these float arrays and the double ones are null
+    int f32;
+    float *phi_f, *phiS_f, *phiN_f;
+    // the stencil band phiSB of the reference after the min/max loop is the band of the field the LAST narrowBand
+    // call saw (set3d.f90:460): phiN after a tolerance EXIT, phi otherwise (lsf_nodes.cu)
+    bool sb_from_phiN;
     bool prev_sweep_valid;        // the previous launch on this grid was a sweep of the same free-running sequence
     long long prev_sweep_epoch;
     int prev_sweep_fb;
@@ -61,6 +67,7 @@ struct Global {
     int arith_last = LSF_ARITH_FAST;
     int sched = LSF_SCHED_MARCH;
     int mm_algo = LSF_MINMAX_LIST;
+    int prec = LSF_PREC_F64;       // precision of the host-buffer lsf_reinit entry point
     long long mm_active = 0;       // length of the active list of the most recent min/max call (this rank)
     int n_launch = 0;
     double last_ms = 0.;
@@ -115,7 +122,17 @@ template <class T> inline T *peer_ptr(const Grid *g, int rank, T *mine)
 int march_prepare(Grid *g);
 int march_ntiles(const Grid *g);
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc);
+void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc);
 const int *march_order();
+
+// lsf_f32.cu -- fp32 grids (g->f32)
+int f32_upload(Grid *g, const double *host, float *dev);
+int f32_download(Grid *g, const float *dev, double *host);
+int f32_fill(Grid *g, double value);
+int f32_narrowband(Grid *g, double dx, int32_t *d_nb, int32_t *d_sb);
+int f32_reinit(Grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist);
+int f32_shadow_open(Grid *g, lsf_grid **shadow);
+int f32_shadow_close(Grid *g, lsf_grid *shadow, bool write_back);
 
 // lsf_mm_march.cu
 int mm_march_prepare(Grid *g);

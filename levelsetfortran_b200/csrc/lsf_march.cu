@@ -1,5 +1,6 @@
 // lsf_march.cu -- GPU launch of the skewed x-marching column-tile sweep (lsf_march.cuh).
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #include "lsf_internal.cuh"
@@ -29,6 +30,37 @@ k_reinit_march(const MarchParams p)
 }
 
 typedef void (*MarchKernel)(const MarchParams);
+
+// ---- fp32 mode (F32Arith, float ring): single GPU -------------------------------------------------
+#ifndef LSF_OCC32
+#define LSF_OCC32 4
+#endif
+typedef MarchCfg<LSF_TB, LSF_TC, LSF_ROWS, float> CFG32;
+typedef MarchParamsT<float> MarchParamsF;
+
+template <bool FA, bool FB, bool FC>
+__global__ void __launch_bounds__(CFG32::THREADS, LSF_OCC32)
+k_reinit_march_f32(const MarchParamsF p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MarchSmem<CFG32> &sm = *reinterpret_cast<MarchSmem<CFG32> *>(smem_raw);
+    march_cta<F32Arith, FA, FB, FC, CFG32, false>(p, sm, threadIdx.x);
+}
+
+typedef void (*MarchKernelF)(const MarchParamsF);
+static MarchKernelF march_kernel_f32(int fa, int fb, int fc)
+{
+    switch ((fa ? 1 : 0) | (fb ? 2 : 0) | (fc ? 4 : 0)) {
+    case 0: return k_reinit_march_f32<false, false, false>;
+    case 1: return k_reinit_march_f32<true, false, false>;
+    case 2: return k_reinit_march_f32<false, true, false>;
+    case 3: return k_reinit_march_f32<true, true, false>;
+    case 4: return k_reinit_march_f32<false, false, true>;
+    case 5: return k_reinit_march_f32<true, false, true>;
+    case 6: return k_reinit_march_f32<false, true, true>;
+    default: return k_reinit_march_f32<true, true, true>;
+    }
+}
 
 template <class AR, bool MG>
 static MarchKernel march_kernel_mg(int fa, int fb, int fc)
@@ -73,7 +105,8 @@ static int march_order_tilt(const Grid *g)
     return sharded(g) ? 8 : 1;
 }
 
-static void march_orient_grid(MarchParams &p, const Grid *g, int raster)
+template <class T>
+static void march_orient_grid(MarchParamsT<T> &p, const Grid *g, int raster)
 {
     const SlabGeom &sg = g->sg;
     march_orient<CFG>(p, g->dm.nx, g->dm.ny, g->dm.nz, g->dm.sx, g->dm.sxy, raster, sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ);
@@ -110,9 +143,28 @@ int march_prepare(Grid *g)
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
         }
+        for (int o = 0; o < 8; ++o)
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel_f32(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG32>)));
         attr_done = true;
     }
     return LSF_OK;
+}
+
+// fp32 grid (lsf_f32.cu): same schedule, float phi / phiS and a float slot ring
+void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc)
+{
+    MarchParamsF p;
+    memset(&p, 0, sizeof(p));
+    march_orient_grid(p, g, raster);
+    p.phi = g->phi_f; p.phiS = g->phiS_f;
+    p.cc.dx = (float)cc.dx; p.cc.inv_dx = (float)cc.inv_dx; p.cc.k12 = (float)cc.k12; p.cc.dx2 = (float)cc.dx2; p.cc.h = (float)cc.h;
+    p.partial = g->partial; p.ticket = g->march_ticket; p.order = MH.d_order;
+    p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
+    cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
+    static const int occ = getenv("LSF_OCC32_RUN") ? atoi(getenv("LSF_OCC32_RUN")) : LSF_OCC32;   // experiments: fewer resident CTAs
+    const int ncta = p.ntiles < occ * G.num_sms ? p.ntiles : occ * G.num_sms;
+    march_kernel_f32(p.fa, p.fb, p.fc)<<<ncta, CFG32::THREADS, sizeof(MarchSmem<CFG32>), G.stream>>>(p);
+    G.n_launch++;
 }
 
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)

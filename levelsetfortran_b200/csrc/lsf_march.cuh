@@ -43,6 +43,8 @@ namespace lsf {
 LSF_DEV void p_sync() { __syncthreads(); }
 LSF_DEV double p_ldcg(const double *p) { return __ldcg(p); }
 LSF_DEV void p_stcg(double *p, double v) { __stcg(p, v); }
+LSF_DEV float p_ldcg(const float *p) { return __ldcg(p); }
+LSF_DEV void p_stcg(float *p, float v) { __stcg(p, v); }
 LSF_DEV void p_fence() { __threadfence(); }
 LSF_DEV unsigned p_ticket(unsigned *ctr) { return atomicAdd(ctr, 1u); }
 LSF_DEV long long p_ld_acquire(const long long *p)
@@ -81,6 +83,7 @@ LSF_DEV void p_st_release_sys(long long *p, long long v)
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 LSF_DEV void p_st_peer(double *p, double v) { __stcg(p, v); }
+LSF_DEV void p_st_peer(float *p, float v) { __stcg(p, v); }
 LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 }  // namespace lsf
 #endif
@@ -101,23 +104,30 @@ constexpr int M_ERR_TIMEOUT = -4;            // = LSF_ERR_TIMEOUT (include/lsf_b
 #ifndef LSF_ROWS
 #define LSF_ROWS 1
 #endif
-template <int TB_, int TC_, int R_ = LSF_ROWS>
+template <int TB_, int TC_, int R_ = LSF_ROWS, class T_ = double>
 struct MarchCfg {
+    typedef T_ real;                                          // element type of phi and of the slot ring
     static constexpr int TB = TB_, TC = TC_, R = R_;          // R rows (cells per step) per thread
     static constexpr int THREADS = TB * TC / R;
     static constexpr int SW = TB + 2 * M_H, SH = TC + 2 * M_H;
     // pitch of one c-row of positions, in doubles; for TB = 8 a warp spans 4 c-rows and the pitch
     // is padded to 8 (mod 16) doubles so that the two rows of a half-warp hit disjoint banks
-    static constexpr int RP = (TB >= 16) ? SW * M_SLOTW : ((SW * M_SLOTW + 15) / 16) * 16 + 8;
+    // fp32 ring: a warp spans two c-rows of 16 positions; the 17-float position stride puts one row on 16
+    // distinct banks, a pitch of 16 (mod 32) floats puts the other row on the complementary 16
+    static constexpr int RP_F64 = (TB >= 16) ? SW * M_SLOTW : ((SW * M_SLOTW + 15) / 16) * 16 + 8;
+    static constexpr int RP_F32 = ((SW * M_SLOTW + 15) / 32) * 32 + 16;
+    static constexpr int RP = sizeof(T_) == 4 ? RP_F32 : RP_F64;
     static constexpr int NHALO = 2 * M_H * (TB + TC);               // halo rows
     static constexpr int HR = (NHALO + THREADS - 1) / THREADS;      // halo rows fed per thread
     static constexpr int SMEM_DOUBLES = SH * RP;
 };
 typedef MarchCfg<16, 16> MarchCfgDefault;
+typedef MarchCfg<16, 16, 1, float> MarchCfgF32;
 
-struct MarchParams {
-    double *phi;
-    const double *phiS;
+template <class T>
+struct MarchParamsT {
+    T *phi;
+    const T *phiS;
     int nx, ny, nz;
     long long sa, sb, sc, off0;    // signed strides / origin of the sweep-oriented frame
     int fa, fb, fc;                // axis flipped?
@@ -126,7 +136,7 @@ struct MarchParams {
                                    // (whole grid on one GPU: 1, nz-1, nz; a z-slab with ghost planes: lsf_slab.cu)
     int ntb, ntc, ntiles;
     int tend;                      // last step index
-    CellConst cc;
+    CellConstT<T> cc;
     double *partial;               // per tile: sum over its cells of (new-old)^2
     unsigned *ticket;
     const int *order;              // ticket -> J | (K << 16)
@@ -157,6 +167,7 @@ struct MarchParams {
     long long edge_need;           // epoch of the previous sweep (tiles of row ntc-1 wait for it before reading / overwriting that rank's planes)
     int edge_prev_fb;              // b-orientation of the previous sweep (maps this sweep's tile columns onto that sweep's)
 };
+typedef MarchParamsT<double> MarchParams;
 
 // Spin until *flag >= need.  SYS: the flag is written by a peer GPU.  Gives up (and poisons the loop
 // status) after M_SPIN_LIMIT polls or as soon as another waiter has given up.
@@ -176,7 +187,7 @@ LSF_DEV void wait_ge(const long long *flag, long long need, Ctrl *ctrl)
 
 template <class CFG>
 struct MarchSmem {
-    double S[CFG::SMEM_DOUBLES];
+    typename CFG::real S[CFG::SMEM_DOUBLES];
     double red[CFG::THREADS];
     int tile;
 };
@@ -185,8 +196,8 @@ struct MarchSmem {
 // nz = last plane index of the LOCAL array.  Whole grid on one GPU: kupd_lo = 1, kupd_hi = nz-1, kbase = 0,
 // NZ = nz.  z-slab: local planes kupd_lo..kupd_hi are updated, local plane k is global plane k + kbase of
 // a grid 0..NZ (the high-order window of subs.f90:506 is a property of the GLOBAL index).
-template <class CFG>
-inline void march_orient(MarchParams &p, int nx, int ny, int nz, long long sx, long long sxy, int raster,
+template <class CFG, class T>
+inline void march_orient(MarchParamsT<T> &p, int nx, int ny, int nz, long long sx, long long sxy, int raster,
                          int kupd_lo = 1, int kupd_hi = -1, int kbase = 0, int NZ = -1)
 {
     if (kupd_hi < 0) kupd_hi = nz - 1;
@@ -229,11 +240,13 @@ inline void march_fill_order(int ntb, int ntc, int *order, int m = 1)
 // One cell of row `Sown` at step t: gather the 19 stencil values from the ring (orientation resolved at
 // compile time) and update.  HI: the caller knows the high-order branch applies (compile-time), else `hi`.
 template <class AR, bool FA, bool FB, bool FC, class CFG, bool HI>
-LSF_DEV double march_cell(const double *Sown, int t, double ps, bool hi, const CellConst &cc, bool &sens, double &df2)
+LSF_DEV typename AR::real march_cell(const typename AR::real *Sown, int t, typename AR::real ps, bool hi,
+                                     const CellConstT<typename AR::real> &cc, bool &sens, typename AR::real &df2)
 {
+    typedef typename AR::real real;
     constexpr int W = M_SLOTW, RP = CFG::RP;
-    const double *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
-    double vx[7], vy[7], vz[7];
+    const real *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
+    real vx[7], vy[7], vz[7];
 #pragma unroll
     for (int m = -3; m <= 3; ++m) {
         vx[FA ? 3 - m : 3 + m] = Wn[3 + m];
@@ -243,26 +256,27 @@ LSF_DEV double march_cell(const double *Sown, int t, double ps, bool hi, const C
         }
     }
     vy[3] = vx[3]; vz[3] = vx[3];
-    double g[3], gM;
-    const double pn = reinit_cell<AR>(vx, vy, vz, ps, HI ? true : hi, cc, g, gM, sens);
-    const double df = pn - vx[3];
+    real g[3], gM;
+    const real pn = reinit_cell<AR>(vx, vy, vz, ps, HI ? true : hi, cc, g, gM, sens);
+    const real df = pn - vx[3];
     df2 = df * df;
     return pn;
 }
 
 // MG = false compiles the z-slab hooks (peer stores, peer flags) out of the single-GPU kernel.
 template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true>
-LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K)
+LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K)
 {
+    typedef typename AR::real real;
     constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP, R = CFG::R;
     constexpr int W = M_SLOTW;
     // thread tid owns rows tid, tid + THREADS, ... of the tile (row q: tb = q % TB, tc = q / TB); all rows of a
     // step lie on one hyperplane, so the R cells a thread updates per step are independent of each other
     bool rowValid[R], compValid[R], pushRow[R], pushUpRow[R], hiBC[R];
     int sig[R];
-    double *Sown[R];
-    double *pOut[R];
-    const double *pSgn[R];
+    real *Sown[R];
+    real *pOut[R];
+    const real *pSgn[R];
     constexpr long long SA = FA ? -1 : 1;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -285,8 +299,8 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
     // halo duty: thread q feeds halo rows q, q+THREADS, ... (< NHALO)
     bool hvalid[CFG::HR], hlow[CFG::HR];
     int hsig[CFG::HR];
-    const double *hrow[CFG::HR];
-    double *hS[CFG::HR];
+    const real *hrow[CFG::HR];
+    real *hS[CFG::HR];
 #pragma unroll
     for (int r = 0; r < CFG::HR; ++r) {
         const int q = tid + r * THREADS;
@@ -335,13 +349,13 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
         p_sync();
     }
 
-    double acc = 0.;
+    real acc = 0;
 #if defined(LSF_EXP_TIMING)
     long long dbg_wait = 0, dbg_t0 = 0, dbg_c0 = 0;
     if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); dbg_c0 = clock64(); }
 #endif
     // cell ah of each halo row, advanced by one cell per step
-    const double *hp[CFG::HR];
+    const real *hp[CFG::HR];
 #pragma unroll
     for (int r = 0; r < CFG::HR; ++r)
         hp[r] = hrow[r] + (long long)(1 - M_LOOK + (hlow[r] ? 0 : M_LOOK) - hsig[r]) * SA;
@@ -367,25 +381,25 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
         p_emu_hook(tid == 0 && t == 6);
         // ---- (1) issue the global loads of this step --------------------------------------
         bool ldLook[R], active[R], hi[R];
-        double la[R], ps[R];
+        real la[R], ps[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int a = 1 + t - sig[r];
             const int a4 = a + M_LOOK;
             ldLook[r] = rowValid[r] && (a4 >= 0) && (a4 <= p.nx);
-            la[r] = 0.;
+            la[r] = 0;
             if (ldLook[r]) la[r] = p_ldcg(pOut[r] + M_LOOK * SA);
             active[r] = compValid[r] && (a >= 1) && (a <= p.nx - 1);
-            ps[r] = 0.;
+            ps[r] = 0;
             if (active[r]) ps[r] = p_ldcg(pSgn[r]);
             hi[r] = hiBC[r] && (a >= p.lo_a) && (a <= p.hi_a);
         }
         bool hdep[CFG::HR];
-        double hv[CFG::HR];
+        real hv[CFG::HR];
         int hh[CFG::HR];
 #pragma unroll
         for (int r = 0; r < CFG::HR; ++r) {
-            hdep[r] = false; hv[r] = 0.; hh[r] = 0;
+            hdep[r] = false; hv[r] = 0; hh[r] = 0;
             if (hvalid[r]) {
                 hh[r] = hlow[r] ? t : t + M_LOOK;
                 const int ah = 1 + hh[r] - hsig[r];
@@ -394,7 +408,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             hp[r] += SA;
         }
         // ---- (2) cell updates ---------------------------------------------------------------
-        double pn[R];
+        real pn[R];
         bool sens = false;
         bool fused = false;
         if (R == 2) {
@@ -402,7 +416,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
             // independent dependence chains interleave on the FP64 pipe
             if (active[0] && active[R - 1] && hi[0] && hi[R - 1]) {
                 bool s0, s1;
-                double d0, d1;
+                real d0, d1;
                 pn[0] = march_cell<AR, FA, FB, FC, CFG, true>(Sown[0], t, ps[0], true, p.cc, s0, d0);
                 pn[R - 1] = march_cell<AR, FA, FB, FC, CFG, true>(Sown[R - 1], t, ps[R - 1], true, p.cc, s1, d1);
                 sens = s0 || s1;
@@ -414,10 +428,10 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
         if (!fused) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                pn[r] = 0.;
+                pn[r] = 0;
                 if (active[r]) {
                     bool s0;
-                    double d0;
+                    real d0;
                     pn[r] = march_cell<AR, FA, FB, FC, CFG, false>(Sown[r], t, ps[r], hi[r], p.cc, s0, d0);
                     sens = sens || s0;
                     acc += d0;
@@ -432,14 +446,14 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
                 p_stcg(pOut[r], pn[r]);
                 if (pushRow[r]) p_st_peer(pOut[r] + p.push_delta, pn[r]);
                 if (pushUpRow[r]) p_st_peer(pOut[r] + p.push_up_delta, pn[r]);
-                double *d = Sown[r] + (t & (M_NSLOT - 1)); d[0] = pn[r]; d[M_NSLOT] = pn[r];
+                real *d = Sown[r] + (t & (M_NSLOT - 1)); d[0] = pn[r]; d[M_NSLOT] = pn[r];
             }
-            if (ldLook[r]) { double *d = Sown[r] + ((t + M_LOOK) & (M_NSLOT - 1)); d[0] = la[r]; d[M_NSLOT] = la[r]; }
+            if (ldLook[r]) { real *d = Sown[r] + ((t + M_LOOK) & (M_NSLOT - 1)); d[0] = la[r]; d[M_NSLOT] = la[r]; }
             pOut[r] += SA; pSgn[r] += SA;
         }
 #pragma unroll
         for (int r = 0; r < CFG::HR; ++r)
-            if (hdep[r]) { double *d = hS[r] + (hh[r] & (M_NSLOT - 1)); d[0] = hv[r]; d[M_NSLOT] = hv[r]; }
+            if (hdep[r]) { real *d = hS[r] + (hh[r] & (M_NSLOT - 1)); d[0] = hv[r]; d[M_NSLOT] = hv[r]; }
         // ---- (4) publish progress every CHUNK steps -----------------------------------------
         // (all threads' stores -> CTA barrier -> one thread's gpu-scope release: cumulative, so the
         // whole tile's stores of this chunk are visible to whoever acquires the flag)
@@ -455,7 +469,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
         }
     }
     // ---- tile done: final publish + deterministic block reduction of the RMS partial --------
-    sm.red[tid] = acc;
+    sm.red[tid] = (double)acc;
     p_sync();
     if (tid == 0) {
         p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN);
@@ -482,7 +496,7 @@ LSF_DEV void march_tile(const MarchParams &p, MarchSmem<CFG> &sm, const int tid,
 
 // Persistent CTA: take tickets until the tile list is exhausted.
 template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true>
-LSF_DEV void march_cta(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
+LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid)
 {
     if (p.ctrl->done) return;
     if (MG && p.halo_seq) {          // z-slab: both neighbours must have refreshed this rank's ghost planes
@@ -505,7 +519,7 @@ LSF_DEV void march_cta(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
 
 // Run-time orientation -> compile-time orientation.
 template <class AR, class CFG>
-LSF_DEV void march_cta_any(const MarchParams &p, MarchSmem<CFG> &sm, const int tid)
+LSF_DEV void march_cta_any(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid)
 {
     const int o = (p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0);
     switch (o) {

@@ -70,6 +70,13 @@ def set_minmax_algo(march: bool):
     check(lib().lsf_set_minmax_algo(_lib.MINMAX_MARCH if march else _lib.MINMAX_LIST))
 
 
+def set_precision(f32: bool):
+    """False (default): the reference's REAL(8) on the device; True: the optional fp32 mode of the host-buffer
+    `reinit` (device fields and WENO5 arithmetic in single precision, host arrays stay float64; contract
+    max|phi - phi_ref| <= 1e-4 max|phi_ref|; gradPhi / gradPhiMag are not written)."""
+    check(lib().lsf_set_precision(_lib.PREC_F32 if f32 else _lib.PREC_F64))
+
+
 def reinit(phi, gradPhi, gradPhiMag, nx, ny, nz, iter, dx, h, stop_on_nan=True):
     """SUBROUTINE reinit (subs.f90:717-931).  Returns (n_exit, rms_hist) -- the iteration index at
     which the loop left and the RMS errors the reference prints at subs.f90:923."""
@@ -122,13 +129,34 @@ def minMaxFlow(phi, phiN, phiNB, phiSB, nx, ny, nz, iter, dx, h1, tol=1.0e-7, st
     return n_exit.value, hist
 
 
+def advectNodes(phi, phiSB, nx, ny, nz, xLo, dx, surfX, iter=1000):
+    """The "Advect Nodes" block of set3d.f90:465-501: firstDeriv(order 8) on the stencil band, setPhiSurf, and the
+    node loop (every node with phiSurf > 1E-13 moves by phiSurf*gradPhiSurf).  surfX (nSurfNode,3) is not modified;
+    returns (surfXX, phiSurf, gradPhiSurf, n_moves) as the reference leaves them."""
+    _grid_array(phi, nx, ny, nz, np.float64, "phi")
+    _grid_array(phiSB, nx, ny, nz, np.int32, "phiSB")
+    XX = np.asfortranarray(surfX, dtype=np.float64).copy(order="F")     # surfXX = surfX, set3d.f90:485
+    n = XX.shape[0]
+    ps = np.zeros(n)
+    gs = np.zeros((n, 3), order="F")
+    xLo = np.ascontiguousarray(xLo, dtype=np.float64)
+    moves = C.c_longlong(0)
+    check(lib().lsf_advect_nodes(_dp(phi), _ip(phiSB), nx, ny, nz, _dp(xLo), float(dx), _dp(XX), n, _dp(ps), _dp(gs),
+                                 int(iter), C.byref(moves)))
+    return XX, ps, gs, moves.value
+
+
 class DeviceGrid:
     """A device-resident phi(0:nx,0:ny,0:nz): sign search -> reinit -> min/max without host round trips."""
 
-    def __init__(self, nx, ny, nz):
+    def __init__(self, nx, ny, nz, f32=False):
+        """f32=True: the optional single-precision mode (phi stored as float on the device, reinit on the FP32
+        pipe; upload / download still take float64 host arrays)."""
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.f32 = bool(f32)
         self._h = C.c_void_p()
-        check(lib().lsf_grid_create(C.byref(self._h), self.nx, self.ny, self.nz))
+        create = lib().lsf_grid_create_f32 if self.f32 else lib().lsf_grid_create
+        check(create(C.byref(self._h), self.nx, self.ny, self.nz))
 
     @property
     def shape(self):
@@ -188,6 +216,21 @@ class DeviceGrid:
         n_exit = C.c_int(-1)
         rc = check(lib().lsf_grid_minmax(self._h, int(iter), float(dx), float(h1), float(tol), C.byref(n_exit), _dp(hist)))
         return rc, n_exit.value, hist[: n_exit.value]
+
+
+def _advect_nodes_method(self, xLo, dx, surfX, iter=1000):
+    """set3d.f90:465-501 on the resident phi (see advectNodes); returns (surfXX, phiSurf, gradPhiSurf, n_moves)."""
+    XX = np.asfortranarray(surfX, dtype=np.float64).copy(order="F")
+    n = XX.shape[0]
+    ps = np.zeros(n)
+    gs = np.zeros((n, 3), order="F")
+    xLo = np.ascontiguousarray(xLo, dtype=np.float64)
+    moves = C.c_longlong(0)
+    check(lib().lsf_grid_advect_nodes(self._h, _dp(xLo), float(dx), _dp(XX), n, _dp(ps), _dp(gs), int(iter), C.byref(moves)))
+    return XX, ps, gs, moves.value
+
+
+DeviceGrid.advectNodes = _advect_nodes_method
 
 
 def slab_range(nz, nranks, rank):

@@ -572,3 +572,132 @@ int orc_stl_read(const char *path, double *surfX_out, int32_t *surfElem_out, int
     free(tri); free(nodes);
     return ntri;
 }
+
+/* =========================================================================
+ * Surface-node projection ("Advect Nodes"), set3d.f90:465-501  
+ * ========================================================================= */
+
+/* firstDeriv, order == 8 branch, subs.f90:311-347 + :357-364.  Literal, including the typo of
+ * :346 (phi(i,jp1,k)*aa7 instead of jp2).  Writes gradPhi(i,j,k,1:3) and returns gMM. */
+double orc_firstderiv8(int i, int j, int k, int nx, int ny, int nz, double dx, const double *phi, double *gradPhi)
+{
+    const size_t sx = (size_t)nx + 1, sy = (size_t)ny + 1, np = sx * sy * ((size_t)nz + 1);
+    const double aa1 = 1. / 280., aa2 = -4. / 105., aa3 = 1. / 5., aa4 = -4. / 5.;
+    const double aa6 = 4. / 5, aa7 = -1. / 5., aa8 = 4. / 105., aa9 = -1. / 280.;
+#define P(a, b, c) phi[IDX(a, b, c)]
+    const double phiX = (P(i - 4, j, k) * aa1 + P(i - 3, j, k) * aa2 + P(i - 2, j, k) * aa3 + P(i - 1, j, k) * aa4 +
+                         P(i + 1, j, k) * aa6 + P(i + 2, j, k) * aa7 + P(i + 3, j, k) * aa8 + P(i + 4, j, k) * aa9) / dx;
+    const double phiY = (P(i, j - 4, k) * aa1 + P(i, j - 3, k) * aa2 + P(i, j - 2, k) * aa3 + P(i, j - 1, k) * aa4 +
+                         P(i, j + 1, k) * aa6 + P(i, j + 1, k) * aa7 + P(i, j + 3, k) * aa8 + P(i, j + 4, k) * aa9) / dx;
+    const double phiZ = (P(i, j, k - 4) * aa1 + P(i, j, k - 3) * aa2 + P(i, j, k - 2) * aa3 + P(i, j, k - 1) * aa4 +
+                         P(i, j, k + 1) * aa6 + P(i, j, k + 2) * aa7 + P(i, j, k + 3) * aa8 + P(i, j, k + 4) * aa9) / dx;
+#undef P
+    gradPhi[IDX(i, j, k)] = phiX;
+    gradPhi[IDX(i, j, k) + np] = phiY;
+    gradPhi[IDX(i, j, k) + 2 * np] = phiZ;
+    double gMM = phiX * phiX + phiY * phiY + phiZ * phiZ;
+    return sqrt(gMM);
+}
+
+/* set3d.f90:469-478: gradPhi (zeroed at :372) gets the order-8 derivative on the stencil band.
+ * A band cell closer than 4 points to the boundary makes the reference read outside phi's bounds (it does so
+ * on its own cube40 input: the 8.1*dx band reaches to 2 points from the boundary); what it reads there is
+ * undefined, so those entries are poisoned with NaN here and any node that would interpolate from one is
+ * reported (-3) instead of being given a made-up value.  Returns the number of poisoned cells. */
+int orc_gradphi_band8(int nx, int ny, int nz, double dx, const double *phi, const int32_t *phiSB, double *gradPhi)
+{
+    const size_t sx = (size_t)nx + 1, sy = (size_t)ny + 1, np = sx * sy * ((size_t)nz + 1);
+    int poisoned = 0;
+    for (int i = 0; i <= nx; ++i)
+        for (int j = 0; j <= ny; ++j)
+            for (int k = 0; k <= nz; ++k)
+                if (phiSB[IDX(i, j, k)] == 1) {
+                    if (i < 4 || j < 4 || k < 4 || i > nx - 4 || j > ny - 4 || k > nz - 4) {
+                        for (int c = 0; c < 3; ++c) gradPhi[IDX(i, j, k) + (size_t)c * np] = NAN;
+                        ++poisoned;
+                    } else
+                        orc_firstderiv8(i, j, k, nx, ny, nz, dx, phi, gradPhi);
+                }
+    return poisoned;
+}
+
+/* setPhiSurf for ONE node, subs.f90:1078-1166.  surfX / gradPhiSurf are (nSurfNode,3) column-major.
+ * Returns -5 if the node's cell lies outside the grid (out-of-bounds read in the reference). */
+static int set_phi_surf_node(int n, const double xLo[3], int nx, int ny, int nz, double dx, double *phiSurf, const double *phi,
+                             int nSurfNode, const double *surfX, double *gradPhiSurf, const double *gradPhi)
+{
+    const size_t sx = (size_t)nx + 1, sy = (size_t)ny + 1, np = sx * sy * ((size_t)nz + 1);
+    const double minX = xLo[0], minY = xLo[1], minZ = xLo[2];
+    const double x = surfX[n], y = surfX[n + (size_t)nSurfNode], z = surfX[n + 2 * (size_t)nSurfNode];
+    const double fi = floor((x - minX) / dx), fj = floor((y - minY) / dx), fk = floor((z - minZ) / dx);
+    if (!(fi >= 0 && fi <= nx - 1 && fj >= 0 && fj <= ny - 1 && fk >= 0 && fk <= nz - 1)) return -5;
+    const int i0 = (int)fi, j0 = (int)fj, k0 = (int)fk;
+    const double x0 = i0 * dx + minX, y0 = j0 * dx + minY, z0 = k0 * dx + minZ;
+    const int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    const double x1 = i1 * dx + minX, y1 = j1 * dx + minY, z1 = k1 * dx + minZ;
+    const double xd = (x - x0) / (x1 - x0), yd = (y - y0) / (y1 - y0), zd = (z - z0) / (z1 - z0);
+    for (int m = 0; m < 8; ++m)                                   /* poisoned corner: see orc_gradphi_band8 */
+        if (isnan(gradPhi[IDX(i0 + (m & 1), j0 + ((m >> 1) & 1), k0 + ((m >> 2) & 1))])) return -3;
+    double c00, c10, c01, c11, c0, c1;
+#define TRI(F, off)                                                                         \
+    c00 = F[IDX(i0, j0, k0) + off] * (1. - xd) + F[IDX(i1, j0, k0) + off] * xd;            \
+    c10 = F[IDX(i0, j1, k0) + off] * (1. - xd) + F[IDX(i1, j1, k0) + off] * xd;            \
+    c01 = F[IDX(i0, j0, k1) + off] * (1. - xd) + F[IDX(i1, j0, k1) + off] * xd;            \
+    c11 = F[IDX(i0, j1, k1) + off] * (1. - xd) + F[IDX(i1, j1, k1) + off] * xd;            \
+    c0 = c00 * (1. - yd) + c10 * yd;                                                        \
+    c1 = c01 * (1. - yd) + c11 * yd;
+    TRI(phi, 0)
+    phiSurf[n] = c0 * (1. - zd) + c1 * zd;
+    double gs[3];
+    for (int c = 0; c < 3; ++c) {
+        TRI(gradPhi, (size_t)c * np)
+        gs[c] = -(c0 * (1. - zd) + c1 * zd);
+    }
+#undef TRI
+    const double gradMag2 = gs[0] * gs[0] + gs[1] * gs[1] + gs[2] * gs[2];
+    if (gradMag2 < 1.E-7) {
+        gs[0] = gs[1] = gs[2] = 0.;
+    } else {
+        const double gradPhiMag = sqrt(gradMag2);
+        gs[0] = gs[0] / gradPhiMag; gs[1] = gs[1] / gradPhiMag; gs[2] = gs[2] / gradPhiMag;
+    }
+    for (int c = 0; c < 3; ++c) gradPhiSurf[n + (size_t)c * nSurfNode] = gs[c];
+    return 0;
+}
+
+/* SUBROUTINE setPhiSurf, subs.f90:1057-1170: all nodes. */
+int orc_set_phi_surf(const double xLo[3], int nx, int ny, int nz, double dx, double *phiSurf, const double *phi,
+                     int nSurfNode, const double *surfX, double *gradPhiSurf, const double *gradPhi)
+{
+    for (int n = 0; n < nSurfNode; ++n) {
+        const int rc = set_phi_surf_node(n, xLo, nx, ny, nz, dx, phiSurf, phi, nSurfNode, surfX, gradPhiSurf, gradPhi);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/* The node loop of set3d.f90:480-501.  literal != 0: exactly as written -- setPhiSurf over ALL nodes after
+ * every single move (O(iter * nNode^2): only for small inputs); literal == 0: only the moved node is
+ * re-interpolated, which is equivalent because setPhiSurf is a pure function of each node's own position
+ * (checked by tests/test_oracle_pins.py).  surfXX holds surfX on entry (:485).  Returns 0, or -5.
+ * moves (may be NULL) receives the number of node moves executed. */
+int orc_advect_nodes(const double xLo[3], int nx, int ny, int nz, double dx, const double *phi, const double *gradPhi,
+                     int nSurfNode, double *surfXX, double *phiSurf, double *gradPhiSurf, int iter, int literal, long long *moves)
+{
+    long long nm = 0;
+    for (int n = 0; n < nSurfNode; ++n) phiSurf[n] = 0.;                        /* set3d.f90:483 */
+    int rc = orc_set_phi_surf(xLo, nx, ny, nz, dx, phiSurf, phi, nSurfNode, surfXX, gradPhiSurf, gradPhi);   /* :487 */
+    if (rc) return rc;
+    for (int k = 1; k <= iter; ++k)                                             /* :491 */
+        for (int n = 0; n < nSurfNode; ++n)
+            if (phiSurf[n] > 1E-13) {                                           /* :493 */
+                for (int c = 0; c < 3; ++c)
+                    surfXX[n + (size_t)c * nSurfNode] = surfXX[n + (size_t)c * nSurfNode] + phiSurf[n] * gradPhiSurf[n + (size_t)c * nSurfNode];
+                ++nm;
+                if (literal) rc = orc_set_phi_surf(xLo, nx, ny, nz, dx, phiSurf, phi, nSurfNode, surfXX, gradPhiSurf, gradPhi);
+                else rc = set_phi_surf_node(n, xLo, nx, ny, nz, dx, phiSurf, phi, nSurfNode, surfXX, gradPhiSurf, gradPhi);
+                if (rc) return rc;
+            }
+    if (moves) *moves = nm;
+    return 0;
+}

@@ -69,6 +69,11 @@ def lib():
         L.orc_stl_ntri.argtypes = [C.c_char_p]
         L.orc_stl_read.restype = C.c_int
         L.orc_stl_read.argtypes = [C.c_char_p, c_double_p, c_i32_p, c_int_p]
+        L.orc_gradphi_band8.restype = C.c_int
+        L.orc_gradphi_band8.argtypes = [C.c_int] * 3 + [C.c_double, c_double_p, c_i32_p, c_double_p]
+        L.orc_advect_nodes.restype = C.c_int
+        L.orc_advect_nodes.argtypes = ([c_double_p] + [C.c_int] * 3 + [C.c_double, c_double_p, c_double_p, C.c_int]
+                                       + [c_double_p] * 3 + [C.c_int, C.c_int, C.POINTER(C.c_longlong)])
         _lib = L
     return _lib
 
@@ -183,3 +188,23 @@ def minmax(phi, iter, dx, h1, tol=1.0e-7):
 def weno_gm(phi, i, j, k, dx):
     nx, ny, nz = _chk(phi)
     return lib().orc_weno(i, j, k, nx, ny, nz, dx, _dp(phi), None, None)
+
+
+def advect_nodes(phi, phiSB, xLo, dx, surfX, iter=1000, literal=False):
+    """set3d.f90:465-501 (firstDeriv order 8 on the stencil band, setPhiSurf, the node loop).
+    Returns (status, surfXX, phiSurf, gradPhiSurf, n_moves); status -3 / -5: the reference would read out of bounds."""
+    nx, ny, nz = _chk(phi)
+    phiSB = np.asfortranarray(phiSB, dtype=np.int32)
+    grad = np.zeros(phi.shape + (3,), order="F")                      # gradPhi = 0., set3d.f90:372
+    lib().orc_gradphi_band8(nx, ny, nz, dx, _dp(phi), _ip(phiSB), _dp(grad))      # band cells it cannot evaluate in bounds are poisoned
+    st = 0
+    XX = np.asfortranarray(surfX, dtype=np.float64).copy(order="F")
+    n = XX.shape[0]
+    ps = np.zeros(n)
+    gs = np.zeros((n, 3), order="F")
+    moves = C.c_longlong(0)
+    if st == 0:
+        xLo = np.ascontiguousarray(xLo, dtype=np.float64)
+        st = lib().orc_advect_nodes(_dp(xLo), nx, ny, nz, dx, _dp(phi), _dp(grad), n, _dp(XX), _dp(ps), _dp(gs), int(iter),
+                                    1 if literal else 0, C.byref(moves))
+    return st, XX, ps, gs, moves.value

@@ -11,6 +11,8 @@ extern thread_local EmuCta *emu_cta;
 inline void p_sync() { pthread_barrier_wait(&emu_cta->bar); }
 inline double p_ldcg(const double *p) { return *(const volatile double *)p; }
 inline void p_stcg(double *p, double v) { *(volatile double *)p = v; }
+inline float p_ldcg(const float *p) { return *(const volatile float *)p; }
+inline void p_stcg(float *p, float v) { *(volatile float *)p = v; }
 inline void p_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned p_ticket(unsigned *ctr) { return __atomic_fetch_add(ctr, 1u, __ATOMIC_SEQ_CST); }
 inline long long p_ld_acquire(const long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
@@ -26,4 +28,5 @@ inline long long p_ld_relaxed_sys(const long long *p) { return __atomic_load_n(p
 inline void p_fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void p_st_release_sys(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void p_st_peer(double *p, double v) { *(volatile double *)p = v; }
+inline void p_st_peer(float *p, float v) { *(volatile float *)p = v; }
 }  // namespace lsf

@@ -428,3 +428,143 @@ extern "C" double emu_mm_list_iteration(const double *A, double *B, const unsign
     if (stats) { stats[0] = nband; stats[1] = ncomb; stats[2] = (long long)w.size(); }
     return s;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 mode (F32Arith, float slot ring, MarchCfgF32): one sweep through the production schedule, and the
+// literal lexicographic in-place loop (subs.f90:742-852) over the same cell arithmetic for comparison --
+// the schedule must be an exact re-ordering in fp32 too (bitwise equal on the CPU).
+typedef MarchCfg<16, 16, LSF_ROWS, float> CFGF;
+typedef MarchSmem<CFGF> SmemF;
+struct ThreadArgF { const MarchParamsT<float> *p; SmemF *sm; EmuCta *cta; int tid; };
+
+static void *thread_main_f32(void *v)
+{
+    ThreadArgF *a = (ThreadArgF *)v;
+    emu_cta = a->cta;
+    const MarchParamsT<float> &p = *a->p;
+    const int o = (p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0);
+    switch (o) {
+    case 0: march_cta<F32Arith, false, false, false, CFGF, false>(p, *a->sm, a->tid); break;
+    case 1: march_cta<F32Arith, true, false, false, CFGF, false>(p, *a->sm, a->tid); break;
+    case 2: march_cta<F32Arith, false, true, false, CFGF, false>(p, *a->sm, a->tid); break;
+    case 3: march_cta<F32Arith, true, true, false, CFGF, false>(p, *a->sm, a->tid); break;
+    case 4: march_cta<F32Arith, false, false, true, CFGF, false>(p, *a->sm, a->tid); break;
+    case 5: march_cta<F32Arith, true, false, true, CFGF, false>(p, *a->sm, a->tid); break;
+    case 6: march_cta<F32Arith, false, true, true, CFGF, false>(p, *a->sm, a->tid); break;
+    default: march_cta<F32Arith, true, true, true, CFGF, false>(p, *a->sm, a->tid); break;
+    }
+    return nullptr;
+}
+
+static void cc_f32(CellConstT<float> &cc, double dx, double h)
+{
+    cc.dx = (float)dx; cc.inv_dx = (float)(1. / dx); cc.k12 = (float)(1. / (12. * dx)); cc.dx2 = (float)(dx * dx); cc.h = (float)h;
+}
+
+extern "C" double emu_march_sweep_f32(float *phi, const float *phiS, int nx, int ny, int nz, int raster,
+                                      double dx, double h, int ncta)
+{
+    MarchParamsT<float> p;
+    memset(&p, 0, sizeof(p));
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    march_orient<CFGF>(p, nx, ny, nz, sx, sxy, raster);
+    p.phi = phi; p.phiS = phiS;
+    cc_f32(p.cc, dx, h);
+    std::vector<double> partial(p.ntiles, 0.);
+    std::vector<int> order(p.ntiles);
+    std::vector<long long> progress(p.ntiles, 0);
+    march_fill_order(p.ntb, p.ntc, order.data());
+    unsigned ticket = 0;
+    Ctrl ctrl = {0, 0, 0, 0, 0};
+    p.partial = partial.data(); p.order = order.data(); p.progress = progress.data();
+    p.ticket = &ticket; p.ctrl = &ctrl; p.epoch = 1;
+    if (ncta > p.ntiles) ncta = p.ntiles;
+    constexpr int NT = CFGF::THREADS;
+    std::vector<SmemF> sm(ncta);
+    std::vector<EmuCta> ctas(ncta);
+    std::vector<ThreadArgF> args((size_t)ncta * NT);
+    std::vector<pthread_t> th((size_t)ncta * NT);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    for (int c = 0; c < ncta; ++c) pthread_barrier_init(&ctas[c].bar, nullptr, NT);
+    for (int c = 0; c < ncta; ++c)
+        for (int t = 0; t < NT; ++t) {
+            ThreadArgF &a = args[(size_t)c * NT + t];
+            a.p = &p; a.sm = &sm[c]; a.cta = &ctas[c]; a.tid = t;
+            if (pthread_create(&th[(size_t)c * NT + t], &attr, thread_main_f32, &a) != 0) return -1.;
+        }
+    for (size_t q = 0; q < th.size(); ++q) pthread_join(th[q], nullptr);
+    for (int c = 0; c < ncta; ++c) pthread_barrier_destroy(&ctas[c].bar);
+    double s = 0.;
+    for (int q = 0; q < p.ntiles; ++q) s += partial[q];
+    return s;
+}
+
+// literal in-place raster sweep with the F32Arith cell (plus the closed-form boundary block when bc != 0)
+extern "C" void emu_lex_sweep_f32(float *phi, const float *phiS, int nx, int ny, int nz, int raster, double dx, double h, int bc)
+{
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    CellConstT<float> cc;
+    cc_f32(cc, dx, h);
+    int d[3];
+    raster_dirs(raster, d);
+    for (int a = 1; a <= nx - 1; ++a)
+        for (int b = 1; b <= ny - 1; ++b)
+            for (int c = 1; c <= nz - 1; ++c) {
+                const int i = d[0] > 0 ? a : nx - a, j = d[1] > 0 ? b : ny - b, k = d[2] > 0 ? c : nz - c;
+                const long long q = i + sx * j + sxy * k;
+                const bool hi = (i > 3) && (i < nx - 4) && (j > 3) && (j < ny - 4) && (k > 3) && (k < nz - 4);
+                float vx[7], vy[7], vz[7];
+                for (int m = -3; m <= 3; ++m) {
+                    const bool ok = hi || (m >= -1 && m <= 1);
+                    vx[m + 3] = ok ? phi[q + m] : 0.f;
+                    vy[m + 3] = ok ? phi[q + m * sx] : 0.f;
+                    vz[m + 3] = ok ? phi[q + m * sxy] : 0.f;
+                }
+                float g[3], gM;
+                bool sens;
+                phi[q] = reinit_cell<F32Arith>(vx, vy, vz, phiS[q], hi, cc, g, gM, sens);
+            }
+    if (!bc) return;
+    const float dxf = (float)dx;
+    for (int k = 0; k <= nz; ++k)
+        for (int j = 0; j <= ny; ++j)
+            for (int i = 0; i <= nx; ++i) {
+                const int B = (i == 0 || i == nx) + (j == 0 || j == ny) + (k == 0 || k == nz);
+                if (!B) continue;
+                const int H = (i == nx) + (j == ny) + (k == nz);
+                const int m = 1 + H < B ? 1 + H : B;
+                const int ci = i < 1 ? 1 : (i > nx - 1 ? nx - 1 : i), cj = j < 1 ? 1 : (j > ny - 1 ? ny - 1 : j),
+                          ck = k < 1 ? 1 : (k > nz - 1 ? nz - 1 : k);
+                float v = phi[ci + sx * cj + sxy * ck];
+                for (int r = 0; r < m; ++r) v = v + dxf;
+                phi[i + sx * j + sxy * k] = v;
+            }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Surface-node projection (lsf_nodes.cuh): the per-node code of the product kernel, run serially on the CPU.
+#include "../../levelsetfortran_b200/csrc/lsf_nodes.cuh"
+extern "C" int emu_advect_nodes(const double *phi, const double *sbsrc, int nx, int ny, int nz, const double *xLo, double dx,
+                                double *X, int nNode, double *phiSurf, double *gradPhiSurf, int iter, long long *moves)
+{
+    NodeConst c;
+    c.sx = nx + 1; c.sxy = c.sx * (ny + 1); c.nx = nx; c.ny = ny; c.nz = nz;
+    c.xLo[0] = xLo[0]; c.xLo[1] = xLo[1]; c.xLo[2] = xLo[2]; c.dx = dx; c.bSB = 8.1 * dx;
+    int worst = 0;
+    long long nm = 0;
+    for (int n = 0; n < nNode; ++n) {
+        double x[3] = {X[n], X[n + (size_t)nNode], X[n + 2 * (size_t)nNode]}, ps, gs[3];
+        int mv;
+        const int st = node_project(c, phi, sbsrc, x, ps, gs, iter, mv);
+        if (st > worst) worst = st;
+        if (st) continue;
+        X[n] = x[0]; X[n + (size_t)nNode] = x[1]; X[n + 2 * (size_t)nNode] = x[2];
+        phiSurf[n] = ps;
+        for (int q = 0; q < 3; ++q) gradPhiSurf[n + (size_t)q * nNode] = gs[q];
+        nm += mv;
+    }
+    if (moves) *moves = nm;
+    return worst;
+}

@@ -208,3 +208,32 @@ def test_minmax_march_given_mask(emu, oracle):
     m8 = np.asfortranarray(nb.astype(np.uint8))
     emu.emu_mm_iteration(A.ctypes.data_as(dp), B.ctypes.data_as(dp), m8.ctypes.data, nx, ny, nz, 0.05, 1.0e-4, 3)
     assert np.array_equal(B, a)
+
+
+# ------------------------------------------------------------------------------------ fp32 mode
+@pytest.mark.parametrize("shape,ncta", [((22, 21, 23), 1), ((24, 36, 22), 4), ((40, 38, 36), 6)])
+def test_f32_march_schedule_is_an_exact_reordering(emu, oracle, shape, ncta):
+    """The fp32 instantiation (F32Arith, float slot ring) of the production schedule against the literal in-place
+    raster loop over the same cell arithmetic: bit-identical for all 8 rasters; and within the fp32 contract
+    (1e-4 relative) of the fp64 oracle."""
+    fp = C.POINTER(C.c_float)
+    emu.emu_march_sweep_f32.restype = C.c_double
+    emu.emu_march_sweep_f32.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    emu.emu_lex_sweep_f32.restype = None
+    emu.emu_lex_sweep_f32.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    p0 = synth_field(shape, seed=1)
+    d = p0.copy(order="F")
+    pSd = p0.copy(order="F")
+    a = p0.astype(np.float32, order="F")
+    b = a.copy(order="F")
+    pS = a.copy(order="F")
+    nx, ny, nz = (s - 1 for s in shape)
+    for r in range(1, 9):
+        before = a.astype(np.float64)
+        emu.emu_lex_sweep_f32(a.ctypes.data_as(fp), pS.ctypes.data_as(fp), nx, ny, nz, r, 0.05, 0.0014, 0)
+        s = emu.emu_march_sweep_f32(b.ctypes.data_as(fp), pS.ctypes.data_as(fp), nx, ny, nz, r, 0.05, 0.0014, ncta)
+        assert np.array_equal(a, b), f"raster {r}: fp32 march differs from the fp32 lexicographic loop"
+        ref = float(((a.astype(np.float64) - before)[1:-1, 1:-1, 1:-1] ** 2).sum())
+        assert abs(s - ref) <= 1e-4 * max(ref, 1e-300)
+        oracle.reinit_sweep(d, pSd, 0.05, 0.0014, r)
+        assert np.abs(a - d).max() <= 1e-4 * np.abs(d).max()
