@@ -9,6 +9,7 @@
 !   CALL reinit(...)              subs.f90:717-931       CALL reinit_b200(...)      (same argument list)
 !   CALL narrowBand(...)          subs.f90:178-207       CALL narrowBand_b200(...)  (same argument list)
 !   inline min/max DO n loop      set3d.f90:394-462      CALL minMaxFlow_b200(...)
+!   "Advect Nodes" block          set3d.f90:465-501      CALL advectNodes_b200(...)
 !
 ! Build (the reference is compiled with -fdefault-real-8, Makefile:4, so REAL == REAL(c_double)
 ! and the default INTEGER == INTEGER(c_int); the module states the kinds explicitly so it is
@@ -28,13 +29,14 @@ USE, INTRINSIC :: ISO_C_BINDING
 IMPLICIT NONE
 PRIVATE
 
-PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched, lsf_set_minmax_algo
+PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched, lsf_set_minmax_algo, lsf_set_precision
 PUBLIC :: lsf_slab_range, lsf_sgrid_create, lsf_sgrid_ipc_handle, lsf_sgrid_attach, lsf_grid_destroy
-PUBLIC :: signSearch_b200, reinit_b200, narrowBand_b200, minMaxFlow_b200
-PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT, LSF_ARITH_AUTO
+PUBLIC :: signSearch_b200, reinit_b200, narrowBand_b200, minMaxFlow_b200, advectNodes_b200
+PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT, LSF_ARITH_AUTO, LSF_PREC_F64, LSF_PREC_F32
 
 INTEGER(c_int), PARAMETER :: LSF_OK = 0, LSF_NAN = 1
 INTEGER(c_int), PARAMETER :: LSF_ARITH_FAST = 0, LSF_ARITH_EXACT = 1, LSF_ARITH_AUTO = 2
+INTEGER(c_int), PARAMETER :: LSF_PREC_F64 = 0, LSF_PREC_F32 = 1
 
 INTERFACE
 
@@ -66,6 +68,14 @@ INTERFACE
       INTEGER(c_int), VALUE :: algo          ! 0 = active list (default), 1 = whole-grid march
       INTEGER(c_int) :: rc
    END FUNCTION lsf_set_minmax_algo
+
+   ! optional fp32 mode of reinit_b200 (device fields and WENO5 arithmetic in single precision; the REAL(8)
+   ! host arrays are unchanged; phi within 1e-4 relative of the fp64 path; gradPhi/gradPhiMag not written)
+   FUNCTION lsf_set_precision(prec) BIND(C, NAME='lsf_set_precision') RESULT(rc)
+      IMPORT :: c_int
+      INTEGER(c_int), VALUE :: prec          ! LSF_PREC_F64 (default) / LSF_PREC_F32
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_set_precision
 
    ! ---- z-slab sharding, one MPI rank per GPU (include/lsf_b200.h; calling sequence: INTEGRATION.md) ----
    FUNCTION lsf_slab_range(nz,nranks,rank,k0,k1) BIND(C, NAME='lsf_slab_range') RESULT(rc)
@@ -152,6 +162,20 @@ INTERFACE
       REAL(c_double) :: rms_hist(*)
       INTEGER(c_int) :: rc
    END FUNCTION c_lsf_minmax
+
+   FUNCTION c_lsf_advect_nodes(phi,phiSB,nx,ny,nz,xLo,dx,surfXX,nSurfNode,phiSurf,gradPhiSurf,iter,n_moves) &
+                               BIND(C, NAME='lsf_advect_nodes') RESULT(rc)
+      IMPORT :: c_int, c_double, c_int32_t, c_long_long
+      REAL(c_double), INTENT(IN) :: phi(*)
+      INTEGER(c_int32_t), INTENT(IN) :: phiSB(*)
+      INTEGER(c_int), VALUE :: nx,ny,nz
+      REAL(c_double), INTENT(IN) :: xLo(3)
+      REAL(c_double), VALUE :: dx
+      REAL(c_double) :: surfXX(*), phiSurf(*), gradPhiSurf(*)
+      INTEGER(c_int), VALUE :: nSurfNode, iter
+      INTEGER(c_long_long) :: n_moves
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_advect_nodes
 
 END INTERFACE
 
@@ -271,5 +295,31 @@ SUBROUTINE minMaxFlow_b200(phi,phiN,phiNB,phiSB,nx,ny,nz,iter,dx,h1,tol,nDone)
    DEALLOCATE(hist)
    IF (rc == LSF_NAN) STOP
 END SUBROUTINE minMaxFlow_b200
+
+!*************************************************************************************!
+! The "Advect Nodes" block, set3d.f90:465-501: firstDeriv(order 8) on the stencil band
+! (:469-478), surfXX = surfX (:485), setPhiSurf (:487) and the node loop (:489-501, iter =
+! 1000 in the reference).  The reference re-interpolates ALL nodes after every single node
+! move (O(iter*nSurfNode**2) trilinear interpolations -- the dominant cost of a run on
+! cube40.stl); the library moves every node independently and returns bit-identical
+! surfXX, phiSurf and gradPhiSurf.  gradPhi itself is not returned: the reference overwrites
+! it at :527-535 (firstDeriv order 2 over the whole grid) before any further use.
+!*************************************************************************************!
+SUBROUTINE advectNodes_b200(xLo,nx,ny,nz,dx,phi,phiSB,nSurfNode,surfX,surfXX,phiSurf,gradPhiSurf,iter)
+   INTEGER, INTENT(IN) :: nx,ny,nz,iter
+   INTEGER(c_int32_t), INTENT(IN) :: nSurfNode
+   REAL(c_double), INTENT(IN) :: xLo(3),dx
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(IN) :: phi
+   INTEGER(c_int32_t), DIMENSION(0:nx,0:ny,0:nz), INTENT(IN) :: phiSB
+   REAL(c_double), DIMENSION(nSurfNode,3), INTENT(IN) :: surfX
+   REAL(c_double), DIMENSION(nSurfNode,3), INTENT(OUT) :: surfXX,gradPhiSurf
+   REAL(c_double), DIMENSION(nSurfNode), INTENT(OUT) :: phiSurf
+   INTEGER(c_int) :: rc
+   INTEGER(c_long_long) :: n_moves
+   surfXX = surfX                                                     ! set3d.f90:485
+   rc = c_lsf_advect_nodes(phi,phiSB,INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),xLo,dx,surfXX, &
+                           INT(nSurfNode,c_int),phiSurf,gradPhiSurf,INT(iter,c_int),n_moves)
+   IF (rc < 0) CALL lsf_fail("advectNodes_b200", rc)
+END SUBROUTINE advectNodes_b200
 
 END MODULE lsf_b200

@@ -99,7 +99,12 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
     CellConst cc;
     cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
     const bool want_grad = d_gradPhi || d_gradPhiMag;
-    const bool march = (G.sched == LSF_SCHED_MARCH) && !want_grad;
+    const bool march = G.sched == LSF_SCHED_MARCH;
+    // gradPhi / gradPhiMag hold the weno outputs of the LAST executed sweep (subs.f90:696-703).  On the march
+    // schedule the sweeps themselves do not write them; instead phi is snapshotted before every sweep (the copy
+    // turns into a no-op once the loop has left, so the snapshot that survives is the input of the last executed
+    // sweep) and that one sweep is replayed afterwards on the snapshot by the plane-schedule kernel, which does.
+    const bool grad_replay = march && want_grad;
     int rc;
     if (march) { rc = march_prepare(g); if (rc) return rc; }
     else LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:732
@@ -109,6 +114,7 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
     *guard_hit = false;
     for (int n = 0; n <= iter; ++n) {                                   // subs.f90:735
         const int raster = n % 8 + 1;                                   // subs.f90:740,855
+        if (grad_replay) launch_copy_if_running(g, g->phiN, g->phi);
         SE.begin();
         if (march) launch_reinit_sweep_march(g, raster, cc);
         else launch_reinit_sweep_plane(g, raster, cc, d_gradPhi, d_gradPhiMag);
@@ -133,6 +139,14 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
     }
     LSF_CUDA(cudaGetLastError());
     const int ne = hc.done ? hc.n_exit : iter;
+    if (grad_replay && !*guard_hit) {
+        // replay sweep `ne` on its input (phiN) with the kernel that writes the weno outputs; both schedules are
+        // exact re-orderings of the same loop, so phiN ends up equal to phi
+        LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
+        launch_reinit_sweep_plane(g, ne % 8 + 1, cc, d_gradPhi, d_gradPhiMag, g->phiN);
+        LSF_CUDA(cudaMemcpyAsync(g->ctrl, &hc, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
+        LSF_CUDA(cudaStreamSynchronize(G.stream));
+    }
     if (G.profile && G.n_sweeps > ne + 1) G.n_sweeps = ne + 1;   // sweeps enqueued after the exit were no-ops
     if (n_exit) *n_exit = ne;
     if (rms_hist) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)(ne + 1), cudaMemcpyDeviceToHost));
@@ -586,7 +600,7 @@ int lsf_grid_create(lsf_grid **out, int nx, int ny, int nz)
     g->dm.sxy = g->dm.sx * ((long long)ny + 1);
     g->np = g->dm.sxy * ((long long)nz + 1);
     slab_geom(nz, 1, 0, g->sg);                                         // one slab: the whole grid
-    const size_t bytes = sizeof(double) * (size_t)g->np;
+    const size_t bytes = sizeof(double) * (size_t)g->np + 64;          // + one chunk: vector row readers may fetch a whole aligned chunk at the end
     cudaError_t e;
     if ((e = cudaMalloc(&g->phi, bytes)) != cudaSuccess || (e = cudaMalloc(&g->phiS, bytes)) != cudaSuccess ||
         (e = cudaMalloc(&g->phiN, bytes)) != cudaSuccess ||

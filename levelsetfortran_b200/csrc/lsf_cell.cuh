@@ -167,6 +167,15 @@ struct FastArith {
     static LSF_HD double rsq(double x) { return 1.0 / sqrt(x); }
 #endif
 
+#if defined(__CUDA_ARCH__)
+    static LSF_HD double dabs_i(double x)
+    {
+        int hi;
+        asm("and.b32 %0, %1, 0x7fffffff;" : "=r"(hi) : "r"(__double2hiint(x)));
+        return __hiloint2double(hi, __double2loint(x));
+    }
+#endif
+
     static LSF_HD double rcp(double x)
     {
 #if defined(__CUDA_ARCH__)
@@ -200,9 +209,17 @@ struct FastArith {
         const double e3 = v[4] - v[3], e4 = v[5] - v[4], e5 = v[6] - v[5];
         const double am = e1 - e0, bm = e2 - e1, c = e3 - e2, bp = e4 - e3, ap = e5 - e4;
         const double tpa = ap - bp, tpb = bp - c, tmc = c - bm, tma = am - bm;
+#if !defined(LSF_NO_ABS_INT) && defined(__CUDA_ARCH__)
+        // |e| through an opaque 32-bit AND on the high word (the 64-bit sign mask is turned into a
+        // DADD |x| by the compiler, i.e. back onto the FP64 pipe)
+        const double mc = max_nn(max_nn(dabs_i(e1), dabs_i(e2)), max_nn(dabs_i(e3), dabs_i(e4)));
+        const double mp = YQ ? mc : max_nn(mc, dabs_i(e5));
+        const double mm = max_nn(mc, dabs_i(e0));
+#else
         const double mc = max_nn(max_nn(dabs(e1), dabs(e2)), max_nn(dabs(e3), dabs(e4)));
         const double mp = YQ ? mc : max_nn(mc, dabs(e5));
         const double mm = max_nn(mc, dabs(e0));
+#endif
         const double tiny = 1.0e-60;
         const double epsp = fma(1.0e-6 * mp, mp, tiny);
         const double epsm = fma(1.0e-6 * mm, mm, tiny);

@@ -243,7 +243,7 @@ extern "C" int lsf_grid_create_f32(lsf_grid **out, int nx, int ny, int nz)
     g->dm.sxy = g->dm.sx * ((long long)ny + 1);
     g->np = g->dm.sxy * ((long long)nz + 1);
     slab_geom(nz, 1, 0, g->sg);
-    const size_t bytes = sizeof(float) * (size_t)g->np;
+    const size_t bytes = sizeof(float) * (size_t)g->np + 64;           // + one chunk: the sweep kernel reads whole aligned vectors (RowReader)
     cudaError_t e;
     if ((e = cudaMalloc(&g->phi_f, bytes)) != cudaSuccess || (e = cudaMalloc(&g->phiS_f, bytes)) != cudaSuccess ||
         (e = cudaMalloc(&g->partial, sizeof(double) * PARTIAL_CAP)) != cudaSuccess ||

@@ -88,7 +88,7 @@ int set_error(int code, const char *fmt, ...);
     } while (0)
 
 // lsf_kernels.cu
-void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double *gradPhi, double *gradPhiMag);
+void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double *gradPhi, double *gradPhiMag, double *phi = nullptr);
 void launch_reinit_bc(Grid *g, double dx);
 void launch_reinit_bc_rms(Grid *g, double dx, int partial_off);
 void launch_rms(Grid *g, bool copy);

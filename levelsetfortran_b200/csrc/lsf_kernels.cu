@@ -57,8 +57,9 @@ k_reinit_plane(double *__restrict__ phi, const double *__restrict__ phiS, Dims d
     }
 }
 
-void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double *gradPhi, double *gradPhiMag)
+void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double *gradPhi, double *gradPhiMag, double *phi)
 {
+    if (!phi) phi = g->phi;
     int d[3];
     raster_dirs(raster, d);
     const Dims &dm = g->dm;
@@ -66,11 +67,11 @@ void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double 
     const bool wg = gradPhi || gradPhiMag;
     for (int s = 3; s <= (dm.nx - 1) + (dm.ny - 1) + (dm.nz - 1); ++s) {
         if (G.arith_run == LSF_ARITH_EXACT) {
-            if (wg) k_reinit_plane<ExactArith, true><<<grd, blk, 0, G.stream>>>(g->phi, g->phiS, dm, d[0], d[1], d[2], s, cc, gradPhi, gradPhiMag, g->ctrl);
-            else k_reinit_plane<ExactArith, false><<<grd, blk, 0, G.stream>>>(g->phi, g->phiS, dm, d[0], d[1], d[2], s, cc, nullptr, nullptr, g->ctrl);
+            if (wg) k_reinit_plane<ExactArith, true><<<grd, blk, 0, G.stream>>>(phi, g->phiS, dm, d[0], d[1], d[2], s, cc, gradPhi, gradPhiMag, g->ctrl);
+            else k_reinit_plane<ExactArith, false><<<grd, blk, 0, G.stream>>>(phi, g->phiS, dm, d[0], d[1], d[2], s, cc, nullptr, nullptr, g->ctrl);
         } else {
-            if (wg) k_reinit_plane<FastArith, true><<<grd, blk, 0, G.stream>>>(g->phi, g->phiS, dm, d[0], d[1], d[2], s, cc, gradPhi, gradPhiMag, g->ctrl);
-            else k_reinit_plane<FastArith, false><<<grd, blk, 0, G.stream>>>(g->phi, g->phiS, dm, d[0], d[1], d[2], s, cc, nullptr, nullptr, g->ctrl);
+            if (wg) k_reinit_plane<FastArith, true><<<grd, blk, 0, G.stream>>>(phi, g->phiS, dm, d[0], d[1], d[2], s, cc, gradPhi, gradPhiMag, g->ctrl);
+            else k_reinit_plane<FastArith, false><<<grd, blk, 0, G.stream>>>(phi, g->phiS, dm, d[0], d[1], d[2], s, cc, nullptr, nullptr, g->ctrl);
         }
         G.n_launch++;
     }

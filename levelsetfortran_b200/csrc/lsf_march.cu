@@ -33,7 +33,7 @@ typedef void (*MarchKernel)(const MarchParams);
 
 // ---- fp32 mode (F32Arith, float ring): single GPU -------------------------------------------------
 #ifndef LSF_OCC32
-#define LSF_OCC32 4
+#define LSF_OCC32 4    // resident CTAs per SM: 64 registers per thread, no spills (2, 3 and 4 CTAs measured within 2 %)
 #endif
 typedef MarchCfg<LSF_TB, LSF_TC, LSF_ROWS, float> CFG32;
 typedef MarchParamsT<float> MarchParamsF;

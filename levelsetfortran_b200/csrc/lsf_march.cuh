@@ -45,6 +45,18 @@ LSF_DEV double p_ldcg(const double *p) { return __ldcg(p); }
 LSF_DEV void p_stcg(double *p, double v) { __stcg(p, v); }
 LSF_DEV float p_ldcg(const float *p) { return __ldcg(p); }
 LSF_DEV void p_stcg(float *p, float v) { __stcg(p, v); }
+// aligned VEC-element chunk, L1-bypassing (one LDG.64 / LDG.128)
+template <int VEC> LSF_DEV void p_ldcg_vec(const float *p, float *out)
+{
+    if (VEC == 4) { const float4 v = __ldcg(reinterpret_cast<const float4 *>(p)); out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+    else if (VEC == 2) { const float2 v = __ldcg(reinterpret_cast<const float2 *>(p)); out[0] = v.x; out[1] = v.y; }
+    else out[0] = __ldcg(p);
+}
+template <int VEC> LSF_DEV void p_ldcg_vec(const double *p, double *out)
+{
+    if (VEC == 2) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(p)); out[0] = v.x; out[1] = v.y; }
+    else out[0] = __ldcg(p);
+}
 LSF_DEV void p_fence() { __threadfence(); }
 LSF_DEV unsigned p_ticket(unsigned *ctr) { return atomicAdd(ctr, 1u); }
 LSF_DEV long long p_ld_acquire(const long long *p)
@@ -90,6 +102,26 @@ LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 
 namespace lsf {
 
+// Per-thread reader of one grid row that is walked one cell per step: fetches the aligned VEC-element chunk when the
+// walk enters it (one vector load per VEC cells instead of one scalar load per cell -- a warp's 32 lanes read 32
+// different rows, so every load instruction costs 32 L1TEX tag cycles whatever its width).  FA: the row is walked
+// towards lower addresses.  Elements of the chunk outside the row are fetched but never used (the arrays are padded).
+template <class real, int VEC, bool FA>
+struct RowReader {
+    real buf[VEC];
+    bool have;
+    LSF_DEV void reset() { have = false; }
+    LSF_DEV real get(const real *p)
+    {
+        const int idx = (int)(((unsigned long long)p / sizeof(real)) & (unsigned long long)(VEC - 1));
+        if (!have || idx == (FA ? VEC - 1 : 0)) { p_ldcg_vec<VEC>(p - idx, buf); have = true; }
+        real v = buf[0];
+#pragma unroll
+        for (int q = 1; q < VEC; ++q) v = (idx == q) ? buf[q] : v;
+        return v;
+    }
+};
+
 constexpr int M_H = 3;                       // stencil half-width
 constexpr int M_NSLOT = 8;                   // hyperplane slots in the ring (each stored twice)
 constexpr int M_SLOTW = 2 * M_NSLOT + 1;     // doubles per position: 16 + 1 pad (bank spread)
@@ -110,12 +142,28 @@ struct MarchCfg {
     static constexpr int TB = TB_, TC = TC_, R = R_;          // R rows (cells per step) per thread
     static constexpr int THREADS = TB * TC / R;
     static constexpr int SW = TB + 2 * M_H, SH = TC + 2 * M_H;
+#ifndef LSF_W32
+#define LSF_W32 M_SLOTW
+#endif
+    // elements per position: 16 slots + pad.  fp32 may use a different pad (LSF_W32) so that the column-halo
+    // deposits (stride = row pitch) do not all fall on two banks
+    static constexpr int W = sizeof(T_) == 4 ? LSF_W32 : M_SLOTW;
+#ifndef LSF_VEC32
+#define LSF_VEC32 1    // measured: 4 (LDG.128) is 5-18 % SLOWER than scalar loads -- the skew puts the lanes of a warp in
+#endif                 // different alignment phases, so the vector load is still issued every step, for a quarter of the lanes
+#ifndef LSF_VEC64
+#define LSF_VEC64 1
+#endif
+    // cells per global vector load of a row walk (RowReader); 1 = scalar loads
+    static constexpr int VEC = (R_ > 1) ? 1 : (sizeof(T_) == 4 ? LSF_VEC32 : LSF_VEC64);
     // pitch of one c-row of positions, in doubles; for TB = 8 a warp spans 4 c-rows and the pitch
     // is padded to 8 (mod 16) doubles so that the two rows of a half-warp hit disjoint banks
     // fp32 ring: a warp spans two c-rows of 16 positions; the 17-float position stride puts one row on 16
     // distinct banks, a pitch of 16 (mod 32) floats puts the other row on the complementary 16
     static constexpr int RP_F64 = (TB >= 16) ? SW * M_SLOTW : ((SW * M_SLOTW + 15) / 16) * 16 + 8;
-    static constexpr int RP_F32 = ((SW * M_SLOTW + 15) / 32) * 32 + 16;
+    // W = 17: one row of 16 positions covers 16 banks, pitch = 16 (mod 32) puts the next row on the other 16;
+    // W = 18: a row covers the 16 even banks, pitch = 1 (mod 32) puts the next row on the odd ones
+    static constexpr int RP_F32 = (W % 2) ? ((SW * W + 15) / 32) * 32 + 16 : ((SW * W + 30) / 32) * 32 + 1;
     static constexpr int RP = sizeof(T_) == 4 ? RP_F32 : RP_F64;
     static constexpr int NHALO = 2 * M_H * (TB + TC);               // halo rows
     static constexpr int HR = (NHALO + THREADS - 1) / THREADS;      // halo rows fed per thread
@@ -244,7 +292,7 @@ LSF_DEV typename AR::real march_cell(const typename AR::real *Sown, int t, typen
                                      const CellConstT<typename AR::real> &cc, bool &sens, typename AR::real &df2)
 {
     typedef typename AR::real real;
-    constexpr int W = M_SLOTW, RP = CFG::RP;
+    constexpr int W = CFG::W, RP = CFG::RP;
     const real *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
     real vx[7], vy[7], vz[7];
 #pragma unroll
@@ -269,7 +317,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 {
     typedef typename AR::real real;
     constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP, R = CFG::R;
-    constexpr int W = M_SLOTW;
+    constexpr int W = CFG::W;
     // thread tid owns rows tid, tid + THREADS, ... of the tile (row q: tb = q % TB, tc = q / TB); all rows of a
     // step lie on one hyperplane, so the R cells a thread updates per step are independent of each other
     bool rowValid[R], compValid[R], pushRow[R], pushUpRow[R], hiBC[R];
@@ -350,6 +398,11 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     }
 
     real acc = 0;
+    constexpr int VEC = CFG::VEC;
+    RowReader<real, VEC, FA> rdLook, rdSgn, rdHalo[CFG::HR];
+    rdLook.reset(); rdSgn.reset();
+#pragma unroll
+    for (int r = 0; r < CFG::HR; ++r) rdHalo[r].reset();
 #if defined(LSF_EXP_TIMING)
     long long dbg_wait = 0, dbg_t0 = 0, dbg_c0 = 0;
     if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); dbg_c0 = clock64(); }
@@ -363,8 +416,9 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     for (int t = -M_LOOK; t <= p.tend; ++t) {
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
         if (t >= 0 && (t % M_CHUNK) == 0) {
-            const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + TB);
-            const long long need_c = ebase + M_BIAS + (t + M_CHUNK - 1 + TC);
+            // (a vector load of a -b/-c halo row fetches the predecessor's cells of up to VEC-1 later steps)
+            const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + TB + (VEC - 1));
+            const long long need_c = ebase + M_BIAS + (t + M_CHUNK - 1 + TC + (VEC - 1));
 #if defined(LSF_EXP_TIMING)
             long long tw0 = 0;
             if (tid == 0) tw0 = clock64();
@@ -388,10 +442,22 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             const int a4 = a + M_LOOK;
             ldLook[r] = rowValid[r] && (a4 >= 0) && (a4 <= p.nx);
             la[r] = 0;
-            if (ldLook[r]) la[r] = p_ldcg(pOut[r] + M_LOOK * SA);
+#if !defined(LSF_EXP_NOLDG)
+            if (ldLook[r]) {
+                if constexpr (VEC > 1) la[r] = rdLook.get(pOut[r] + M_LOOK * SA);
+                else la[r] = p_ldcg(pOut[r] + M_LOOK * SA);
+            }
+#endif
             active[r] = compValid[r] && (a >= 1) && (a <= p.nx - 1);
             ps[r] = 0;
-            if (active[r]) ps[r] = p_ldcg(pSgn[r]);
+#if !defined(LSF_EXP_NOLDG)
+            if (active[r]) {
+                if constexpr (VEC > 1) ps[r] = rdSgn.get(pSgn[r]);
+                else ps[r] = p_ldcg(pSgn[r]);
+            }
+#else
+            if (active[r]) ps[r] = (real)0.5;
+#endif
             hi[r] = hiBC[r] && (a >= p.lo_a) && (a <= p.hi_a);
         }
         bool hdep[CFG::HR];
@@ -403,7 +469,15 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             if (hvalid[r]) {
                 hh[r] = hlow[r] ? t : t + M_LOOK;
                 const int ah = 1 + hh[r] - hsig[r];
-                if (hh[r] >= 0 && ah >= 0 && ah <= p.nx) { hv[r] = p_ldcg(hp[r]); hdep[r] = true; }
+#if !defined(LSF_EXP_NOLDG)
+                if (hh[r] >= 0 && ah >= 0 && ah <= p.nx) {
+                    if constexpr (VEC > 1) hv[r] = rdHalo[r].get(hp[r]);
+                    else hv[r] = p_ldcg(hp[r]);
+                    hdep[r] = true;
+                }
+#else
+                if (hh[r] >= 0 && ah >= 0 && ah <= p.nx) { hv[r] = (real)hh[r]; hdep[r] = true; }
+#endif
             }
             hp[r] += SA;
         }
@@ -443,7 +517,9 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (active[r]) {
+#if !defined(LSF_EXP_NOSTG)
                 p_stcg(pOut[r], pn[r]);
+#endif
                 if (pushRow[r]) p_st_peer(pOut[r] + p.push_delta, pn[r]);
                 if (pushUpRow[r]) p_st_peer(pOut[r] + p.push_up_delta, pn[r]);
                 real *d = Sown[r] + (t & (M_NSLOT - 1)); d[0] = pn[r]; d[M_NSLOT] = pn[r];

@@ -13,6 +13,7 @@ inline double p_ldcg(const double *p) { return *(const volatile double *)p; }
 inline void p_stcg(double *p, double v) { *(volatile double *)p = v; }
 inline float p_ldcg(const float *p) { return *(const volatile float *)p; }
 inline void p_stcg(float *p, float v) { *(volatile float *)p = v; }
+template <int VEC, class T> inline void p_ldcg_vec(const T *p, T *out) { for (int q = 0; q < VEC; ++q) out[q] = *(const volatile T *)(p + q); }
 inline void p_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned p_ticket(unsigned *ctr) { return __atomic_fetch_add(ctr, 1u, __ATOMIC_SEQ_CST); }
 inline long long p_ld_acquire(const long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }

