@@ -44,6 +44,9 @@ LSF_DEV void p_sync() { __syncthreads(); }
 LSF_DEV double p_ldcg(const double *p) { return __ldcg(p); }
 LSF_DEV void p_stcg(double *p, double v) { __stcg(p, v); }
 LSF_DEV float p_ldcg(const float *p) { return __ldcg(p); }
+// L1-allocating load: only for data no other CTA writes while this tile may still hold the line (phiS; OLD values)
+LSF_DEV double p_ldca(const double *p) { return __ldca(p); }
+LSF_DEV float p_ldca(const float *p) { return __ldca(p); }
 LSF_DEV void p_stcg(float *p, float v) { __stcg(p, v); }
 // aligned VEC-element chunk, L1-bypassing (one LDG.64 / LDG.128)
 template <int VEC> LSF_DEV void p_ldcg_vec(const float *p, float *out)
@@ -442,18 +445,27 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             const int a4 = a + M_LOOK;
             ldLook[r] = rowValid[r] && (a4 >= 0) && (a4 <= p.nx);
             la[r] = 0;
-#if !defined(LSF_EXP_NOLDG)
+#ifndef LSF_LD_CACHED
+#define LSF_LD_CACHED 0                // bit 0: look-ahead loads through L1, bit 1: phiS loads, bit 2: +b/+c halo rows (OLD values)
+#endif
+#if defined(LSF_EXP_NOLDG) && !defined(LSF_EXP_NOLDG_MASK)
+#define LSF_EXP_NOLDG_MASK 7
+#endif
+#if !defined(LSF_EXP_NOLDG_MASK)
+#define LSF_EXP_NOLDG_MASK 0           // timing experiments only (results wrong): 1 = no look-ahead load, 2 = no phiS load, 4 = no halo loads
+#endif
+#if !(LSF_EXP_NOLDG_MASK & 1)
             if (ldLook[r]) {
                 if constexpr (VEC > 1) la[r] = rdLook.get(pOut[r] + M_LOOK * SA);
-                else la[r] = p_ldcg(pOut[r] + M_LOOK * SA);
+                else la[r] = (LSF_LD_CACHED & 1) ? p_ldca(pOut[r] + M_LOOK * SA) : p_ldcg(pOut[r] + M_LOOK * SA);
             }
 #endif
             active[r] = compValid[r] && (a >= 1) && (a <= p.nx - 1);
             ps[r] = 0;
-#if !defined(LSF_EXP_NOLDG)
+#if !(LSF_EXP_NOLDG_MASK & 2)
             if (active[r]) {
                 if constexpr (VEC > 1) ps[r] = rdSgn.get(pSgn[r]);
-                else ps[r] = p_ldcg(pSgn[r]);
+                else ps[r] = (LSF_LD_CACHED & 2) ? p_ldca(pSgn[r]) : p_ldcg(pSgn[r]);
             }
 #else
             if (active[r]) ps[r] = (real)0.5;
@@ -469,10 +481,10 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             if (hvalid[r]) {
                 hh[r] = hlow[r] ? t : t + M_LOOK;
                 const int ah = 1 + hh[r] - hsig[r];
-#if !defined(LSF_EXP_NOLDG)
+#if !(LSF_EXP_NOLDG_MASK & 4)
                 if (hh[r] >= 0 && ah >= 0 && ah <= p.nx) {
                     if constexpr (VEC > 1) hv[r] = rdHalo[r].get(hp[r]);
-                    else hv[r] = p_ldcg(hp[r]);
+                    else hv[r] = ((LSF_LD_CACHED & 4) && !hlow[r]) ? p_ldca(hp[r]) : p_ldcg(hp[r]);
                     hdep[r] = true;
                 }
 #else

@@ -12,6 +12,8 @@ inline void p_sync() { pthread_barrier_wait(&emu_cta->bar); }
 inline double p_ldcg(const double *p) { return *(const volatile double *)p; }
 inline void p_stcg(double *p, double v) { *(volatile double *)p = v; }
 inline float p_ldcg(const float *p) { return *(const volatile float *)p; }
+inline double p_ldca(const double *p) { return *(const volatile double *)p; }
+inline float p_ldca(const float *p) { return *(const volatile float *)p; }
 inline void p_stcg(float *p, float v) { *(volatile float *)p = v; }
 template <int VEC, class T> inline void p_ldcg_vec(const T *p, T *out) { for (int q = 0; q < VEC; ++q) out[q] = *(const volatile T *)(p + q); }
 inline void p_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
