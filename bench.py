@@ -280,6 +280,18 @@ def run_gpu(args):
                            "dense_equivalent_GBs": 16.0 * mm_rate},
               "last_rms": float(hist_mm[-1]) if len(hist_mm) else None}
 
+    # ---- companion: surface-node projection (set3d.f90:465-501) of the STL's own nodes on the resident field ----
+    nodes = None
+    if world == 1 and not f32 and args.minmax_iters > 0:
+        try:
+            XX, ps_n, gs_n, n_moves = G.advectNodes(g["xLo"], DX, surfX, 1000)
+            nd_ms, _nl = _lib.last_timing()
+            nodes = {"metric": "surface-node projection (lsf_grid_advect_nodes), kernel ms", "ms": nd_ms, "nodes": int(len(surfX)),
+                     "moves": int(n_moves), "max_displacement": float(np.abs(XX - surfX).max()),
+                     "reference_cost": "O(moves x nodes) trilinear interpolations: %.3g" % (float(n_moves) * len(surfX))}
+        except Exception as e:      # e.g. a band point too close to the boundary: reported, not fatal for the bench line
+            nodes = {"error": str(e)[:200]}
+
     # ---- companion: the optional fp32 mode on the same geometry (single GPU; not part of `value`) ----
     fp32 = None
     if world == 1 and not f32 and not args.no_f32:
@@ -395,6 +407,7 @@ def run_gpu(args):
                                 "lsf_grid_upload + lsf_grid_reinit + lsf_grid_download on each rank's slab"} if e2e else None),
                 "minmax_flow": mm,
                 "fp32_mode": fp32,
+                "node_projection": nodes,
                 "sign_search": {"ms": sign_ms, "points": int(np.prod([g["box"][1] - g["box"][0] + 1, g["box"][3] - g["box"][2] + 1,
                                                                       g["box"][5] - g["box"][4] + 1])),
                                 "triangles": int(len(surfElem))},
