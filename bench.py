@@ -213,11 +213,9 @@ def run_gpu(args):
     cells_per_step = (nx - 1) * (ny - 1) * (nz - 1) * SWEEPS_PER_STEP     # whole job
 
     f32 = bool(args.f32)
-    if f32 and world > 1:
-        raise SystemExit("bench.py: the fp32 mode is single-GPU (sharded fp32 grids are not built)")
     bytes_per_update = 12.0 if f32 else BYTES_PER_UPDATE
     if world > 1:
-        G = ShardedGrid(nx, ny, nz)
+        G = ShardedGrid(nx, ny, nz, f32=f32)
         k_upd = min(G.k1 - 1, nz - 1) - max(G.k0, 1) + 1      # planes this rank's sweeps update
     else:
         G = DeviceGrid(nx, ny, nz, f32=f32)

@@ -126,7 +126,7 @@ int lsf_grid_create(lsf_grid **g, int nx, int ny, int nz);
 /* fp32 mode: phi is stored as float on the device; the same lsf_grid_* calls apply (upload / download convert
  * from / to the caller's REAL(8) arrays).  reinit runs natively in fp32; sign search and min/max flow -- a
  * negligible share of a run -- execute the fp64 kernels on a transient fp64 copy and round the result.
- * Not available: sharded grids, lsf_grid_download_phiN. */
+ * Not available: lsf_grid_download_phiN; on sharded fp32 grids (lsf_sgrid_create_f32) also min/max and node projection. */
 int lsf_grid_create_f32(lsf_grid **g, int nx, int ny, int nz);
 int lsf_grid_is_f32(lsf_grid *g);
 int lsf_grid_destroy(lsf_grid *g);
@@ -160,6 +160,8 @@ int lsf_grid_advect_nodes(lsf_grid *g, const double xLo[3], double dx, double *s
  * handles (MPI_Allgather / torch.distributed.all_gather) and every rank attaches. */
 int lsf_slab_range(int nz, int nranks, int rank, int *k0, int *k1);   /* owned planes [k0, k1) of rank */
 int lsf_sgrid_create(lsf_grid **g, int nx, int ny, int nz, int rank, int nranks);   /* nz: GLOBAL extent */
+int lsf_sgrid_create_f32(lsf_grid **g, int nx, int ny, int nz, int rank, int nranks);   /* the same slab in the optional fp32 mode:
+                                            fill, upload, download, sign_init, reinit, narrowband (no min/max, no node projection) */
 int lsf_sgrid_ipc_handle(lsf_grid *g, void *handle /* LSF_IPC_HANDLE_BYTES */);
 int lsf_sgrid_attach(lsf_grid *g, const void *handles /* nranks * LSF_IPC_HANDLE_BYTES, rank order */);
 int lsf_sgrid_sync_ghosts(lsf_grid *g);   /* refresh the ghost planes after writing phi through lsf_grid_device_ptr */

@@ -161,11 +161,23 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
 // of such a batch, phi is rolled back to the snapshot taken at the previous evaluation (phiN is free on
 // this path) and the sweeps up to the exit are replayed, so phi, n_exit and rms_hist are exactly those of
 // the sweep-by-sweep loop.  Snapshots are only taken when an EXIT is possible (tol > 0).
+// (fp64 and fp32 slabs alike: only the field pointers, the element size and the two launches differ)
+static void *field_phi(Grid *g) { return g->f32 ? (void *)g->phi_f : (void *)g->phi; }
+static void *field_phiN(Grid *g) { return g->f32 ? (void *)g->phiN_f : (void *)g->phiN; }
+static void sweep_any(Grid *g, int raster, const CellConst &cc)
+{
+    if (g->f32) launch_reinit_sweep_march_f32(g, raster, cc); else launch_reinit_sweep_march(g, raster, cc);
+}
+static void bc_rms_any(Grid *g, double dx, int off)
+{
+    if (g->f32) launch_reinit_bc_rms_f32(g, dx, off); else launch_reinit_bc_rms(g, dx, off);
+}
+
 static int reinit_attempt_slab(Grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist,
                                bool watch_guard, bool *guard_hit)
 {
     if (G.sched != LSF_SCHED_MARCH) return set_error(LSF_ERR_ARG, "reinit: a sharded grid supports the march schedule only");
-    const size_t bytes = sizeof(double) * (size_t)g->np;
+    const size_t bytes = (g->f32 ? sizeof(float) : sizeof(double)) * (size_t)g->np;
     LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
     CellConst cc;
     cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = h;
@@ -176,16 +188,16 @@ static int reinit_attempt_slab(Grid *g, int iter, double dx, double h, double to
     const int npart = march_ntiles(g) + BC_BLOCKS;
     Ctrl hc = {0, 0, 0, 0, 0};
     slab_exchange(g, false);                                            // ghost planes = neighbours' current phi
-    if (snap) LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));
+    if (snap) LSF_CUDA(cudaMemcpyAsync(field_phiN(g), field_phi(g), bytes, cudaMemcpyDeviceToDevice, G.stream));
     int batch_first = 0;
     long long seq_first = 0;
     SE.npend = 0;
     for (int n = 0; n <= iter; ++n) {                                   // subs.f90:735
         const int raster = n % 8 + 1;                                   // subs.f90:740,855
         SE.begin();
-        launch_reinit_sweep_march(g, raster, cc);
+        sweep_any(g, raster, cc);
         SE.end();
-        launch_reinit_bc_rms(g, dx, march_ntiles(g));                   // subs.f90:858-897 + boundary part of :902-914
+        bc_rms_any(g, dx, march_ntiles(g));                   // subs.f90:858-897 + boundary part of :902-914
         const long long seq = slab_publish_sum(g, npart);
         if (n == batch_first) seq_first = seq;
         if (n % 4 == 0 || n == iter) {                                  // after raster 1 / 5: the k direction flips next
@@ -197,19 +209,19 @@ static int reinit_attempt_slab(Grid *g, int iter, double dx, double h, double to
             if (hc.done) {
                 if (hc.status >= 0 && hc.n_exit < n && snap) {
                     // left in the middle of the batch: roll back and replay sweeps batch_first..n_exit
-                    LSF_CUDA(cudaMemcpyAsync(g->phi, g->phiN, bytes, cudaMemcpyDeviceToDevice, G.stream));
+                    LSF_CUDA(cudaMemcpyAsync(field_phi(g), field_phiN(g), bytes, cudaMemcpyDeviceToDevice, G.stream));
                     LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
                     slab_exchange(g, false);
                     for (int m = batch_first; m <= hc.n_exit; ++m) {
-                        launch_reinit_sweep_march(g, m % 8 + 1, cc);
-                        launch_reinit_bc_rms(g, dx, march_ntiles(g));
+                        sweep_any(g, m % 8 + 1, cc);
+                        bc_rms_any(g, dx, march_ntiles(g));
                     }
                     LSF_CUDA(cudaMemcpyAsync(g->ctrl, &hc, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
                     LSF_CUDA(cudaStreamSynchronize(G.stream));
                 }
                 break;
             }
-            if (snap && n < iter) LSF_CUDA(cudaMemcpyAsync(g->phiN, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));
+            if (snap && n < iter) LSF_CUDA(cudaMemcpyAsync(field_phiN(g), field_phi(g), bytes, cudaMemcpyDeviceToDevice, G.stream));
             batch_first = n + 1;
         }
     }
@@ -254,6 +266,27 @@ static int reinit_core(Grid *g, int iter, double dx, double h, double tol, doubl
                         : reinit_attempt(g, iter, dx, h, tol, d_gradPhi, d_gradPhiMag, n_exit, rms_hist, false, &guard_hit);
     }
     G.arith_last = G.arith_run;
+    rc = tm.stop();
+    if (rc) return rc;
+    return st;
+}
+
+// reinit on a sharded fp32 grid: the loop of reinit_attempt_slab on the float fields (no conditioning guard in fp32)
+static int f32_reinit_slab(Grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist)
+{
+    if (iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "reinit: bad iter/dx");
+    if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "reinit: grid too small");
+    int rc = slab_check_attached(g);
+    if (rc) return rc;
+    rc = ensure_hist(g, iter + 1);
+    if (rc) return rc;
+    LSF_CUDA(cudaMemcpyAsync(g->phiS_f, g->phi_f, sizeof(float) * (size_t)g->np, cudaMemcpyDeviceToDevice, G.stream));   // subs.f90:731
+    Timer tm;
+    tm.start();
+    G.sweep_ms = 0.; G.n_sweeps = 0;
+    bool guard_hit = false;
+    const int st = reinit_attempt_slab(g, iter, dx, h, tol, n_exit, rms_hist, false, &guard_hit);
+    G.arith_last = LSF_ARITH_FAST;
     rc = tm.stop();
     if (rc) return rc;
     return st;
@@ -443,9 +476,12 @@ static int sign_core(Grid *g, const double xLo[3], double dx, const double *surf
     LSF_CUDA(cudaMemcpyAsync(d_E, surfElem, sizeof(int32_t) * 3 * (size_t)nElem, cudaMemcpyHostToDevice, G.stream));
     Timer tm;
     tm.start();
-    launch_sign_init(g, xLo, dx, d_X, nNode, d_E, nElem, d_cen, im, ip, jm, jp, km, kp);
+    int rcs = LSF_OK;
+    if (g->f32) rcs = f32_sign_init(g, xLo, dx, d_X, nNode, d_E, nElem, d_cen, im, ip, jm, jp, km, kp);
+    else launch_sign_init(g, xLo, dx, d_X, nNode, d_E, nElem, d_cen, im, ip, jm, jp, km, kp);
     slab_exchange(g, false);
     int rc = tm.stop();
+    if (!rc) rc = rcs;
     cudaError_t e = cudaGetLastError();
     cudaFree(d_X); cudaFree(d_E); cudaFree(d_cen);
     if (rc) return rc;
@@ -623,7 +659,8 @@ int lsf_grid_destroy(lsf_grid *g)
         cudaFree(g->shared_base);
         cudaFree(g->exch_counter);
     } else { cudaFree(g->phi); cudaFree(g->phiN); }
-    cudaFree(g->phi_f); cudaFree(g->phiS_f); cudaFree(g->phiN_f);
+    if (!g->shared_base) { cudaFree(g->phi_f); cudaFree(g->phiN_f); }
+    cudaFree(g->phiS_f);
     cudaFree(g->phiS); cudaFree(g->lap); cudaFree(g->mask);
     cudaFree(g->partial); cudaFree(g->hist); cudaFree(g->ctrl);
     cudaFree(g->march_ticket); cudaFree(g->march_progress);
@@ -644,10 +681,16 @@ int lsf_grid_fill(lsf_grid *g, double value)
 int lsf_grid_upload(lsf_grid *g, const double *phi_host)
 {
     if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
-    if (g->f32) return f32_upload(g, phi_host, g->phi_f);
     g->sb_from_phiN = false;
     int rc = slab_check_attached(g);
     if (rc) return rc;
+    if (g->f32) {
+        rc = f32_upload(g, phi_host, g->phi_f + owned_off(g), (long long)owned_elems(g));
+        if (rc) return rc;
+        slab_exchange(g, false);
+        LSF_CUDA(cudaStreamSynchronize(G.stream));
+        return LSF_OK;
+    }
     // z-slab: the host array holds this rank's owned planes k0..k1-1 (a contiguous range of the global array)
     LSF_CUDA(cudaMemcpyAsync(g->phi + owned_off(g), phi_host, sizeof(double) * owned_elems(g), cudaMemcpyHostToDevice, G.stream));
     slab_exchange(g, false);
@@ -658,7 +701,7 @@ int lsf_grid_upload(lsf_grid *g, const double *phi_host)
 int lsf_grid_download(lsf_grid *g, double *phi_host)
 {
     if (!g || !phi_host) return set_error(LSF_ERR_ARG, "null argument");
-    if (g->f32) return f32_download(g, g->phi_f, phi_host);
+    if (g->f32) return f32_download(g, g->phi_f + owned_off(g), phi_host, (long long)owned_elems(g));
     LSF_CUDA(cudaMemcpyAsync(phi_host, g->phi + owned_off(g), sizeof(double) * owned_elems(g), cudaMemcpyDeviceToHost, G.stream));
     LSF_CUDA(cudaStreamSynchronize(G.stream));
     return LSF_OK;
@@ -681,21 +724,14 @@ int lsf_grid_sign_init(lsf_grid *g, const double xLo[3], double dx, const double
                        const int32_t *surfElem, int nSurfElem, int im, int ip, int jm, int jp, int km, int kp)
 {
     if (!g || !xLo || !surfX || !surfElem) return set_error(LSF_ERR_ARG, "null argument");
-    if (g->f32) {                                                       // fp64 search on a transient shadow, rounded to fp32
-        lsf_grid *sh = nullptr;
-        int rc = f32_shadow_open(g, &sh);
-        if (rc) return rc;
-        rc = sign_core(sh, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
-        const int rc2 = f32_shadow_close(g, sh, rc == LSF_OK);
-        return rc ? rc : rc2;
-    }
     return sign_core(g, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
 }
 
 int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
-    if (g->f32) return f32_reinit(g, iter, dx, h, tol, n_exit, rms_hist);
+    if (g->f32 && !sharded(g)) return f32_reinit(g, iter, dx, h, tol, n_exit, rms_hist);
+    if (g->f32) return f32_reinit_slab(g, iter, dx, h, tol, n_exit, rms_hist);
     g->sb_from_phiN = false;
     return reinit_core(g, iter, dx, h, tol, nullptr, nullptr, n_exit, rms_hist);
 }
@@ -727,6 +763,7 @@ int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *ph
 int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol, int *n_exit, double *rms_hist)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    if (g->f32 && sharded(g)) return set_error(LSF_ERR_ARG, "minmax: not available on a sharded fp32 grid");
     if (g->f32) {                                                       // fp64 flow on a transient shadow, rounded to fp32
         lsf_grid *sh = nullptr;
         int rc = f32_shadow_open(g, &sh);

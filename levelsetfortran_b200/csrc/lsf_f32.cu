@@ -10,7 +10,8 @@
 //   sign search and min/max flow are <1 % of the work of a run: they execute on a transient fp64 shadow grid
 //   (the fp64 kernels, results rounded to fp32) so that the sign field stays the fp64 one and the active-list
 //   exactness argument of lsf_mm_list.cuh is untouched.
-// Sharded fp32 grids are not built yet (LSF_ERR_ARG).
+// Sharded fp32 grids (lsf_sgrid_create_f32) run fill / upload / download / sign search / reinit / narrowBand: the
+// sweep kernel, the ghost-plane exchange and the loop control are the fp64 path's, instantiated for float.
 #include <stdlib.h>
 #include <string.h>
 
@@ -35,26 +36,30 @@ __global__ void k_fill_f(float *__restrict__ p, long long np, float v)
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < np; q += (long long)gridDim.x * blockDim.x) p[q] = v;
 }
 
-// Boundary block of reinit (closed form, see k_reinit_bc_rms in lsf_kernels.cu) + boundary part of the RMS sum.
+// Boundary block of reinit (closed form) + boundary part of the RMS sum: the fp32 twin of k_reinit_bc_rms
+// (lsf_kernels.cu), including its z-slab form (a rank visits the boundary points of its owned planes only).
 __global__ void __launch_bounds__(256)
-k_reinit_bc_rms_f32(float *__restrict__ phi, Dims dm, float dx, double *__restrict__ partial, const Ctrl *__restrict__ ctrl)
+k_reinit_bc_rms_f32(float *__restrict__ phi, Dims dm, float dx, double *__restrict__ partial, const Ctrl *__restrict__ ctrl,
+                    int kA, int kB, int kbase, int NZ, int hasLo, int hasHi)
 {
     if (ctrl->done) return;
     __shared__ double sh[256];
-    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzm = dm.nz - 1, nym = dm.ny - 1;
+    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzm = kB - kA + 1, nym = dm.ny - 1;
     const long long fk = nxp * nyp, fj = nxp * nzm, fi = nym * nzm;
-    const long long tot = 2 * (fk + fj + fi);
+    const long long nkf = (long long)(hasLo + hasHi) * fk;
+    const long long tot = nkf + 2 * (fj + fi);
     double acc = 0.;
     for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < tot; t0 += (long long)gridDim.x * blockDim.x) {
         long long t = t0;
         int i, j, k;
-        if (t < 2 * fk) { k = (t >= fk) ? dm.nz : 0; t %= fk; i = (int)(t % nxp); j = (int)(t / nxp); }
-        else if ((t -= 2 * fk) < 2 * fj) { j = (t >= fj) ? dm.ny : 0; t %= fj; i = (int)(t % nxp); k = 1 + (int)(t / nxp); }
-        else { t -= 2 * fj; i = (t >= fi) ? dm.nx : 0; t %= fi; j = 1 + (int)(t % nym); k = 1 + (int)(t / nym); }
-        const int B = (i == 0 || i == dm.nx) + (j == 0 || j == dm.ny) + (k == 0 || k == dm.nz);
-        const int H = (i == dm.nx) + (j == dm.ny) + (k == dm.nz);
+        if (t < nkf) { k = (t >= fk || !hasLo) ? NZ - kbase : -kbase; t %= fk; i = (int)(t % nxp); j = (int)(t / nxp); }
+        else if ((t -= nkf) < 2 * fj) { j = (t >= fj) ? dm.ny : 0; t %= fj; i = (int)(t % nxp); k = kA + (int)(t / nxp); }
+        else { t -= 2 * fj; i = (t >= fi) ? dm.nx : 0; t %= fi; j = 1 + (int)(t % nym); k = kA + (int)(t / nym); }
+        const int kg = k + kbase;
+        const int B = (i == 0 || i == dm.nx) + (j == 0 || j == dm.ny) + (kg == 0 || kg == NZ);
+        const int H = (i == dm.nx) + (j == dm.ny) + (kg == NZ);
         const int m = min(1 + H, B);
-        const int ci = min(max(i, 1), dm.nx - 1), cj = min(max(j, 1), dm.ny - 1), ck = min(max(k, 1), dm.nz - 1);
+        const int ci = min(max(i, 1), dm.nx - 1), cj = min(max(j, 1), dm.ny - 1), ck = min(max(kg, 1), NZ - 1) - kbase;
         float v = phi[ci + dm.sx * cj + dm.sxy * ck];
         for (int r = 0; r < m; ++r) v = __fadd_rn(v, dx);
         const long long q = i + dm.sx * j + dm.sxy * k;
@@ -69,6 +74,14 @@ k_reinit_bc_rms_f32(float *__restrict__ phi, Dims dm, float dx, double *__restri
         __syncthreads();
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+void launch_reinit_bc_rms_f32(Grid *g, double dx, int partial_off)
+{
+    const SlabGeom &sg = g->sg;
+    k_reinit_bc_rms_f32<<<BC_BLOCKS, 256, 0, G.stream>>>(g->phi_f, g->dm, (float)dx, g->partial + partial_off, g->ctrl, sg.kupd_lo,
+                                                         sg.kupd_hi, sg.kbase, sg.NZ, sg.k0 == 0, sg.k1 == sg.NZ + 1);
+    G.n_launch++;
 }
 
 __global__ void k_narrowband_f32(const float *__restrict__ phi, long long np, double bNB, double bSB,
@@ -97,14 +110,15 @@ static void convert_f2d(const float *src, double *dst, long long n)
 // nothing: simple and bounded in memory; PCIe is the limit either way)
 constexpr long long F32_STAGE = 1LL << 25;   // elements per chunk (256 MB of doubles)
 
-int f32_upload(Grid *g, const double *host, float *dev)
+int f32_upload(Grid *g, const double *host, float *dev, long long np)
 {
+    (void)g;
     double *stage = nullptr;
-    const long long cap = g->np < F32_STAGE ? g->np : F32_STAGE;
+    const long long cap = np < F32_STAGE ? np : F32_STAGE;
     LSF_CUDA(cudaMalloc(&stage, sizeof(double) * (size_t)cap));
     cudaError_t e = cudaSuccess;
-    for (long long o = 0; o < g->np && e == cudaSuccess; o += cap) {
-        const long long n = g->np - o < cap ? g->np - o : cap;
+    for (long long o = 0; o < np && e == cudaSuccess; o += cap) {
+        const long long n = np - o < cap ? np - o : cap;
         e = cudaMemcpyAsync(stage, host + o, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, G.stream);
         convert_d2f(stage, dev + o, n);
     }
@@ -114,14 +128,15 @@ int f32_upload(Grid *g, const double *host, float *dev)
     return LSF_OK;
 }
 
-int f32_download(Grid *g, const float *dev, double *host)
+int f32_download(Grid *g, const float *dev, double *host, long long np)
 {
+    (void)g;
     double *stage = nullptr;
-    const long long cap = g->np < F32_STAGE ? g->np : F32_STAGE;
+    const long long cap = np < F32_STAGE ? np : F32_STAGE;
     LSF_CUDA(cudaMalloc(&stage, sizeof(double) * (size_t)cap));
     cudaError_t e = cudaSuccess;
-    for (long long o = 0; o < g->np && e == cudaSuccess; o += cap) {
-        const long long n = g->np - o < cap ? g->np - o : cap;
+    for (long long o = 0; o < np && e == cudaSuccess; o += cap) {
+        const long long n = np - o < cap ? np - o : cap;
         convert_f2d(dev + o, stage, n);
         e = cudaMemcpyAsync(host + o, stage, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, G.stream);
     }
@@ -179,8 +194,7 @@ int f32_reinit(Grid *g, int iter, double dx, double h, double tol, int *n_exit, 
         if (G.profile) cudaEventRecord(pe[npend][0], G.stream);
         launch_reinit_sweep_march_f32(g, raster, cc);
         if (G.profile) { cudaEventRecord(pe[npend][1], G.stream); ++npend; }
-        k_reinit_bc_rms_f32<<<BC_BLOCKS, 256, 0, G.stream>>>(g->phi_f, g->dm, (float)dx, g->partial + ntiles, g->ctrl);   // :858-897
-        G.n_launch++;
+        launch_reinit_bc_rms_f32(g, dx, ntiles);                        // :858-897
         launch_finalize(g, ntiles + BC_BLOCKS, 0, tol);                 // :914-926
         if ((n + 1) % 8 == 0 || n == iter) {
             LSF_CUDA(cudaMemcpyAsync(&hc, g->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, G.stream));
@@ -205,6 +219,26 @@ int f32_reinit(Grid *g, int iter, double dx, double h, double tol, int *n_exit, 
     G.last_ms = ms;
     G.arith_last = LSF_ARITH_FAST;
     return hc.done ? hc.status : LSF_OK;
+}
+
+// Sign search on an fp32 grid (whole or z-slab): the fp64 kernels write into one temporary fp64 field holding the
+// widened phi, the result is rounded to fp32 -- so the sign field is the fp64 one, exact zeros and -0.0 included.
+int f32_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode, const int32_t *d_surfElem, int nElem,
+                  double *d_cen, int im, int ip, int jm, int jp, int km, int kp)
+{
+    double *tmp = nullptr;
+    LSF_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)g->np));
+    convert_f2d(g->phi_f, tmp, g->np);
+    Grid view = *g;                       // same extents and slab geometry, phi -> the temporary
+    view.f32 = 0;
+    view.phi = tmp;
+    launch_sign_init(&view, xLo, dx, d_surfX, nNode, d_surfElem, nElem, d_cen, im, ip, jm, jp, km, kp);
+    G.n_launch += 0;
+    convert_d2f(tmp, g->phi_f, g->np);
+    cudaError_t e = cudaStreamSynchronize(G.stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "sign_init (fp32 grid): %s", cudaGetErrorString(e));
+    return LSF_OK;
 }
 
 // transient fp64 shadow of an fp32 grid: phi widened on creation, rounded back by f32_shadow_close

@@ -109,7 +109,8 @@ inline bool sharded(const Grid *g) { return g->sg.nranks > 1; }
 int slab_check_attached(Grid *g);
 // ghost-plane refresh of buf (default phi); no-op on one GPU.  handshake = false: the caller guarantees that
 // the neighbours no longer read the ghost planes being overwritten (lsf_api.cu, active-list min/max)
-void slab_exchange(Grid *g, bool in_loop, double *buf = nullptr, bool handshake = true);
+void slab_exchange(Grid *g, bool in_loop, double *buf = nullptr, bool handshake = true);   // fp32 grid: exchanges phi_f
+void slab_exchange_raw(Grid *g, bool in_loop, char *buf, size_t esize, bool handshake);
 void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol, int n);
 long long slab_publish_sum(Grid *g, int npart);  // this rank's sum of partials -> every rank (fire and forget); returns its sequence number
 void slab_decide(Grid *g, long long seq_first, int count, int n_first, int hist_off, double tol);   // EXIT / NaN tests of `count` iterations
@@ -126,8 +127,11 @@ void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc);
 const int *march_order();
 
 // lsf_f32.cu -- fp32 grids (g->f32)
-int f32_upload(Grid *g, const double *host, float *dev);
-int f32_download(Grid *g, const float *dev, double *host);
+int f32_upload(Grid *g, const double *host, float *dev, long long n);      // n elements, host -> dev
+int f32_download(Grid *g, const float *dev, double *host, long long n);
+void launch_reinit_bc_rms_f32(Grid *g, double dx, int partial_off);
+int f32_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode, const int32_t *d_surfElem, int nElem,
+                  double *d_cen, int im, int ip, int jm, int jp, int km, int kp);
 int f32_fill(Grid *g, double value);
 int f32_narrowband(Grid *g, double dx, int32_t *d_nb, int32_t *d_sb);
 int f32_reinit(Grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist);

@@ -38,28 +38,33 @@ typedef void (*MarchKernel)(const MarchParams);
 typedef MarchCfg<LSF_TB, LSF_TC, LSF_ROWS, float> CFG32;
 typedef MarchParamsT<float> MarchParamsF;
 
-template <bool FA, bool FB, bool FC>
+template <bool FA, bool FB, bool FC, bool MG>
 __global__ void __launch_bounds__(CFG32::THREADS, LSF_OCC32)
 k_reinit_march_f32(const MarchParamsF p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MarchSmem<CFG32> &sm = *reinterpret_cast<MarchSmem<CFG32> *>(smem_raw);
-    march_cta<F32Arith, FA, FB, FC, CFG32, false>(p, sm, threadIdx.x);
+    march_cta<F32Arith, FA, FB, FC, CFG32, MG>(p, sm, threadIdx.x);
 }
 
 typedef void (*MarchKernelF)(const MarchParamsF);
-static MarchKernelF march_kernel_f32(int fa, int fb, int fc)
+template <bool MG>
+static MarchKernelF march_kernel_f32_mg(int fa, int fb, int fc)
 {
     switch ((fa ? 1 : 0) | (fb ? 2 : 0) | (fc ? 4 : 0)) {
-    case 0: return k_reinit_march_f32<false, false, false>;
-    case 1: return k_reinit_march_f32<true, false, false>;
-    case 2: return k_reinit_march_f32<false, true, false>;
-    case 3: return k_reinit_march_f32<true, true, false>;
-    case 4: return k_reinit_march_f32<false, false, true>;
-    case 5: return k_reinit_march_f32<true, false, true>;
-    case 6: return k_reinit_march_f32<false, true, true>;
-    default: return k_reinit_march_f32<true, true, true>;
+    case 0: return k_reinit_march_f32<false, false, false, MG>;
+    case 1: return k_reinit_march_f32<true, false, false, MG>;
+    case 2: return k_reinit_march_f32<false, true, false, MG>;
+    case 3: return k_reinit_march_f32<true, true, false, MG>;
+    case 4: return k_reinit_march_f32<false, false, true, MG>;
+    case 5: return k_reinit_march_f32<true, false, true, MG>;
+    case 6: return k_reinit_march_f32<false, true, true, MG>;
+    default: return k_reinit_march_f32<true, true, true, MG>;
     }
+}
+static MarchKernelF march_kernel_f32(int fa, int fb, int fc, bool mg = false)
+{
+    return mg ? march_kernel_f32_mg<true>(fa, fb, fc) : march_kernel_f32_mg<false>(fa, fb, fc);
 }
 
 template <class AR, bool MG>
@@ -143,11 +148,46 @@ int march_prepare(Grid *g)
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
         }
-        for (int o = 0; o < 8; ++o)
-            LSF_CUDA(cudaFuncSetAttribute(march_kernel_f32(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG32>)));
+        for (int o = 0; o < 16; ++o)
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel_f32(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG32>)));
         attr_done = true;
     }
     return LSF_OK;
+}
+
+// z-slabs: the streaming-halo / write-through / completion-flag fields of the sweep parameters (lsf_march.cuh).
+// phi: this rank's field inside its shared allocation (fp64 or fp32).
+template <class T>
+static void march_fill_slab(MarchParamsT<T> &p, Grid *g, T *phi)
+{
+    // the Gauss-Seidel pipeline along k (lsf_slab.cuh): upstream = the rank owning lower oriented c
+    const SlabGeom &sg = g->sg;
+    const int up = p.fc ? sg.rank + 1 : sg.rank - 1, down = p.fc ? sg.rank - 1 : sg.rank + 1;
+    const int side_up = p.fc ? 1 : 0, side_down = p.fc ? 0 : 1;     // which of THIS rank's sides that neighbour is on
+    if (up >= 0 && up < sg.nranks) {
+        SlabGeom ug;
+        slab_geom(sg.NZ, sg.nranks, up, ug);
+        p.in_progress = g->sync->in_progress;
+        p.push_up_delta = (peer_ptr(g, up, phi) + (long long)(sg.kbase - ug.kbase) * g->dm.sxy) - phi;
+        p.edge_pub[0] = peer_ptr(g, up, g->sync)->edge_done[1 - side_up];        // address computation only
+    }
+    if (down >= 0 && down < sg.nranks) {
+        SlabGeom dg;
+        slab_geom(sg.NZ, sg.nranks, down, dg);
+        p.push_delta = (peer_ptr(g, down, phi) + (long long)(sg.kbase - dg.kbase) * g->dm.sxy) - phi;
+        p.push_progress = peer_ptr(g, down, g->sync)->in_progress;
+        p.edge_pub[1] = peer_ptr(g, down, g->sync)->edge_done[1 - side_down];
+        if (g->prev_sweep_valid) {
+            p.edge_wait = g->sync->edge_done[side_down];
+            p.edge_need = g->prev_sweep_epoch;
+            p.edge_prev_fb = g->prev_sweep_fb;
+        }
+    }
+    // the first sweep after a bulk exchange: both neighbours' planes must have landed in the ghost planes
+    p.halo_seq = g->sync->halo_seq;
+    if (sg.rank > 0) p.halo_need[0] = g->phase;
+    if (sg.rank < sg.nranks - 1) p.halo_need[1] = g->phase;
+    g->prev_sweep_valid = true; g->prev_sweep_epoch = p.epoch; g->prev_sweep_fb = p.fb;
 }
 
 // fp32 grid (lsf_f32.cu): same schedule, float phi / phiS and a float slot ring
@@ -160,10 +200,11 @@ void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc)
     p.cc.dx = (float)cc.dx; p.cc.inv_dx = (float)cc.inv_dx; p.cc.k12 = (float)cc.k12; p.cc.dx2 = (float)cc.dx2; p.cc.h = (float)cc.h;
     p.partial = g->partial; p.ticket = g->march_ticket; p.order = MH.d_order;
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
+    if (sharded(g)) march_fill_slab(p, g, g->phi_f);
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     static const int occ = getenv("LSF_OCC32_RUN") ? atoi(getenv("LSF_OCC32_RUN")) : LSF_OCC32;   // experiments: fewer resident CTAs
     const int ncta = p.ntiles < occ * G.num_sms ? p.ntiles : occ * G.num_sms;
-    march_kernel_f32(p.fa, p.fb, p.fc)<<<ncta, CFG32::THREADS, sizeof(MarchSmem<CFG32>), G.stream>>>(p);
+    march_kernel_f32(p.fa, p.fb, p.fc, sharded(g))<<<ncta, CFG32::THREADS, sizeof(MarchSmem<CFG32>), G.stream>>>(p);
     G.n_launch++;
 }
 
@@ -178,36 +219,7 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
     p.in_progress = nullptr; p.push_delta = 0; p.push_progress = nullptr; p.halo_seq = nullptr;
     p.halo_need[0] = p.halo_need[1] = 0;
     p.push_up_delta = 0; p.edge_pub[0] = p.edge_pub[1] = nullptr; p.edge_wait = nullptr; p.edge_need = 0; p.edge_prev_fb = 0;
-    if (sharded(g)) {
-        // the Gauss-Seidel pipeline along k (lsf_slab.cuh): upstream = the rank owning lower oriented c
-        const SlabGeom &sg = g->sg;
-        const int up = p.fc ? sg.rank + 1 : sg.rank - 1, down = p.fc ? sg.rank - 1 : sg.rank + 1;
-        const int side_up = p.fc ? 1 : 0, side_down = p.fc ? 0 : 1;     // which of THIS rank's sides that neighbour is on
-        if (up >= 0 && up < sg.nranks) {
-            SlabGeom ug;
-            slab_geom(sg.NZ, sg.nranks, up, ug);
-            p.in_progress = g->sync->in_progress;
-            p.push_up_delta = (peer_ptr(g, up, g->phi) + (long long)(sg.kbase - ug.kbase) * g->dm.sxy) - g->phi;
-            p.edge_pub[0] = peer_ptr(g, up, g->sync)->edge_done[1 - side_up];        // address computation only
-        }
-        if (down >= 0 && down < sg.nranks) {
-            SlabGeom dg;
-            slab_geom(sg.NZ, sg.nranks, down, dg);
-            p.push_delta = (peer_ptr(g, down, g->phi) + (long long)(sg.kbase - dg.kbase) * g->dm.sxy) - g->phi;
-            p.push_progress = peer_ptr(g, down, g->sync)->in_progress;
-            p.edge_pub[1] = peer_ptr(g, down, g->sync)->edge_done[1 - side_down];
-            if (g->prev_sweep_valid) {
-                p.edge_wait = g->sync->edge_done[side_down];
-                p.edge_need = g->prev_sweep_epoch;
-                p.edge_prev_fb = g->prev_sweep_fb;
-            }
-        }
-        // the first sweep after a bulk exchange: both neighbours' planes must have landed in the ghost planes
-        p.halo_seq = g->sync->halo_seq;
-        if (sg.rank > 0) p.halo_need[0] = g->phase;
-        if (sg.rank < sg.nranks - 1) p.halo_need[1] = g->phase;
-        g->prev_sweep_valid = true; g->prev_sweep_epoch = p.epoch; g->prev_sweep_fb = p.fb;
-    }
+    if (sharded(g)) march_fill_slab(p, g, g->phi);
 #if defined(LSF_EXP_TIMING)
     {   // experiment: dump per-tile timing of this sweep to $LSF_TIMING_DUMP after the launch (synchronous)
         static long long *d_dbg = nullptr; static int cap = 0;

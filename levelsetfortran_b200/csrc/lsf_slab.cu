@@ -32,9 +32,9 @@ int slab_check_attached(Grid *g)
 struct ExchArgs {
     SlabSync *self;
     SlabSync *nbr[2];
-    const double *src[2];
-    double *dst[2];
-    long long n;               // doubles per side (3 planes)
+    const uint32_t *src[2];    // the planes are moved as 32-bit words (fp64 and fp32 fields alike)
+    uint32_t *dst[2];
+    long long n;               // words per side (3 planes)
     long long phase;
     unsigned *counter;
     Ctrl *ctrl;
@@ -54,16 +54,16 @@ k_slab_exchange(const ExchArgs a)
         if (threadIdx.x < 2 && a.nbr[threadIdx.x]) wait_ge<true>(&a.self->phase_done[threadIdx.x], a.phase, a.ctrl);
         __syncthreads();
     }
-    const long long n2 = a.n / 2;     // planes are even-sized or not: handle the tail below
+    const long long n4 = a.n / 4;     // 16-byte chunks; the tail (< 4 words) is handled below
     for (int s = 0; s < 2; ++s) {
         if (!a.nbr[s]) continue;
-        const double2 *src = reinterpret_cast<const double2 *>(a.src[s]);
-        double2 *dst = reinterpret_cast<double2 *>(a.dst[s]);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.src[s]);
+        uint4 *dst = reinterpret_cast<uint4 *>(a.dst[s]);
         const bool vec = ((((uintptr_t)a.src[s]) | ((uintptr_t)a.dst[s])) & 15) == 0;
         if (vec) {
-            for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += (long long)gridDim.x * blockDim.x)
+            for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x)
                 __stcg(dst + q, __ldcg(src + q));
-            if (blockIdx.x == 0 && threadIdx.x == 0 && (a.n & 1)) __stcg(a.dst[s] + a.n - 1, __ldcg(a.src[s] + a.n - 1));
+            if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) __stcg(a.dst[s] + 4 * n4 + threadIdx.x, __ldcg(a.src[s] + 4 * n4 + threadIdx.x));
         } else {
             for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < a.n; q += (long long)gridDim.x * blockDim.x)
                 __stcg(a.dst[s] + q, __ldcg(a.src[s] + q));
@@ -85,12 +85,21 @@ k_slab_exchange(const ExchArgs a)
 void slab_exchange(Grid *g, bool in_loop, double *buf, bool handshake)
 {
     if (!sharded(g)) return;
+    if (g->f32) { slab_exchange_raw(g, in_loop, (char *)g->phi_f, sizeof(float), handshake); return; }
     if (!buf) buf = g->phi;
+    slab_exchange_raw(g, in_loop, (char *)buf, sizeof(double), handshake);
+}
+
+// buf: a field inside the rank's shared allocation (phi / phiN, fp64 or fp32), esize: bytes per element
+void slab_exchange_raw(Grid *g, bool in_loop, char *buf, size_t esize, bool handshake)
+{
+    if (!sharded(g)) return;
     const SlabGeom &sg = g->sg;
+    const long long pb = (long long)g->dm.sxy * (long long)esize;       // bytes per plane
     ExchArgs a;
     memset(&a, 0, sizeof(a));
     a.self = g->sync;
-    a.n = (long long)SLAB_GHOST * g->dm.sxy;
+    a.n = (long long)SLAB_GHOST * pb / 4;
     a.phase = ++g->phase;
     a.counter = g->exch_counter;
     a.ctrl = g->ctrl;
@@ -100,15 +109,15 @@ void slab_exchange(Grid *g, bool in_loop, double *buf, bool handshake)
         SlabGeom ng;
         slab_geom(sg.NZ, sg.nranks, sg.rank - 1, ng);
         a.nbr[0] = peer_ptr(g, sg.rank - 1, g->sync);
-        a.src[0] = buf + (long long)sg.own_lo * g->dm.sxy;                                      // my global planes k0..k0+2
-        a.dst[0] = peer_ptr(g, sg.rank - 1, buf) + (long long)(sg.k0 - ng.kbase) * g->dm.sxy;      // = its upper ghost planes
+        a.src[0] = (const uint32_t *)(buf + (long long)sg.own_lo * pb);                                   // my global planes k0..k0+2
+        a.dst[0] = (uint32_t *)(peer_ptr(g, sg.rank - 1, buf) + (long long)(sg.k0 - ng.kbase) * pb);      // = its upper ghost planes
     }
     if (sg.rank < sg.nranks - 1) {
         SlabGeom ng;
         slab_geom(sg.NZ, sg.nranks, sg.rank + 1, ng);
         a.nbr[1] = peer_ptr(g, sg.rank + 1, g->sync);
-        a.src[1] = buf + (long long)(sg.own_hi - SLAB_GHOST + 1) * g->dm.sxy;                   // my global planes k1-3..k1-1
-        a.dst[1] = peer_ptr(g, sg.rank + 1, buf) + (long long)(sg.k1 - SLAB_GHOST - ng.kbase) * g->dm.sxy;      // = its lower ghost planes
+        a.src[1] = (const uint32_t *)(buf + (long long)(sg.own_hi - SLAB_GHOST + 1) * pb);                // my global planes k1-3..k1-1
+        a.dst[1] = (uint32_t *)(peer_ptr(g, sg.rank + 1, buf) + (long long)(sg.k1 - SLAB_GHOST - ng.kbase) * pb);      // = its lower ghost planes
     }
     k_slab_exchange<<<2 * G.num_sms, 256, 0, G.stream>>>(a);
     G.n_launch++;
@@ -237,11 +246,23 @@ int lsf_slab_range(int nz, int nranks, int rank, int *k0, int *k1)
     return LSF_OK;
 }
 
+static int sgrid_create(lsf_grid **out, int nx, int ny, int nz, int rank, int nranks, bool f32);
+
 int lsf_sgrid_create(lsf_grid **out, int nx, int ny, int nz, int rank, int nranks)
+{
+    return sgrid_create(out, nx, ny, nz, rank, nranks, false);
+}
+
+int lsf_sgrid_create_f32(lsf_grid **out, int nx, int ny, int nz, int rank, int nranks)
+{
+    return sgrid_create(out, nx, ny, nz, rank, nranks, true);
+}
+
+static int sgrid_create(lsf_grid **out, int nx, int ny, int nz, int rank, int nranks, bool f32)
 {
     if (!out) return set_error(LSF_ERR_ARG, "null handle");
     *out = nullptr;
-    if (nranks == 1) return lsf_grid_create(out, nx, ny, nz);
+    if (nranks == 1) return f32 ? lsf_grid_create_f32(out, nx, ny, nz) : lsf_grid_create(out, nx, ny, nz);
     if (!G.inited) { int rc = lsf_init(-1); if (rc) return rc; }
     if (nx < 2 || ny < 2) return set_error(LSF_ERR_ARG, "grid extents must be >= 2");
     SlabGeom sg;
@@ -259,13 +280,15 @@ int lsf_sgrid_create(lsf_grid **out, int nx, int ny, int nz, int rank, int nrank
     // to a peer's by its offset): size the two fields for the thickest slab
     int nzl_max = sg.nzl;
     for (int r = 0; r < nranks; ++r) { SlabGeom o; slab_geom(nz, nranks, r, o); if (o.nzl > nzl_max) nzl_max = o.nzl; }
-    const size_t fbytes = align_up(sizeof(double) * (size_t)g->dm.sxy * ((size_t)nzl_max + 1), 256);
+    const size_t esize = f32 ? sizeof(float) : sizeof(double);
+    g->f32 = f32 ? 1 : 0;
+    const size_t fbytes = align_up(esize * (size_t)g->dm.sxy * ((size_t)nzl_max + 1) + 64, 256);
     const size_t sbytes = align_up(sizeof(SlabSync), 256);
     g->shared_bytes = sbytes + 2 * fbytes;
     cudaError_t e;
     if ((e = cudaMalloc(&g->shared_base, g->shared_bytes)) != cudaSuccess ||
         (e = cudaMemset(g->shared_base, 0, sbytes)) != cudaSuccess ||
-        (e = cudaMalloc(&g->phiS, sizeof(double) * (size_t)g->np)) != cudaSuccess ||
+        (e = cudaMalloc(f32 ? (void **)&g->phiS_f : (void **)&g->phiS, esize * (size_t)g->np + 64)) != cudaSuccess ||
         (e = cudaMalloc(&g->partial, sizeof(double) * PARTIAL_CAP)) != cudaSuccess ||
         (e = cudaMalloc(&g->ctrl, sizeof(Ctrl))) != cudaSuccess ||
         (e = cudaMalloc(&g->exch_counter, sizeof(unsigned))) != cudaSuccess ||
@@ -275,8 +298,13 @@ int lsf_sgrid_create(lsf_grid **out, int nx, int ny, int nz, int rank, int nrank
         return set_error(LSF_ERR_CUDA, "sgrid_create: %s", cudaGetErrorString(e));
     }
     g->sync = (SlabSync *)g->shared_base;
-    g->phi = (double *)((char *)g->shared_base + sbytes);
-    g->phiN = (double *)((char *)g->shared_base + sbytes + fbytes);
+    if (f32) {
+        g->phi_f = (float *)((char *)g->shared_base + sbytes);
+        g->phiN_f = (float *)((char *)g->shared_base + sbytes + fbytes);
+    } else {
+        g->phi = (double *)((char *)g->shared_base + sbytes);
+        g->phiN = (double *)((char *)g->shared_base + sbytes + fbytes);
+    }
     g->peer_base[rank] = g->shared_base;
     *out = g;
     return LSF_OK;

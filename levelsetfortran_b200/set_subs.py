@@ -247,15 +247,17 @@ class ShardedGrid(DeviceGrid):
     on all ranks.  `torch.distributed` must be initialised: it is used once, to all-gather the CUDA-IPC
     handles; the data path itself is peer stores over NVLink from inside the kernels."""
 
-    def __init__(self, nx, ny, nz, rank=None, nranks=None):
+    def __init__(self, nx, ny, nz, rank=None, nranks=None, f32=False):
         import torch
         import torch.distributed as dist
         self.rank = dist.get_rank() if rank is None else int(rank)
         self.nranks = dist.get_world_size() if nranks is None else int(nranks)
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.f32 = bool(f32)          # optional fp32 mode: fill / upload / download / signSearch / reinit / narrowBand
         self.k0, self.k1 = slab_range(self.nz, self.nranks, self.rank)
         self._h = C.c_void_p()
-        check(lib().lsf_sgrid_create(C.byref(self._h), self.nx, self.ny, self.nz, self.rank, self.nranks))
+        create = lib().lsf_sgrid_create_f32 if self.f32 else lib().lsf_sgrid_create
+        check(create(C.byref(self._h), self.nx, self.ny, self.nz, self.rank, self.nranks))
         if self.nranks > 1:
             buf = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
             check(lib().lsf_sgrid_ipc_handle(self._h, buf))

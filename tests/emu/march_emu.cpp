@@ -435,24 +435,29 @@ extern "C" double emu_mm_list_iteration(const double *A, double *B, const unsign
 // the schedule must be an exact re-ordering in fp32 too (bitwise equal on the CPU).
 typedef MarchCfg<16, 16, LSF_ROWS, float> CFGF;
 typedef MarchSmem<CFGF> SmemF;
-struct ThreadArgF { const MarchParamsT<float> *p; SmemF *sm; EmuCta *cta; int tid; };
+struct ThreadArgF { const MarchParamsT<float> *p; SmemF *sm; EmuCta *cta; int tid; int mg; };
+
+template <bool MG>
+static void run_cta_f32(const MarchParamsT<float> &p, SmemF &sm, int tid)
+{
+    const int o = (p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0);
+    switch (o) {
+    case 0: march_cta<F32Arith, false, false, false, CFGF, MG>(p, sm, tid); break;
+    case 1: march_cta<F32Arith, true, false, false, CFGF, MG>(p, sm, tid); break;
+    case 2: march_cta<F32Arith, false, true, false, CFGF, MG>(p, sm, tid); break;
+    case 3: march_cta<F32Arith, true, true, false, CFGF, MG>(p, sm, tid); break;
+    case 4: march_cta<F32Arith, false, false, true, CFGF, MG>(p, sm, tid); break;
+    case 5: march_cta<F32Arith, true, false, true, CFGF, MG>(p, sm, tid); break;
+    case 6: march_cta<F32Arith, false, true, true, CFGF, MG>(p, sm, tid); break;
+    default: march_cta<F32Arith, true, true, true, CFGF, MG>(p, sm, tid); break;
+    }
+}
 
 static void *thread_main_f32(void *v)
 {
     ThreadArgF *a = (ThreadArgF *)v;
     emu_cta = a->cta;
-    const MarchParamsT<float> &p = *a->p;
-    const int o = (p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0);
-    switch (o) {
-    case 0: march_cta<F32Arith, false, false, false, CFGF, false>(p, *a->sm, a->tid); break;
-    case 1: march_cta<F32Arith, true, false, false, CFGF, false>(p, *a->sm, a->tid); break;
-    case 2: march_cta<F32Arith, false, true, false, CFGF, false>(p, *a->sm, a->tid); break;
-    case 3: march_cta<F32Arith, true, true, false, CFGF, false>(p, *a->sm, a->tid); break;
-    case 4: march_cta<F32Arith, false, false, true, CFGF, false>(p, *a->sm, a->tid); break;
-    case 5: march_cta<F32Arith, true, false, true, CFGF, false>(p, *a->sm, a->tid); break;
-    case 6: march_cta<F32Arith, false, true, true, CFGF, false>(p, *a->sm, a->tid); break;
-    default: march_cta<F32Arith, true, true, true, CFGF, false>(p, *a->sm, a->tid); break;
-    }
+    if (a->mg) run_cta_f32<true>(*a->p, *a->sm, a->tid); else run_cta_f32<false>(*a->p, *a->sm, a->tid);
     return nullptr;
 }
 
@@ -497,7 +502,7 @@ extern "C" double emu_march_sweep_f32(float *phi, const float *phiS, int nx, int
     for (int c = 0; c < ncta; ++c)
         for (int t = 0; t < NT; ++t) {
             ThreadArgF &a = args[(size_t)c * NT + t];
-            a.p = &p; a.sm = &sm[c]; a.cta = &ctas[c]; a.tid = t;
+            a.p = &p; a.sm = &sm[c]; a.cta = &ctas[c]; a.tid = t; a.mg = 0;
             if (pthread_create(&th[(size_t)c * NT + t], &attr, thread_main_f32, &a) != 0) return -1.;
         }
     for (size_t q = 0; q < th.size(); ++q) pthread_join(th[q], nullptr);
@@ -575,4 +580,83 @@ extern "C" int emu_advect_nodes(const double *phi, const double *sbsrc, int nx, 
     }
     if (moves) *moves = nm;
     return worst;
+}
+
+
+// fp32 twin of emu_march_sweep_slabs: one sweep on `nranks` z-slabs running concurrently, coupled only through the
+// streaming-halo protocol (peer stores of float values + in_progress flags).
+extern "C" double emu_march_sweep_slabs_f32(float *phi, const float *phiS, int nx, int ny, int NZ, int nranks, int raster,
+                                            double dx, double h, int ncta, int order_m)
+{
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    std::vector<SlabGeom> geo(nranks);
+    for (int r = 0; r < nranks; ++r) if (!slab_geom(NZ, nranks, r, geo[r])) return -2.;
+    std::vector<std::vector<float>> lphi(nranks), lphiS(nranks);
+    std::vector<std::vector<double>> partial(nranks);
+    std::vector<std::vector<int>> order(nranks);
+    std::vector<std::vector<long long>> progress(nranks);
+    std::vector<SlabSync> sync(nranks);
+    std::vector<MarchParamsT<float>> P(nranks);
+    std::vector<unsigned> ticket(nranks, 0u);
+    std::vector<Ctrl> ctrl(nranks, Ctrl{0, 0, 0, 0, 0});
+    memset(sync.data(), 0, sizeof(SlabSync) * nranks);
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        const size_t n = (size_t)sxy * (g.nzl + 1);
+        lphi[r].assign(phi + (size_t)g.kbase * sxy, phi + (size_t)g.kbase * sxy + n);
+        lphiS[r].assign(phiS + (size_t)g.kbase * sxy, phiS + (size_t)g.kbase * sxy + n);
+        lphi[r].resize(n + 16, 1.e30f); lphiS[r].resize(n + 16, 1.e30f);
+    }
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        MarchParamsT<float> &p = P[r];
+        memset(&p, 0, sizeof(p));
+        march_orient<CFGF>(p, nx, ny, g.nzl, sx, sxy, raster, g.kupd_lo, g.kupd_hi, g.kbase, NZ);
+        p.phi = lphi[r].data(); p.phiS = lphiS[r].data();
+        cc_f32(p.cc, dx, h);
+        partial[r].assign(p.ntiles, 0.); order[r].resize(p.ntiles); progress[r].assign(p.ntiles, 0);
+        march_fill_order(p.ntb, p.ntc, order[r].data(), order_m);
+        p.partial = partial[r].data(); p.order = order[r].data(); p.progress = progress[r].data();
+        p.ticket = &ticket[r]; p.ctrl = &ctrl[r]; p.epoch = 1;
+        const int up = p.fc ? r + 1 : r - 1, down = p.fc ? r - 1 : r + 1;
+        if (up >= 0 && up < nranks) p.in_progress = sync[r].in_progress;
+        if (down >= 0 && down < nranks) {
+            p.push_delta = (lphi[down].data() + (long long)(g.kbase - geo[down].kbase) * sxy) - lphi[r].data();
+            p.push_progress = sync[down].in_progress;
+        }
+    }
+    constexpr int NT = CFGF::THREADS;
+    std::vector<int> nc(nranks);
+    size_t nthreads = 0;
+    for (int r = 0; r < nranks; ++r) { nc[r] = ncta < P[r].ntiles ? ncta : P[r].ntiles; nthreads += (size_t)nc[r] * NT; }
+    std::vector<std::vector<SmemF>> sm(nranks);
+    std::vector<std::vector<EmuCta>> ctas(nranks);
+    std::vector<ThreadArgF> args(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    for (int r = 0; r < nranks; ++r) {
+        sm[r] = std::vector<SmemF>(nc[r]);
+        ctas[r] = std::vector<EmuCta>(nc[r]);
+        for (int c = 0; c < nc[r]; ++c) pthread_barrier_init(&ctas[r][c].bar, nullptr, NT);
+    }
+    size_t q = 0;
+    for (int r = 0; r < nranks; ++r)
+        for (int c = 0; c < nc[r]; ++c)
+            for (int t = 0; t < NT; ++t, ++q) {
+                ThreadArgF &a = args[q];
+                a.p = &P[r]; a.sm = &sm[r][c]; a.cta = &ctas[r][c]; a.tid = t; a.mg = 1;
+                if (pthread_create(&th[q], &attr, thread_main_f32, &a) != 0) return -1.;
+            }
+    for (size_t i = 0; i < th.size(); ++i) pthread_join(th[i], nullptr);
+    double s = 0.;
+    for (int r = 0; r < nranks; ++r) {
+        const SlabGeom &g = geo[r];
+        for (int c = 0; c < nc[r]; ++c) pthread_barrier_destroy(&ctas[r][c].bar);
+        if (ctrl[r].status != 0) return -3.;
+        memcpy(phi + (size_t)g.k0 * sxy, lphi[r].data() + (size_t)g.own_lo * sxy, sizeof(float) * (size_t)sxy * (g.k1 - g.k0));
+        for (int i = 0; i < P[r].ntiles; ++i) s += partial[r][i];
+    }
+    return s;
 }

@@ -237,3 +237,23 @@ def test_f32_march_schedule_is_an_exact_reordering(emu, oracle, shape, ncta):
         assert abs(s - ref) <= 1e-4 * max(ref, 1e-300)
         oracle.reinit_sweep(d, pSd, 0.05, 0.0014, r)
         assert np.abs(a - d).max() <= 1e-4 * np.abs(d).max()
+
+
+@pytest.mark.parametrize("shape,nranks,ncta,m", [((22, 21, 40), 2, 2, 1), ((20, 36, 51), 3, 3, 2)])
+def test_f32_slab_pipeline_is_an_exact_reordering(emu, shape, nranks, ncta, m):
+    """z-slab sharding of the fp32 mode: the slabs' concurrent sweeps (float peer stores + in_progress flags) gathered
+    back must be bit-identical to the fp32 lexicographic sweep of the whole grid, all 8 rasters."""
+    fp = C.POINTER(C.c_float)
+    emu.emu_lex_sweep_f32.restype = None
+    emu.emu_lex_sweep_f32.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    emu.emu_march_sweep_slabs_f32.restype = C.c_double
+    emu.emu_march_sweep_slabs_f32.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    p0 = synth_field(shape, seed=2).astype(np.float32, order="F")
+    pS = p0.copy(order="F")
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    nx, ny, nz = (s - 1 for s in shape)
+    for r in range(1, 9):
+        emu.emu_lex_sweep_f32(a.ctypes.data_as(fp), pS.ctypes.data_as(fp), nx, ny, nz, r, 0.05, 0.0014, 0)
+        s = emu.emu_march_sweep_slabs_f32(b.ctypes.data_as(fp), pS.ctypes.data_as(fp), nx, ny, nz, nranks, r, 0.05, 0.0014, ncta, m)
+        assert s >= 0, s
+        assert np.array_equal(a, b), f"raster {r}: fp32 slab pipeline differs from the fp32 lexicographic sweep"
