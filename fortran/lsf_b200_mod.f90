@@ -30,7 +30,7 @@ IMPLICIT NONE
 PRIVATE
 
 PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched, lsf_set_minmax_algo, lsf_set_precision
-PUBLIC :: lsf_slab_range, lsf_sgrid_create, lsf_sgrid_ipc_handle, lsf_sgrid_attach, lsf_grid_destroy
+PUBLIC :: lsf_slab_range, lsf_sgrid_create, lsf_sgrid_create_f32, lsf_sgrid_ipc_handle, lsf_sgrid_attach, lsf_grid_destroy
 PUBLIC :: signSearch_b200, reinit_b200, narrowBand_b200, minMaxFlow_b200, advectNodes_b200
 PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT, LSF_ARITH_AUTO, LSF_PREC_F64, LSF_PREC_F32
 
@@ -91,6 +91,13 @@ INTERFACE
       INTEGER(c_int), VALUE :: nx,ny,nz,rank,nranks
       INTEGER(c_int) :: rc
    END FUNCTION lsf_sgrid_create
+
+   FUNCTION lsf_sgrid_create_f32(g,nx,ny,nz,rank,nranks) BIND(C, NAME='lsf_sgrid_create_f32') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr) :: g                        ! lsf_grid**, the slab in the optional fp32 mode
+      INTEGER(c_int), VALUE :: nx,ny,nz,rank,nranks
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_sgrid_create_f32
 
    FUNCTION lsf_sgrid_ipc_handle(g,handle) BIND(C, NAME='lsf_sgrid_ipc_handle') RESULT(rc)
       IMPORT :: c_int, c_ptr, c_char

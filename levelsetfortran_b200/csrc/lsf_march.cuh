@@ -103,12 +103,35 @@ LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 }  // namespace lsf
 #endif
 
+// ---- build-time switches (defaults = the production kernel; the others are the measured alternatives and the
+// ---- switch-off experiments of DESIGN.md section 9, built with tools/build_variant.sh) ---------------------------
+#ifndef LSF_W32
+#define LSF_W32 17              // fp32 ring: floats per position (16 slots + pad); 18 makes the column-halo deposits conflict-free (-0.7 %)
+#endif
+#ifndef LSF_VEC32
+#define LSF_VEC32 1             // cells per global vector load of a row walk in fp32; 4 (LDG.128) measured 5-18 % SLOWER
+#endif
+#ifndef LSF_VEC64
+#define LSF_VEC64 1             // same in fp64; 2 (LDG.64) measured 40 % slower
+#endif
+#ifndef LSF_LD_CACHED
+#define LSF_LD_CACHED 0         // bit 0: look-ahead loads through L1, bit 1: phiS loads, bit 2: +b/+c halo rows (OLD values); measured 1-6 % slower
+#endif
+#if defined(LSF_EXP_NOLDG) && !defined(LSF_EXP_NOLDG_MASK)
+#define LSF_EXP_NOLDG_MASK 7
+#endif
+#ifndef LSF_EXP_NOLDG_MASK
+#define LSF_EXP_NOLDG_MASK 0    // timing experiments only (results wrong): 1 = no look-ahead load, 2 = no phiS load, 4 = no halo loads
+#endif
+// LSF_EXP_NOSTG / LSF_EXP_NOSYNC: no global stores / no CTA barrier per step (timing experiments, results wrong)
+
 namespace lsf {
 
 // Per-thread reader of one grid row that is walked one cell per step: fetches the aligned VEC-element chunk when the
-// walk enters it (one vector load per VEC cells instead of one scalar load per cell -- a warp's 32 lanes read 32
-// different rows, so every load instruction costs 32 L1TEX tag cycles whatever its width).  FA: the row is walked
-// towards lower addresses.  Elements of the chunk outside the row are fetched but never used (the arrays are padded).
+// walk enters it (one vector load per VEC cells instead of one scalar load per cell).  Measured slower than scalar
+// loads (the skew puts the lanes of a warp in different alignment phases, so the load is still issued every step, for
+// a fraction of the lanes, under a divergent branch): kept behind LSF_VEC32 / LSF_VEC64, off by default.  FA: the row
+// is walked towards lower addresses.  Elements of the chunk outside the row are fetched but never used (arrays padded).
 template <class real, int VEC, bool FA>
 struct RowReader {
     real buf[VEC];
@@ -145,18 +168,9 @@ struct MarchCfg {
     static constexpr int TB = TB_, TC = TC_, R = R_;          // R rows (cells per step) per thread
     static constexpr int THREADS = TB * TC / R;
     static constexpr int SW = TB + 2 * M_H, SH = TC + 2 * M_H;
-#ifndef LSF_W32
-#define LSF_W32 M_SLOTW
-#endif
     // elements per position: 16 slots + pad.  fp32 may use a different pad (LSF_W32) so that the column-halo
     // deposits (stride = row pitch) do not all fall on two banks
     static constexpr int W = sizeof(T_) == 4 ? LSF_W32 : M_SLOTW;
-#ifndef LSF_VEC32
-#define LSF_VEC32 1    // measured: 4 (LDG.128) is 5-18 % SLOWER than scalar loads -- the skew puts the lanes of a warp in
-#endif                 // different alignment phases, so the vector load is still issued every step, for a quarter of the lanes
-#ifndef LSF_VEC64
-#define LSF_VEC64 1
-#endif
     // cells per global vector load of a row walk (RowReader); 1 = scalar loads
     static constexpr int VEC = (R_ > 1) ? 1 : (sizeof(T_) == 4 ? LSF_VEC32 : LSF_VEC64);
     // pitch of one c-row of positions, in doubles; for TB = 8 a warp spans 4 c-rows and the pitch
@@ -445,15 +459,6 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             const int a4 = a + M_LOOK;
             ldLook[r] = rowValid[r] && (a4 >= 0) && (a4 <= p.nx);
             la[r] = 0;
-#ifndef LSF_LD_CACHED
-#define LSF_LD_CACHED 0                // bit 0: look-ahead loads through L1, bit 1: phiS loads, bit 2: +b/+c halo rows (OLD values)
-#endif
-#if defined(LSF_EXP_NOLDG) && !defined(LSF_EXP_NOLDG_MASK)
-#define LSF_EXP_NOLDG_MASK 7
-#endif
-#if !defined(LSF_EXP_NOLDG_MASK)
-#define LSF_EXP_NOLDG_MASK 0           // timing experiments only (results wrong): 1 = no look-ahead load, 2 = no phiS load, 4 = no halo loads
-#endif
 #if !(LSF_EXP_NOLDG_MASK & 1)
             if (ldLook[r]) {
                 if constexpr (VEC > 1) la[r] = rdLook.get(pOut[r] + M_LOOK * SA);
