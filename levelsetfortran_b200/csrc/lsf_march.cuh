@@ -123,6 +123,12 @@ LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 #ifndef LSF_EXP_NOLDG_MASK
 #define LSF_EXP_NOLDG_MASK 0    // timing experiments only (results wrong): 1 = no look-ahead load, 2 = no phiS load, 4 = no halo loads
 #endif
+#ifndef LSF_CHUNK
+#define LSF_CHUNK 8             // steps between two progress publications / predecessor waits of a tile
+#endif
+#ifndef LSF_ASYNC_POLL
+#define LSF_ASYNC_POLL 0        // 1: the predecessor flags are read one step before the chunk start that tests them
+#endif
 // LSF_EXP_NOSTG / LSF_EXP_NOSYNC: no global stores / no CTA barrier per step (timing experiments, results wrong)
 
 namespace lsf {
@@ -151,7 +157,7 @@ struct RowReader {
 constexpr int M_H = 3;                       // stencil half-width
 constexpr int M_NSLOT = 8;                   // hyperplane slots in the ring (each stored twice)
 constexpr int M_SLOTW = 2 * M_NSLOT + 1;     // doubles per position: 16 + 1 pad (bank spread)
-constexpr int M_CHUNK = 8;                   // publish / wait granularity in steps
+constexpr int M_CHUNK = LSF_CHUNK;           // publish / wait granularity in steps
 constexpr int M_LOOK = 4;                    // old values are deposited this many steps ahead
 constexpr long long M_FIN = 1LL << 30;       // "tile finished" progress value
 constexpr long long M_BIAS = 1000;
@@ -430,6 +436,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     for (int r = 0; r < CFG::HR; ++r)
         hp[r] = hrow[r] + (long long)(1 - M_LOOK + (hlow[r] ? 0 : M_LOOK) - hsig[r]) * SA;
 
+    long long preB = 0, preC = 0;           // LSF_ASYNC_POLL: flag values read ahead of the wait
     for (int t = -M_LOOK; t <= p.tend; ++t) {
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
         if (t >= 0 && (t % M_CHUNK) == 0) {
@@ -440,14 +447,21 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             long long tw0 = 0;
             if (tid == 0) tw0 = clock64();
 #endif
-            if (tid == 0 && predB) wait_ge<false>(predB, need_b, p.ctrl);
+            if (tid == 0 && predB) {
+                if (LSF_ASYNC_POLL && preB >= need_b) p_fence_acquire(); else wait_ge<false>(predB, need_b, p.ctrl);
+            }
             if (tid == 32 % THREADS && predC) {
-                if (predCpeer) wait_ge<true>(predC, need_c, p.ctrl); else wait_ge<false>(predC, need_c, p.ctrl);
+                if (LSF_ASYNC_POLL && preC >= need_c) { if (predCpeer) p_fence_sys(); else p_fence_acquire(); }
+                else if (predCpeer) wait_ge<true>(predC, need_c, p.ctrl); else wait_ge<false>(predC, need_c, p.ctrl);
             }
             p_sync();
 #if defined(LSF_EXP_TIMING)
             if (tid == 0) dbg_wait += clock64() - tw0;
 #endif
+        }
+        if (LSF_ASYNC_POLL && t + 1 >= 0 && ((t + 1) % M_CHUNK) == 0) {   // the flags the next chunk start will test: the
+            if (tid == 0 && predB) preB = p_ld_relaxed(predB);            // L2 round trip overlaps this step's arithmetic
+            if (tid == 32 % THREADS && predC) preC = predCpeer ? p_ld_relaxed_sys(predC) : p_ld_relaxed(predC);
         }
         p_emu_hook(tid == 0 && t == 6);
         // ---- (1) issue the global loads of this step --------------------------------------
