@@ -136,10 +136,11 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(grid):
+def ncu_traffic(grid, f32=False):
     """DRAM bytes (read + write) of ONE sweep-kernel launch from the committed `ncu --set full` capture of this
-    kernel at the same grid size (profiles/r1g_march_<grid>_full.txt), or None if there is no capture."""
-    path = os.path.join(ROOT, "profiles", f"r1g_march_{grid}_full.txt")
+    kernel at the same grid size (profiles/r1g_march_<grid>_full.txt; fp32 kernel: r1j_march_f32_<grid>_full.txt),
+    or None if there is no capture."""
+    path = os.path.join(ROOT, "profiles", f"r1j_march_f32_{grid}_full.txt" if f32 else f"r1g_march_{grid}_full.txt")
     if not os.path.exists(path):
         return None
     tot = 0.0
@@ -314,7 +315,8 @@ def run_gpu(args):
         fp32 = {"metric": METRIC + " (fp32 mode)", "value": cells_per_step * k32 / (ms32 * 1e-3) / 1e9, "unit": UNIT, "dtype": "f32",
                 "steps": k32, "ms_per_step": ms32 / k32,
                 "roofline": {"bound": "hbm", "bytes_per_update": 12.0, "achieved": a32, "peak": measured_peak()[0], "unit": "GB/s",
-                             "frac": a32 / measured_peak()[0] if a32 else None, "launch_ms": l32, "kernel": "k_reinit_march_f32"},
+                             "frac": a32 / measured_peak()[0] if a32 else None, "launch_ms": l32, "kernel": "k_reinit_march_f32",
+                             "traffic": ncu_traffic(n, True)},
                 "last_rms": float(hist32[-1]), "last_rms_fp64": float(hist[-1]) if hist is not None else None}
 
     # ---- e2e: the host-buffer drop-in call, pinned host memory, H2D + compute + D2H timed ------
@@ -388,9 +390,10 @@ def run_gpu(args):
                            "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
                            "last_rms": float(hist[-1]) if hist is not None else None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak if achieved else None, "traffic": None if f32 else ncu_traffic(n),
-                             "traffic_note": "DRAM read+write bytes of one launch, ncu --set full (profiles/r1g_march_%d_full.txt); "
-                                             "algorithmic bytes per launch: %.4g" % (n, bytes_per_update * cells_per_launch),
+                             "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(n, f32),
+                             "traffic_note": "DRAM read+write bytes of one launch of a whole %d^3 grid, ncu --set full (profiles/%s_%d_full.txt); "
+                                             "algorithmic bytes per launch: %.4g" % (n, "r1j_march_f32" if f32 else "r1g_march", n,
+                                                                                    bytes_per_update * cells_per_launch),
                              "kernel": ("k_reinit_march_f32" if f32 else "k_reinit_march") if args.sched == "march" else "k_reinit_plane",
                              "launch_ms": launch_ms, "peak_source": peak_src,
                              "fp64_pipe_frac": (FP64_PER_UPDATE * cells_per_launch / (launch_ms * 1e-3)) / FP64_PIPE_PEAK if launch_ms > 0 and not f32 else None,

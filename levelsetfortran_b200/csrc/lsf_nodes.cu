@@ -28,6 +28,13 @@ k_advect_nodes(NodeConst c, const double *__restrict__ phi, const double *__rest
     if (mv) atomicAdd(moves, (unsigned long long)mv);
 }
 
+// the caller's phiSB as a stand-in field: abs(.) < 8.1*dx exactly where phiSB == 1
+__global__ void k_sb_to_field(const int32_t *__restrict__ sb, double *__restrict__ out, long long n)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+        out[q] = sb[q] == 1 ? 0. : 1.0e300;
+}
+
 // d_phi: the level set; d_sbsrc: the field whose band abs(.) < 8.1*dx is phiSB (the last narrowBand call's input)
 int advect_nodes_core(Grid *g, const double *d_phi, const double *d_sbsrc, const double xLo[3], double dx, double *surfXX,
                       int nNode, double *phiSurf, double *gradPhiSurf, int iter, long long *n_moves)
@@ -109,13 +116,18 @@ int lsf_advect_nodes(const double *phi, const int32_t *phiSB, int nx, int ny, in
     lsf_grid *g = nullptr;
     int rc = lsf_grid_create(&g, nx, ny, nz);
     if (rc) return rc;
-    // the caller's phiSB decides band membership: phiS is used as a stand-in field with abs(.) < 8.1*dx exactly on the band
-    const size_t np = (size_t)g->np;
-    double *h = (double *)malloc(sizeof(double) * np);
-    if (!h) { lsf_grid_destroy(g); return set_error(LSF_ERR_ARG, "out of host memory"); }
-    for (size_t q = 0; q < np; ++q) h[q] = phiSB[q] == 1 ? 0. : 1.0e300;
-    cudaError_t e = cudaMemcpy(g->phiS, h, sizeof(double) * np, cudaMemcpyHostToDevice);
-    free(h);
+    // the caller's phiSB decides band membership: phiS becomes a stand-in field with abs(.) < 8.1*dx exactly on the band
+    // (masks go up in chunks through a small staging buffer)
+    const long long np = g->np, cap = np < (1LL << 25) ? np : (1LL << 25);
+    int32_t *stage = nullptr;
+    cudaError_t e = cudaMalloc(&stage, sizeof(int32_t) * (size_t)cap);
+    for (long long o = 0; o < np && e == cudaSuccess; o += cap) {
+        const long long n = np - o < cap ? np - o : cap;
+        e = cudaMemcpyAsync(stage, phiSB + o, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, G.stream);
+        k_sb_to_field<<<RMS_BLOCKS, 256, 0, G.stream>>>(stage, g->phiS + o, n);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
+    cudaFree(stage);
     if (e != cudaSuccess) rc = set_error(LSF_ERR_CUDA, "advect_nodes: %s", cudaGetErrorString(e));
     if (!rc) rc = lsf_grid_upload(g, phi);
     if (!rc) rc = advect_nodes_core(g, g->phi, g->phiS, xLo, dx, surfXX, nSurfNode, phiSurf, gradPhiSurf, iter, n_moves);
