@@ -38,7 +38,8 @@ SWEEPS_PER_STEP = 8
 METRIC = "WENO5 reinit Gcell-updates/s"
 UNIT = "Gcell-updates/s"
 BYTES_PER_UPDATE = 24.0          # fp64: read phi + read phiS + write phi
-FP64_PER_UPDATE = 307            # FP64-pipe warp instructions per cell update of the FAST sweep kernel (ncu source page)
+FP64_PER_UPDATE = 290            # FP64-pipe warp instructions per cell update of the FAST sweep kernel (ncu source page: 307,
+                                 # minus the 17 DADD |x| that now run as integer ANDs on the ALU pipe)
 FP64_PIPE_PEAK = 148 * 64 * 1.965e9   # lane-ops/s
 
 
@@ -427,7 +428,7 @@ def main():
     ap.add_argument("--grid", type=int, default=1024, help="grid points per axis per GPU")
     ap.add_argument("--arith", default="auto", choices=["auto", "fast", "exact"])
     ap.add_argument("--sched", default="march", choices=["march", "plane"])
-    ap.add_argument("--ref-slab", type=int, default=32, help="z thickness of the CPU sample slab")
+    ap.add_argument("--ref-slab", type=int, default=64, help="z thickness of the CPU sample slab (64: ~18 s of serial CPU work per sweep)")
     ap.add_argument("--minmax-iters", type=int, default=64, help="min/max iterations of the companion measurement (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--f32", action="store_true", help="measure the optional fp32 mode as the main line (single GPU)")
