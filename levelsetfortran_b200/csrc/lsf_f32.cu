@@ -14,6 +14,7 @@
 // sweep kernel, the ghost-plane exchange and the loop control are the fp64 path's, instantiated for float.
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "lsf_internal.cuh"
 
@@ -110,9 +111,19 @@ static void convert_f2d(const float *src, double *dst, long long n)
 // nothing: simple and bounded in memory; PCIe is the limit either way)
 constexpr long long F32_STAGE = 1LL << 25;   // elements per chunk (256 MB of doubles)
 
+// LSF_F32_IO_LOG=1: wall time of the conversions on stderr (diagnostics)
+static double io_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static bool io_log() { static const bool on = getenv("LSF_F32_IO_LOG") != nullptr; return on; }
+
 int f32_upload(Grid *g, const double *host, float *dev, long long np)
 {
     (void)g;
+    const double t_io = io_now();
     double *stage = nullptr;
     const long long cap = np < F32_STAGE ? np : F32_STAGE;
     LSF_CUDA(cudaMalloc(&stage, sizeof(double) * (size_t)cap));
@@ -123,7 +134,10 @@ int f32_upload(Grid *g, const double *host, float *dev, long long np)
         convert_d2f(stage, dev + o, n);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
+    const double t_sync = io_now();
     cudaFree(stage);
+    if (io_log()) fprintf(stderr, "[lsf f32] upload %.1f MB: %.3f s to sync (%.1f GB/s), %.3f s cudaFree\n", np * 8e-6, t_sync - t_io,
+                          np * 8e-9 / (t_sync - t_io), io_now() - t_sync);
     if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "f32 upload: %s", cudaGetErrorString(e));
     return LSF_OK;
 }
@@ -131,6 +145,7 @@ int f32_upload(Grid *g, const double *host, float *dev, long long np)
 int f32_download(Grid *g, const float *dev, double *host, long long np)
 {
     (void)g;
+    const double t_io = io_now();
     double *stage = nullptr;
     const long long cap = np < F32_STAGE ? np : F32_STAGE;
     LSF_CUDA(cudaMalloc(&stage, sizeof(double) * (size_t)cap));
@@ -141,6 +156,7 @@ int f32_download(Grid *g, const float *dev, double *host, long long np)
         e = cudaMemcpyAsync(host + o, stage, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, G.stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
+    if (io_log()) fprintf(stderr, "[lsf f32] download %.1f MB: %.3f s (%.1f GB/s)\n", np * 8e-6, io_now() - t_io, np * 8e-9 / (io_now() - t_io));
     cudaFree(stage);
     if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "f32 download: %s", cudaGetErrorString(e));
     return LSF_OK;
