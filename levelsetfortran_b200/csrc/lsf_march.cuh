@@ -154,6 +154,12 @@ struct RowReader {
     }
 };
 
+// one application of "+ dx" of the boundary block, rounded once (a plain add: nothing to contract)
+LSF_DEV double bc_add(double v, double dx) { return ExactArith::add(v, dx); }
+LSF_DEV float bc_add(float v, float dx) { return v + dx; }
+LSF_DEV int m_imax(int a, int b) { return a > b ? a : b; }
+LSF_DEV int m_imin(int a, int b) { return a < b ? a : b; }
+
 constexpr int M_H = 3;                       // stencil half-width
 constexpr int M_NSLOT = 8;                   // hyperplane slots in the ring (each stored twice)
 constexpr int M_SLOTW = 2 * M_NSLOT + 1;     // doubles per position: 16 + 1 pad (bank spread)
@@ -237,6 +243,19 @@ struct MarchParamsT {
     const long long *edge_wait;    // [ntb of the previous sweep] completion flags of the DOWNSTREAM rank's adjacent tile row, or null
     long long edge_need;           // epoch of the previous sweep (tiles of row ntc-1 wait for it before reading / overwriting that rank's planes)
     int edge_prev_fb;              // b-orientation of the previous sweep (maps this sweep's tile columns onto that sweep's)
+    // ---- overlapped sweeps: ONE launch runs several consecutive sweeps (march_multi_cta) ----
+    // CTAs go on to the tiles of sweep s+1 while sweep s drains.  A tile of sweep s+1 starts once the 3x3 neighbourhood
+    // of tiles of sweep s covering its cells and halo has finished.  The boundary block (subs.f90:858-897) is folded
+    // into the tiles: a finished tile writes the boundary points its cells are the source of into the array the NEXT
+    // sweep reads boundary values from -- phi and a shell array (phiN) alternate, so no reader of the current sweep
+    // ever sees them -- and adds their part of the RMS sum.
+    long long shell_rd_delta;      // (array holding the boundary values this sweep READS) - phi, in elements; 0: phi itself
+    long long shell_wr_delta;      // (array the boundary values for the NEXT sweep are written to) - phi
+    const long long *prev_progress;// progress flags of the previous sweep of this launch; null: first sweep
+    long long prev_fin;            // value a finished tile of that sweep holds
+    int prev_fb, prev_fc;          // b / c orientation of that sweep
+    int fold_bc;                   // 1: finished tiles apply the boundary block for the points they source
+    double *partial_bc;            // per tile: boundary part of the RMS sum
 };
 typedef MarchParamsT<double> MarchParams;
 
@@ -335,15 +354,20 @@ LSF_DEV typename AR::real march_cell(const typename AR::real *Sown, int t, typen
 }
 
 // MG = false compiles the z-slab hooks (peer stores, peer flags) out of the single-GPU kernel.
-template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true>
+// OV = true compiles the overlapped-sweeps hooks in (cross-sweep tile wait, boundary values from the shell array,
+// folded boundary block); single GPU only.
+template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true, bool OV = false>
 LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K)
 {
+    static_assert(!(OV && MG), "overlapped sweeps are a single-GPU schedule");
+    static_assert(!OV || (CFG::VEC == 1 && CFG::R == 1), "overlapped sweeps use scalar loads, one row per thread");
     typedef typename AR::real real;
     constexpr int TB = CFG::TB, TC = CFG::TC, THREADS = CFG::THREADS, RP = CFG::RP, R = CFG::R;
     constexpr int W = CFG::W;
     // thread tid owns rows tid, tid + THREADS, ... of the tile (row q: tb = q % TB, tc = q / TB); all rows of a
     // step lie on one hyperplane, so the R cells a thread updates per step are independent of each other
     bool rowValid[R], compValid[R], pushRow[R], pushUpRow[R], hiBC[R];
+    long long rowShell[R];           // OV: offset to the shell array if the whole row consists of boundary points
     int sig[R];
     real *Sown[R];
     real *pOut[R];
@@ -359,6 +383,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         pushRow[r] = MG && (p.push_delta != 0) && compValid[r] && (c > p.c_hi - M_H);
         pushUpRow[r] = MG && (p.push_up_delta != 0) && compValid[r] && (c < p.c_lo + M_H);
         hiBC[r] = (b >= p.lo_b) && (b <= p.hi_b) && (c >= p.lo_c) && (c <= p.hi_c);
+        rowShell[r] = (OV && (b == p.ny || c == p.c_max)) ? p.shell_rd_delta : 0;
         sig[r] = tb + tc + M_H;
         const long long rowoff = rowValid[r] ? p.off0 + (long long)b * p.sb + (long long)c * p.sc : 0;
         Sown[r] = sm.S + (tc + M_H) * RP + (tb + M_H) * W;
@@ -369,13 +394,14 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 
     // halo duty: thread q feeds halo rows q, q+THREADS, ... (< NHALO)
     bool hvalid[CFG::HR], hlow[CFG::HR];
+    long long hShell[CFG::HR];
     int hsig[CFG::HR];
     const real *hrow[CFG::HR];
     real *hS[CFG::HR];
 #pragma unroll
     for (int r = 0; r < CFG::HR; ++r) {
         const int q = tid + r * THREADS;
-        hvalid[r] = false; hlow[r] = false; hsig[r] = 0; hrow[r] = p.phi; hS[r] = sm.S;
+        hvalid[r] = false; hlow[r] = false; hsig[r] = 0; hrow[r] = p.phi; hS[r] = sm.S; hShell[r] = 0;
         if (q < CFG::NHALO) {
             int htb, htc;
             if (q < 2 * M_H * TC) {                     // -b / +b sides: 3 rows x TC each
@@ -395,6 +421,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             hsig[r] = htb + htc + M_H;
             hS[r] = sm.S + (htc + M_H) * RP + (htb + M_H) * W;
             if (hvalid[r]) hrow[r] = p.phi + p.off0 + (long long)hb * p.sb + (long long)hc * p.sc;
+            if (OV && (hb == 0 || hb == p.ny || hc == 0 || hc == p.c_max)) hShell[r] = p.shell_rd_delta;
         }
     }
 
@@ -404,6 +431,20 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     const long long *predC = (K > 0) ? p.progress + (J + p.ntb * (K - 1)) : (predCpeer ? p.in_progress + J : nullptr);
     long long *mine = p.progress + (J + p.ntb * K);
     long long *minePeer = (MG && K == p.ntc - 1 && p.push_progress) ? p.push_progress + J : nullptr;
+
+    // overlapped sweeps: every tile of the previous sweep that holds a cell this tile reads or overwrites (its rows and
+    // their 3-wide halo) must be finished -- tile columns / rows are counted in that sweep's own orientation
+    if (OV && p.prev_progress) {
+        const int blo = m_imax(1, 1 + J * TB - M_H), bhi = m_imin(p.ny - 1, J * TB + TB + M_H);
+        const int clo = m_imax(1, 1 + K * TC - M_H), chi = m_imin(p.c_max - 1, K * TC + TC + M_H);
+        const bool flipb = p.prev_fb != (FB ? 1 : 0), flipc = p.prev_fc != (FC ? 1 : 0);
+        const int b0 = flipb ? p.ny - bhi : blo, b1 = flipb ? p.ny - blo : bhi;
+        const int c0 = flipc ? p.c_max - chi : clo, c1 = flipc ? p.c_max - clo : chi;
+        const int J0 = (b0 - 1) / TB, J1 = (b1 - 1) / TB, K0 = (c0 - 1) / TC, K1 = (c1 - 1) / TC;
+        const int nj = J1 - J0 + 1, nk = K1 - K0 + 1;
+        if (tid < nj * nk) wait_ge<false>(p.prev_progress + ((J0 + tid % nj) + p.ntb * (K0 + tid / nj)), p.prev_fin, p.ctrl);
+        p_sync();
+    }
 
     // z-slabs: before a tile of the last row touches the downstream rank's planes (reads them as OLD values,
     // streams NEW values into its ghost planes) that rank's adjacent tiles of the PREVIOUS sweep covering the
@@ -476,6 +517,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 #if !(LSF_EXP_NOLDG_MASK & 1)
             if (ldLook[r]) {
                 if constexpr (VEC > 1) la[r] = rdLook.get(pOut[r] + M_LOOK * SA);
+                else if (OV) la[r] = p_ldcg(pOut[r] + M_LOOK * SA + ((a4 == 0 || a4 == p.nx) ? p.shell_rd_delta : rowShell[r]));
                 else la[r] = (LSF_LD_CACHED & 1) ? p_ldca(pOut[r] + M_LOOK * SA) : p_ldcg(pOut[r] + M_LOOK * SA);
             }
 #endif
@@ -503,6 +545,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 #if !(LSF_EXP_NOLDG_MASK & 4)
                 if (hh[r] >= 0 && ah >= 0 && ah <= p.nx) {
                     if constexpr (VEC > 1) hv[r] = rdHalo[r].get(hp[r]);
+                    else if (OV) hv[r] = p_ldcg(hp[r] + ((ah == 0 || ah == p.nx) ? p.shell_rd_delta : hShell[r]));
                     else hv[r] = ((LSF_LD_CACHED & 4) && !hlow[r]) ? p_ldca(hp[r]) : p_ldcg(hp[r]);
                     hdep[r] = true;
                 }
@@ -575,6 +618,58 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + t); }
         }
     }
+    // ---- overlapped sweeps: the boundary block for the points this tile's cells are the source of ------------
+    // (closed form of subs.f90:858-897, see k_reinit_bc_rms: phi(c) = phi(clamp(c)) + dx applied min(1+H,B) times,
+    // B boundary axes of which H on the physical high side).  Results go to the array the NEXT sweep reads boundary
+    // values from; the differences to the values THIS sweep read are the boundary part of the RMS sum.
+    if (OV && p.fold_bc) {
+        p_sync();                                       // the tile's cells are in global memory (L2) for all its threads
+        const real *Xrd = p.phi + p.shell_rd_delta;
+        real *Xwr = p.phi + p.shell_wr_delta;
+        const int bA = 1 + J * TB, bB = m_imin(p.ny - 1, bA + TB - 1);
+        const int cA = 1 + K * TC, cB = m_imin(p.c_max - 1, cA + TC - 1);
+        double accb = 0.;
+        auto point = [&](int a2, int b2, int c2, int b, int c) {        // boundary point (a2,b2,c2), source row (b,c)
+            const int as = a2 < 1 ? 1 : (a2 > p.nx - 1 ? p.nx - 1 : a2);
+            const int i = FA ? p.nx - a2 : a2, j = FB ? p.ny - b2 : b2, k = FC ? p.c_max - c2 : c2;
+            const int Bn = (i == 0 || i == p.nx) + (j == 0 || j == p.ny) + (k == 0 || k == p.c_max);
+            const int Hn = (i == p.nx) + (j == p.ny) + (k == p.c_max);
+            const int m = 1 + Hn < Bn ? 1 + Hn : Bn;
+            real v = p_ldcg(p.phi + p.off0 + (long long)as * SA + (long long)b * p.sb + (long long)c * p.sc);
+            for (int r2 = 0; r2 < m; ++r2) v = bc_add(v, p.cc.dx);
+            const long long q = p.off0 + (long long)a2 * SA + (long long)b2 * p.sb + (long long)c2 * p.sc;
+            const double d = (double)v - (double)p_ldcg(Xrd + q);
+            accb += d * d;
+            p_stcg(Xwr + q, v);
+        };
+        // (1) the two ends of every computed row
+        {
+            const int tb = tid % TB, tc = tid / TB;
+            const int b = bA + tb, c = cA + tc;
+            if (b <= bB && c <= cB) { point(0, b, c, b, c); point(p.nx, b, c, b, c); }
+        }
+        // (2) whole boundary rows next to computed rows on the b / c faces (tiles touching a face only)
+        if (bA == 1 || bB == p.ny - 1 || cA == 1 || cB == p.c_max - 1) {
+            for (int c = cA; c <= cB; ++c)
+                for (int b = bA; b <= bB; ++b)
+                    for (int eb = 0; eb < 3; ++eb)
+                        for (int ec = 0; ec < 3; ++ec) {
+                            if (eb == 0 && ec == 0) continue;
+                            if ((eb == 1 && b != 1) || (eb == 2 && b != p.ny - 1)) continue;
+                            if ((ec == 1 && c != 1) || (ec == 2 && c != p.c_max - 1)) continue;
+                            const int b2 = eb == 0 ? b : (eb == 1 ? 0 : p.ny), c2 = ec == 0 ? c : (ec == 1 ? 0 : p.c_max);
+                            for (int a2 = tid; a2 <= p.nx; a2 += THREADS) point(a2, b2, c2, b, c);
+                        }
+        }
+        sm.red[tid] = accb;
+        p_sync();
+        for (int wdt = THREADS / 2; wdt > 0; wdt >>= 1) {
+            if (tid < wdt) sm.red[tid] = sm.red[tid] + sm.red[tid + wdt];
+            p_sync();
+        }
+        if (tid == 0) p.partial_bc[J + p.ntb * K] = sm.red[0];
+        p_sync();
+    }
     // ---- tile done: final publish + deterministic block reduction of the RMS partial --------
     sm.red[tid] = (double)acc;
     p_sync();
@@ -621,6 +716,45 @@ LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> 
         if (tk >= p.ntiles) break;
         const int jk = p.order[tk];
         march_tile<AR, FA, FB, FC, CFG, MG>(p, sm, tid, jk & 0xffff, jk >> 16);
+    }
+}
+
+// Overlapped sweeps: one launch works through the tiles of `nsweeps` consecutive sweeps (ticket q -> sweep q / ntiles,
+// tile order[q % ntiles]).  Tickets are handed out sweep by sweep and topologically within a sweep, so whatever a tile
+// waits for has a smaller ticket and is held by a resident CTA: no deadlock.  `psm` is a shared-memory copy of the
+// sweep's parameters (they change from ticket to ticket).
+template <class AR, class CFG>
+LSF_DEV void march_multi_cta(const MarchParamsT<typename AR::real> *sweeps, int nsweeps, unsigned *ticket, MarchSmem<CFG> &sm,
+                             MarchParamsT<typename AR::real> &psm, const int tid)
+{
+    if (sweeps[0].ctrl->done) return;
+    const int ntiles = sweeps[0].ntiles;
+    int cur = -1;
+    for (;;) {
+        if (tid == 0) sm.tile = (int)p_ticket(ticket);
+        p_sync();
+        const int tk = sm.tile;
+        p_sync();
+        if (tk >= ntiles * nsweeps) break;
+        const int s = tk / ntiles;
+        if (s != cur) {                                  // (all threads agree on s)
+            if (tid == 0) psm = sweeps[s];
+            cur = s;
+            p_sync();
+        }
+        const MarchParamsT<typename AR::real> &p = psm;
+        const int jk = p.order[tk % ntiles];
+        const int J = jk & 0xffff, K = jk >> 16;
+        switch ((p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0)) {
+        case 0: march_tile<AR, false, false, false, CFG, false, true>(p, sm, tid, J, K); break;
+        case 1: march_tile<AR, true, false, false, CFG, false, true>(p, sm, tid, J, K); break;
+        case 2: march_tile<AR, false, true, false, CFG, false, true>(p, sm, tid, J, K); break;
+        case 3: march_tile<AR, true, true, false, CFG, false, true>(p, sm, tid, J, K); break;
+        case 4: march_tile<AR, false, false, true, CFG, false, true>(p, sm, tid, J, K); break;
+        case 5: march_tile<AR, true, false, true, CFG, false, true>(p, sm, tid, J, K); break;
+        case 6: march_tile<AR, false, true, true, CFG, false, true>(p, sm, tid, J, K); break;
+        default: march_tile<AR, true, true, true, CFG, false, true>(p, sm, tid, J, K); break;
+        }
     }
 }
 

@@ -660,3 +660,96 @@ extern "C" double emu_march_sweep_slabs_f32(float *phi, const float *phiS, int n
     }
     return s;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Overlapped sweeps (march_multi_cta): `nsweeps` consecutive sweeps starting with raster `first_raster` in ONE pass
+// over a shared ticket counter, CTAs moving on to the next sweep's tiles while the previous one drains; boundary block
+// folded into the tiles, boundary values alternating between phi and a shell array.  rms_sum[s] receives the sum of
+// (new-old)^2 over ALL points of sweep s.  Returns 0, or a negative code.
+template <class AR>
+struct MultiArg { const MarchParams *sweeps; int nsweeps; unsigned *ticket; Smem *sm; MarchParams *psm; EmuCta *cta; int tid; };
+
+template <class AR>
+static void *thread_main_multi(void *v)
+{
+    MultiArg<AR> *a = (MultiArg<AR> *)v;
+    emu_cta = a->cta;
+    march_multi_cta<AR, CFG>(a->sweeps, a->nsweeps, a->ticket, *a->sm, *a->psm, a->tid);
+    return nullptr;
+}
+
+extern "C" int emu_march_overlapped(double *phi, const double *phiS, int nx, int ny, int nz, int nsweeps, int first_raster,
+                                    double dx, double h, int arith, int ncta, double *rms_sum)
+{
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    const size_t np = (size_t)sxy * (nz + 1);
+    std::vector<double> shell(np, NAN);                       // only boundary points are ever read, after being written
+    std::vector<MarchParams> P(nsweeps);
+    MarchParams p0;
+    memset(&p0, 0, sizeof(p0));
+    march_orient<CFG>(p0, nx, ny, nz, sx, sxy, 1);
+    const int ntiles = p0.ntiles;
+    std::vector<double> partial((size_t)nsweeps * ntiles, 0.), partial_bc((size_t)nsweeps * ntiles, 0.);
+    std::vector<long long> progress((size_t)nsweeps * ntiles, 0);
+    std::vector<int> order(ntiles);
+    march_fill_order(p0.ntb, p0.ntc, order.data());
+    unsigned ticket = 0;
+    Ctrl ctrl = {0, 0, 0, 0, 0};
+    for (int s = 0; s < nsweeps; ++s) {
+        MarchParams &p = P[s];
+        memset(&p, 0, sizeof(p));
+        march_orient<CFG>(p, nx, ny, nz, sx, sxy, (first_raster - 1 + s) % 8 + 1);
+        p.phi = phi; p.phiS = phiS;
+        p.cc.dx = dx; p.cc.inv_dx = 1. / dx; p.cc.k12 = 1. / (12. * dx); p.cc.dx2 = dx * dx; p.cc.h = h;
+        p.partial = partial.data() + (size_t)s * ntiles; p.partial_bc = partial_bc.data() + (size_t)s * ntiles;
+        p.order = order.data(); p.progress = progress.data() + (size_t)s * ntiles;
+        p.ticket = &ticket; p.ctrl = &ctrl; p.epoch = 1;
+        p.shell_rd_delta = (s & 1) ? shell.data() - phi : 0;
+        p.shell_wr_delta = ((s + 1) & 1) ? shell.data() - phi : 0;
+        p.fold_bc = 1;
+        if (s > 0) {
+            p.prev_progress = progress.data() + (size_t)(s - 1) * ntiles;
+            p.prev_fin = (p.epoch << 32) + M_BIAS + M_FIN;
+            p.prev_fb = P[s - 1].fb; p.prev_fc = P[s - 1].fc;
+        }
+    }
+    if (ncta > ntiles) ncta = ntiles;
+    std::vector<Smem> sm(ncta);
+    std::vector<MarchParams> psm(ncta);
+    std::vector<EmuCta> ctas(ncta);
+    std::vector<pthread_t> th((size_t)ncta * M_THREADS);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 512 * 1024);
+    for (int c = 0; c < ncta; ++c) pthread_barrier_init(&ctas[c].bar, nullptr, M_THREADS);
+    std::vector<MultiArg<ExactArith>> ax((size_t)ncta * M_THREADS);
+    std::vector<MultiArg<FastArith>> af((size_t)ncta * M_THREADS);
+    for (int c = 0; c < ncta; ++c)
+        for (int t = 0; t < M_THREADS; ++t) {
+            const size_t q = (size_t)c * M_THREADS + t;
+            int rc;
+            if (arith == 1) {
+                ax[q] = MultiArg<ExactArith>{P.data(), nsweeps, &ticket, &sm[c], &psm[c], &ctas[c], t};
+                rc = pthread_create(&th[q], &attr, thread_main_multi<ExactArith>, &ax[q]);
+            } else {
+                af[q] = MultiArg<FastArith>{P.data(), nsweeps, &ticket, &sm[c], &psm[c], &ctas[c], t};
+                rc = pthread_create(&th[q], &attr, thread_main_multi<FastArith>, &af[q]);
+            }
+            if (rc != 0) return -1;
+        }
+    for (size_t q = 0; q < th.size(); ++q) pthread_join(th[q], nullptr);
+    for (int c = 0; c < ncta; ++c) pthread_barrier_destroy(&ctas[c].bar);
+    if (ctrl.status != 0) return -3;
+    if (nsweeps & 1)                                          // the last boundary block went to the shell array
+        for (int k = 0; k <= nz; ++k)
+            for (int j = 0; j <= ny; ++j)
+                for (int i = 0; i <= nx; ++i)
+                    if (i == 0 || i == nx || j == 0 || j == ny || k == 0 || k == nz) phi[i + sx * j + sxy * k] = shell[i + sx * j + sxy * k];
+    if (rms_sum)
+        for (int s = 0; s < nsweeps; ++s) {
+            double t = 0.;
+            for (int q = 0; q < ntiles; ++q) t += partial[(size_t)s * ntiles + q] + partial_bc[(size_t)s * ntiles + q];
+            rms_sum[s] = t;
+        }
+    return 0;
+}
