@@ -202,6 +202,8 @@ def run_gpu(args):
     _lib.check(L.lsf_set_arith({"exact": _lib.ARITH_EXACT, "fast": _lib.ARITH_FAST, "auto": _lib.ARITH_AUTO}[args.arith]))
     _lib.check(L.lsf_set_sched(_lib.SCHED_PLANE if args.sched == "plane" else _lib.SCHED_MARCH))
     L.lsf_set_profile(1)
+    if args.overlap:
+        _lib.check(L.lsf_set_overlap(1))
 
     n = args.grid
     shape_pts = (n, n, n)                                      # per GPU (weak scaling)
@@ -383,7 +385,7 @@ def run_gpu(args):
                                        f"{SWEEPS_PER_STEP} Gauss-Seidel raster sweeps (+BC+RMS each)",
                            "global_grid": [n, n, n * world],
                            "grid_per_gpu": list(shape_pts), "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX, "h": h,
-                           "arith": args.arith, "arith_used": "exact" if L.lsf_last_arith() == _lib.ARITH_EXACT else "fast", "sched": args.sched,
+                           "overlapped_sweeps": bool(args.overlap), "arith": args.arith, "arith_used": "exact" if L.lsf_last_arith() == _lib.ARITH_EXACT else "fast", "sched": args.sched,
                            "parallelism": "single GPU" if world == 1 else
                            f"{world} z-slabs, Gauss-Seidel pipeline along k: streaming halo + ghost-plane exchange + RMS reduction "
                            "as peer stores over NVLink from inside the kernels (bit-identical to 1 GPU)",
@@ -430,6 +432,7 @@ def main():
     ap.add_argument("--sched", default="march", choices=["march", "plane"])
     ap.add_argument("--ref-slab", type=int, default=64, help="z thickness of the CPU sample slab (64: ~18 s of serial CPU work per sweep)")
     ap.add_argument("--minmax-iters", type=int, default=64, help="min/max iterations of the companion measurement (0 = skip)")
+    ap.add_argument("--overlap", action="store_true", help="run the sweeps in overlapped batches (lsf_set_overlap; opt-in)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--f32", action="store_true", help="measure the optional fp32 mode as the main line (single GPU)")
     ap.add_argument("--no-f32", action="store_true", help="skip the fp32-mode companion measurement")

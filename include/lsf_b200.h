@@ -69,6 +69,9 @@ int lsf_set_arith(int arith);      /* LSF_ARITH_*  */
 int lsf_last_arith(void);          /* arithmetic the most recent lsf_*reinit call finished in (FAST or EXACT) */
 int lsf_set_sched(int sched);      /* LSF_SCHED_*  */
 int lsf_set_minmax_algo(int algo); /* LSF_MINMAX_* (used with LSF_SCHED_MARCH) */
+int lsf_set_overlap(int on);       /* 1: reinit (fp64, single GPU, march schedule) runs its sweeps in overlapped batches of 8 --
+                                      one launch per batch, CTAs start the next sweep's tiles while the previous one drains
+                                      (same results; opt-in until measured on the target, env LSF_SWEEP_OVERLAP=1) */
 int lsf_set_precision(int prec);   /* LSF_PREC_*: precision lsf_reinit (host-buffer entry point) runs in; env LSF_PRECISION=f32 */
 long long lsf_last_minmax_active(void); /* LSF_MINMAX_LIST: cells on the active list of the most recent min/max call (this rank) */
 /* Timing of the kernels of the most recent lsf_*reinit / lsf_*minmax / lsf_*sign_init call,

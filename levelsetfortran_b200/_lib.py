@@ -36,6 +36,7 @@ SYMBOLS = {
     "lsf_set_minmax_algo": (_I, [_I]),
     "lsf_last_minmax_active": (C.c_longlong, []),
     "lsf_set_precision": (_I, [_I]),
+    "lsf_set_overlap": (_I, [_I]),
     "lsf_last_timing": (_I, [c_double_p, c_int_p]),
     "lsf_set_profile": (_I, [_I]),
     "lsf_last_sweep_timing": (_I, [c_double_p, c_int_p]),

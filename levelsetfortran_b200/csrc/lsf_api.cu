@@ -112,6 +112,40 @@ static int reinit_attempt(Grid *g, int iter, double dx, double h, double tol, do
     Ctrl hc = {0, 0, 0, 0, 0};
     SE.npend = 0;
     *guard_hit = false;
+    // Overlapped sweeps (lsf_set_overlap): batches of OV_BATCH sweeps in one launch each.  With a
+    // tolerance the loop can leave inside a batch: phi is snapshotted before every batch and, if that happens, restored
+    // and the sweeps up to the exit are replayed one by one, so phi, n_exit and rms_hist are those of the plain loop.
+    const bool overlap = march && G.overlap && !want_grad && !sharded(g);
+    if (overlap) {
+        const bool snap = tol > 0.;
+        if (snap && !g->ov_snap) LSF_CUDA(cudaMalloc(&g->ov_snap, bytes + 64));
+        for (int n = 0; n <= iter; n += OV_BATCH) {
+            const int nb = iter + 1 - n < OV_BATCH ? iter + 1 - n : OV_BATCH;
+            if (snap) LSF_CUDA(cudaMemcpyAsync(g->ov_snap, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));
+            SE.begin();
+            rc = launch_reinit_sweeps_overlapped(g, n, nb, cc, tol);
+            SE.end();
+            if (rc) return rc;
+            rc = read_ctrl(g, &hc);
+            if (rc) return rc;
+            SE.collect();
+            if (G.profile) G.n_sweeps += nb - 1;                         // one event pair covered nb sweeps
+            if (watch_guard && hc.guard) { *guard_hit = true; return LSF_OK; }
+            if (hc.done) {
+                if (hc.status >= 0 && hc.n_exit < n + nb - 1 && snap) {
+                    LSF_CUDA(cudaMemcpyAsync(g->phi, g->ov_snap, bytes, cudaMemcpyDeviceToDevice, G.stream));
+                    LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
+                    for (int m = n; m <= hc.n_exit; ++m) {
+                        launch_reinit_sweep_march(g, m % 8 + 1, cc);
+                        launch_reinit_bc_rms(g, dx, march_ntiles(g));
+                    }
+                    LSF_CUDA(cudaMemcpyAsync(g->ctrl, &hc, sizeof(Ctrl), cudaMemcpyHostToDevice, G.stream));
+                    LSF_CUDA(cudaStreamSynchronize(G.stream));
+                }
+                break;
+            }
+        }
+    } else
     for (int n = 0; n <= iter; ++n) {                                   // subs.f90:735
         const int raster = n % 8 + 1;                                   // subs.f90:740,855
         if (grad_replay) launch_copy_if_running(g, g->phiN, g->phi);
@@ -549,6 +583,7 @@ int lsf_init(int device)
         G.arith = (strcmp(a, "exact") == 0) ? LSF_ARITH_EXACT : (strcmp(a, "fast") == 0) ? LSF_ARITH_FAST : LSF_ARITH_AUTO;
     if (const char *s = getenv("LSF_SCHED")) G.sched = (strcmp(s, "plane") == 0) ? LSF_SCHED_PLANE : LSF_SCHED_MARCH;
     if (const char *m = getenv("LSF_MINMAX")) G.mm_algo = (strcmp(m, "march") == 0) ? LSF_MINMAX_MARCH : LSF_MINMAX_LIST;
+    if (const char *o = getenv("LSF_SWEEP_OVERLAP")) G.overlap = atoi(o) != 0;
     if (const char *q = getenv("LSF_PRECISION")) G.prec = (strcmp(q, "f32") == 0) ? LSF_PREC_F32 : LSF_PREC_F64;
     G.inited = true;
     return LSF_OK;
@@ -593,6 +628,12 @@ int lsf_set_minmax_algo(int algo)
 }
 
 long long lsf_last_minmax_active(void) { return G.mm_active; }
+
+int lsf_set_overlap(int on)
+{
+    G.overlap = on != 0;
+    return LSF_OK;
+}
 
 int lsf_set_precision(int prec)
 {
@@ -664,6 +705,7 @@ int lsf_grid_destroy(lsf_grid *g)
     cudaFree(g->phiS); cudaFree(g->lap); cudaFree(g->mask);
     cudaFree(g->partial); cudaFree(g->hist); cudaFree(g->ctrl);
     cudaFree(g->march_ticket); cudaFree(g->march_progress);
+    cudaFree(g->ov_progress); cudaFree(g->ov_partial); cudaFree(g->ov_snap);
     cudaFree(g->mml_list); cudaFree(g->mml_unres); cudaFree(g->mml_work); cudaFree(g->mml_work_count);
     free(g);
     return LSF_OK;

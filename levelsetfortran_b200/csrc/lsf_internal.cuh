@@ -43,6 +43,11 @@ struct lsf_grid {
     // the stencil band phiSB of the reference after the min/max loop is the band of the field the LAST narrowBand
     // call saw (set3d.f90:460): phiN after a tolerance EXIT, phi otherwise (lsf_nodes.cu)
     bool sb_from_phiN;
+    // overlapped sweeps (lsf_march.cu: launch_reinit_sweeps_overlapped)
+    long long *ov_progress;       // per sweep slot and tile
+    double *ov_partial;           // per sweep slot: interior partials [ntiles] then boundary partials [ntiles]
+    int ov_tiles_cap;
+    double *ov_snap;              // phi before the current batch (tolerance EXIT inside a batch -> roll back and replay)
     bool prev_sweep_valid;        // the previous launch on this grid was a sweep of the same free-running sequence
     long long prev_sweep_epoch;
     int prev_sweep_fb;
@@ -68,6 +73,7 @@ struct Global {
     int sched = LSF_SCHED_MARCH;
     int mm_algo = LSF_MINMAX_LIST;
     int prec = LSF_PREC_F64;       // precision of the host-buffer lsf_reinit entry point
+    bool overlap = false;          // reinit: run the sweeps in overlapped batches (lsf_set_overlap)
     long long mm_active = 0;       // length of the active list of the most recent min/max call (this rank)
     int n_launch = 0;
     double last_ms = 0.;
@@ -92,7 +98,8 @@ void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double 
 void launch_reinit_bc(Grid *g, double dx);
 void launch_reinit_bc_rms(Grid *g, double dx, int partial_off);
 void launch_rms(Grid *g, bool copy);
-void launch_finalize(Grid *g, int npart, int hist_off, double tol);
+void launch_finalize(Grid *g, int npart, int hist_off, double tol, const double *partial = nullptr);
+void launch_copy_boundary(Grid *g, double *dst, const double *src);
 void launch_copy_if_running(Grid *g, double *dst, const double *src);
 void launch_narrowband(Grid *g, const double *phi, double dx, int32_t *nb, int32_t *sb);
 void launch_minmax_iteration_plane(Grid *g, double dx, double h1, bool mask_given);
@@ -124,6 +131,8 @@ int march_prepare(Grid *g);
 int march_ntiles(const Grid *g);
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc);
 void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc);
+constexpr int OV_BATCH = 8;      // sweeps per overlapped launch (even: the boundary values are back in phi after a full batch)
+int launch_reinit_sweeps_overlapped(Grid *g, int n_first, int nsweeps, const CellConst &cc, double tol);
 const int *march_order();
 
 // lsf_f32.cu -- fp32 grids (g->f32)

@@ -239,10 +239,32 @@ k_finalize(const double *__restrict__ partial, int npart, Ctrl *ctrl, double *__
     }
 }
 
-void launch_finalize(Grid *g, int npart, int hist_off, double tol)
+void launch_finalize(Grid *g, int npart, int hist_off, double tol, const double *partial)
 {
     const double denom = (double)((long long)g->dm.nx * g->dm.ny * g->dm.nz);
-    k_finalize<<<1, 256, 0, G.stream>>>(g->partial, npart, g->ctrl, g->hist, hist_off, denom, tol);
+    k_finalize<<<1, 256, 0, G.stream>>>(partial ? partial : g->partial, npart, g->ctrl, g->hist, hist_off, denom, tol);
+    G.n_launch++;
+}
+
+// overlapped sweeps: after an odd number of sweeps the current boundary values live in the shell array
+__global__ void k_copy_boundary(double *__restrict__ dst, const double *__restrict__ src, Dims dm)
+{
+    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzp = dm.nz + 1;
+    const long long fxy = nxp * nyp, fxz = nxp * nzp, fyz = nyp * nzp;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < 2 * (fxy + fxz + fyz); t0 += (long long)gridDim.x * blockDim.x) {
+        long long t = t0;
+        long long i, j, k;
+        if (t < 2 * fxy) { k = (t >= fxy) ? dm.nz : 0; t %= fxy; i = t % nxp; j = t / nxp; }
+        else if ((t -= 2 * fxy) < 2 * fxz) { j = (t >= fxz) ? dm.ny : 0; t %= fxz; i = t % nxp; k = t / nxp; }
+        else { t -= 2 * fxz; i = (t >= fyz) ? dm.nx : 0; t %= fyz; j = t % nyp; k = t / nyp; }
+        const long long q = i + dm.sx * j + dm.sxy * k;
+        dst[q] = src[q];
+    }
+}
+
+void launch_copy_boundary(Grid *g, double *dst, const double *src)
+{
+    k_copy_boundary<<<BC_BLOCKS, 256, 0, G.stream>>>(dst, src, g->dm);
     G.n_launch++;
 }
 

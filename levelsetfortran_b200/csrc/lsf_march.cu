@@ -208,6 +208,78 @@ void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc)
     G.n_launch++;
 }
 
+// ---- overlapped sweeps (march_multi_cta, lsf_march.cuh): one launch = OV_BATCH consecutive sweeps -----------------
+struct MultiParams {
+    MarchParams p[OV_BATCH];
+};
+
+template <class AR>
+__global__ void __launch_bounds__(CFG::THREADS, LSF_OCC)
+k_reinit_march_multi(const __grid_constant__ MultiParams mp, int nsweeps, unsigned *ticket)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MarchSmem<CFG> &sm = *reinterpret_cast<MarchSmem<CFG> *>(smem_raw);
+    march_multi_cta<AR, CFG>(mp.p, nsweeps, ticket, sm, threadIdx.x);
+}
+
+// Sweeps n_first .. n_first + nsweeps - 1 of the reinit loop in one launch, then their RMS / EXIT / NaN tests in order
+// (k_finalize per sweep: sweeps after an exit leave the history alone; phi then holds the state after the WHOLE batch and
+// the caller rolls back).  The shell array is phiN.  Returns LSF_OK or an allocation error.
+int launch_reinit_sweeps_overlapped(Grid *g, int n_first, int nsweeps, const CellConst &cc, double tol)
+{
+    MarchParams p0;
+    march_orient_grid(p0, g, 1);
+    const int ntiles = p0.ntiles;
+    if (g->ov_tiles_cap < ntiles) {
+        cudaFree(g->ov_progress); cudaFree(g->ov_partial);
+        g->ov_progress = nullptr; g->ov_partial = nullptr; g->ov_tiles_cap = 0;
+        LSF_CUDA(cudaMalloc(&g->ov_progress, sizeof(long long) * (size_t)OV_BATCH * ntiles));
+        LSF_CUDA(cudaMemsetAsync(g->ov_progress, 0, sizeof(long long) * (size_t)OV_BATCH * ntiles, G.stream));
+        LSF_CUDA(cudaMalloc(&g->ov_partial, sizeof(double) * (size_t)OV_BATCH * 2 * ntiles));
+        g->ov_tiles_cap = ntiles;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        LSF_CUDA(cudaFuncSetAttribute(k_reinit_march_multi<FastArith>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+        LSF_CUDA(cudaFuncSetAttribute(k_reinit_march_multi<ExactArith>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+        attr_done = true;
+    }
+    MultiParams MP;
+    memset(&MP, 0, sizeof(MP));
+    MarchParams *P = MP.p;
+    const long long epoch = ++g->march_epoch;
+    for (int s = 0; s < nsweeps; ++s) {
+        MarchParams &p = P[s];
+        memset(&p, 0, sizeof(p));
+        march_orient_grid(p, g, (n_first + s) % 8 + 1);                  // subs.f90:740,855
+        p.phi = g->phi; p.phiS = g->phiS; p.cc = cc;
+        p.partial = g->ov_partial + (size_t)s * 2 * ntiles;
+        p.partial_bc = p.partial + ntiles;
+        p.ticket = g->march_ticket; p.order = MH.d_order;
+        p.progress = g->ov_progress + (size_t)s * ntiles; p.epoch = epoch; p.ctrl = g->ctrl;
+        p.shell_rd_delta = (s & 1) ? g->phiN - g->phi : 0;
+        p.shell_wr_delta = ((s + 1) & 1) ? g->phiN - g->phi : 0;
+        p.fold_bc = 1;
+        if (s > 0) {
+            p.prev_progress = g->ov_progress + (size_t)(s - 1) * ntiles;
+            p.prev_fin = (epoch << 32) + M_BIAS + M_FIN;
+            p.prev_fb = P[s - 1].fb; p.prev_fc = P[s - 1].fc;
+        }
+    }
+    cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
+    const int ncta = ntiles < LSF_OCC * G.num_sms ? ntiles : LSF_OCC * G.num_sms;
+    if (G.arith_run == LSF_ARITH_EXACT)
+        k_reinit_march_multi<ExactArith><<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(MP, nsweeps, g->march_ticket);
+    else
+        k_reinit_march_multi<FastArith><<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(MP, nsweeps, g->march_ticket);
+    G.n_launch++;
+    if (nsweeps & 1) launch_copy_boundary(g, g->phi, g->phiN);            // the last boundary block went to the shell array
+    for (int s = 0; s < nsweeps; ++s)
+        launch_finalize(g, 2 * ntiles, 0, tol, g->ov_partial + (size_t)s * 2 * ntiles);   // subs.f90:914-926, in sweep order
+    g->prev_sweep_valid = false;
+    return LSF_OK;
+}
+
 void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
 {
     MarchParams p;

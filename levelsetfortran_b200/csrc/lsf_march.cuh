@@ -721,28 +721,21 @@ LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> 
 
 // Overlapped sweeps: one launch works through the tiles of `nsweeps` consecutive sweeps (ticket q -> sweep q / ntiles,
 // tile order[q % ntiles]).  Tickets are handed out sweep by sweep and topologically within a sweep, so whatever a tile
-// waits for has a smaller ticket and is held by a resident CTA: no deadlock.  `psm` is a shared-memory copy of the
-// sweep's parameters (they change from ticket to ticket).
+// waits for has a smaller ticket and is held by a resident CTA: no deadlock.  `sweeps` is the per-sweep parameter
+// array (on the GPU: a __grid_constant__ kernel parameter, i.e. constant-bank reads with a run-time index).
 template <class AR, class CFG>
 LSF_DEV void march_multi_cta(const MarchParamsT<typename AR::real> *sweeps, int nsweeps, unsigned *ticket, MarchSmem<CFG> &sm,
-                             MarchParamsT<typename AR::real> &psm, const int tid)
+                             const int tid)
 {
     if (sweeps[0].ctrl->done) return;
     const int ntiles = sweeps[0].ntiles;
-    int cur = -1;
     for (;;) {
         if (tid == 0) sm.tile = (int)p_ticket(ticket);
         p_sync();
         const int tk = sm.tile;
         p_sync();
         if (tk >= ntiles * nsweeps) break;
-        const int s = tk / ntiles;
-        if (s != cur) {                                  // (all threads agree on s)
-            if (tid == 0) psm = sweeps[s];
-            cur = s;
-            p_sync();
-        }
-        const MarchParamsT<typename AR::real> &p = psm;
+        const MarchParamsT<typename AR::real> &p = sweeps[tk / ntiles];
         const int jk = p.order[tk % ntiles];
         const int J = jk & 0xffff, K = jk >> 16;
         switch ((p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0)) {

@@ -70,6 +70,12 @@ def set_minmax_algo(march: bool):
     check(lib().lsf_set_minmax_algo(_lib.MINMAX_MARCH if march else _lib.MINMAX_LIST))
 
 
+def set_overlap(on: bool):
+    """True: `reinit` (fp64, single GPU, march schedule) runs its sweeps in overlapped batches of 8 (one launch per batch;
+    CTAs go on to the next sweep's tiles while the previous sweep drains).  Same results; opt-in."""
+    check(lib().lsf_set_overlap(1 if on else 0))
+
+
 def set_precision(f32: bool):
     """False (default): the reference's REAL(8) on the device; True: the optional fp32 mode of the host-buffer
     `reinit` (device fields and WENO5 arithmetic in single precision, host arrays stay float64; contract

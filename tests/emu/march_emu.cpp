@@ -667,14 +667,14 @@ extern "C" double emu_march_sweep_slabs_f32(float *phi, const float *phiS, int n
 // folded into the tiles, boundary values alternating between phi and a shell array.  rms_sum[s] receives the sum of
 // (new-old)^2 over ALL points of sweep s.  Returns 0, or a negative code.
 template <class AR>
-struct MultiArg { const MarchParams *sweeps; int nsweeps; unsigned *ticket; Smem *sm; MarchParams *psm; EmuCta *cta; int tid; };
+struct MultiArg { const MarchParams *sweeps; int nsweeps; unsigned *ticket; Smem *sm; EmuCta *cta; int tid; };
 
 template <class AR>
 static void *thread_main_multi(void *v)
 {
     MultiArg<AR> *a = (MultiArg<AR> *)v;
     emu_cta = a->cta;
-    march_multi_cta<AR, CFG>(a->sweeps, a->nsweeps, a->ticket, *a->sm, *a->psm, a->tid);
+    march_multi_cta<AR, CFG>(a->sweeps, a->nsweeps, a->ticket, *a->sm, a->tid);
     return nullptr;
 }
 
@@ -715,7 +715,6 @@ extern "C" int emu_march_overlapped(double *phi, const double *phiS, int nx, int
     }
     if (ncta > ntiles) ncta = ntiles;
     std::vector<Smem> sm(ncta);
-    std::vector<MarchParams> psm(ncta);
     std::vector<EmuCta> ctas(ncta);
     std::vector<pthread_t> th((size_t)ncta * M_THREADS);
     pthread_attr_t attr;
@@ -729,10 +728,10 @@ extern "C" int emu_march_overlapped(double *phi, const double *phiS, int nx, int
             const size_t q = (size_t)c * M_THREADS + t;
             int rc;
             if (arith == 1) {
-                ax[q] = MultiArg<ExactArith>{P.data(), nsweeps, &ticket, &sm[c], &psm[c], &ctas[c], t};
+                ax[q] = MultiArg<ExactArith>{P.data(), nsweeps, &ticket, &sm[c], &ctas[c], t};
                 rc = pthread_create(&th[q], &attr, thread_main_multi<ExactArith>, &ax[q]);
             } else {
-                af[q] = MultiArg<FastArith>{P.data(), nsweeps, &ticket, &sm[c], &psm[c], &ctas[c], t};
+                af[q] = MultiArg<FastArith>{P.data(), nsweeps, &ticket, &sm[c], &ctas[c], t};
                 rc = pthread_create(&th[q], &attr, thread_main_multi<FastArith>, &af[q]);
             }
             if (rc != 0) return -1;

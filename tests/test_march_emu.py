@@ -257,3 +257,37 @@ def test_f32_slab_pipeline_is_an_exact_reordering(emu, shape, nranks, ncta, m):
         s = emu.emu_march_sweep_slabs_f32(b.ctypes.data_as(fp), pS.ctypes.data_as(fp), nx, ny, nz, nranks, r, 0.05, 0.0014, ncta, m)
         assert s >= 0, s
         assert np.array_equal(a, b), f"raster {r}: fp32 slab pipeline differs from the fp32 lexicographic sweep"
+
+
+# ------------------------------------------------------------------------------------ overlapped sweeps
+@pytest.mark.parametrize("shape,ncta,nsweeps,first,stall", [((22, 21, 23), 1, 3, 1, 0), ((40, 38, 36), 9, 10, 1, 20000),
+                                                            ((19, 50, 33), 6, 11, 4, 5000), ((6, 5, 7), 2, 5, 7, 0)])
+def test_overlapped_sweeps_are_an_exact_reordering(emu, oracle, shape, ncta, nsweeps, first, stall):
+    """march_multi_cta: several consecutive sweeps in ONE pass over a shared ticket counter -- CTAs start the next
+    sweep's tiles while the previous sweep drains, the boundary block is folded into the tiles and the boundary values
+    alternate between phi and a shell array.  phi must equal the oracle's sweep + boundary block sequence bit for bit
+    and the per-sweep RMS sums (interior + boundary parts) must match."""
+    emu.emu_march_overlapped.restype = C.c_int
+    emu.emu_march_overlapped.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp]
+    p0 = synth_field(shape, seed=3)
+    pS = p0.copy(order="F")
+    a, b, f = p0.copy(order="F"), p0.copy(order="F"), p0.copy(order="F")
+    nx, ny, nz = (s - 1 for s in shape)
+    ref = np.zeros(nsweeps)
+    for s in range(nsweeps):
+        before = a.copy(order="F")
+        oracle.reinit_sweep(a, pS, 0.05, 0.0014, (first - 1 + s) % 8 + 1)
+        oracle.bc(a, 0.05)
+        ref[s] = float(((a - before) ** 2).sum())
+    rms = np.zeros(nsweeps)
+    emu.emu_set_stall(stall)
+    try:
+        rc = emu.emu_march_overlapped(b.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, nsweeps, first, 0.05, 0.0014, 1, ncta,
+                                      rms.ctypes.data_as(dp))
+    finally:
+        emu.emu_set_stall(0)
+    assert rc == 0
+    assert np.array_equal(a, b), "overlapped sweeps differ from the serial oracle"
+    assert np.allclose(rms, ref, rtol=1e-12, atol=0)
+    rc = emu.emu_march_overlapped(f.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, nsweeps, first, 0.05, 0.0014, 0, ncta, None)
+    assert rc == 0 and np.abs(a - f).max() < 1e-13
