@@ -222,6 +222,37 @@ k_reinit_march_multi(const __grid_constant__ MultiParams mp, int nsweeps, unsign
     march_multi_cta<AR, CFG>(mp.p, nsweeps, ticket, sm, threadIdx.x);
 }
 
+// Second packaging of the same schedule (LSF_OVERLAP_PDL=1): ONE KERNEL PER SWEEP as in the production path -- compile-
+// time orientation, by-value parameters -- with the overlapped-sweeps hooks, chained by programmatic dependent launch:
+// every CTA executes griddepcontrol.launch_dependents as soon as it is resident, so the next sweep's kernel is admitted
+// when all CTAs of this one hold their SM slots and its CTAs move in as these run out of tickets.  No
+// griddepcontrol.wait: the tile flags carry the data dependences.  (Written in the last hour of round 1; the tile code
+// is the one verified above, the launch mechanics have not run on a GPU yet.)
+template <class AR, bool FA, bool FB, bool FC>
+__global__ void __launch_bounds__(CFG::THREADS, LSF_OCC)
+k_reinit_march_ov(const MarchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MarchSmem<CFG> &sm = *reinterpret_cast<MarchSmem<CFG> *>(smem_raw);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    march_cta<AR, FA, FB, FC, CFG, false, true>(p, sm, threadIdx.x);
+}
+
+template <class AR>
+static MarchKernel march_kernel_ov(int fa, int fb, int fc)
+{
+    switch ((fa ? 1 : 0) | (fb ? 2 : 0) | (fc ? 4 : 0)) {
+    case 0: return k_reinit_march_ov<AR, false, false, false>;
+    case 1: return k_reinit_march_ov<AR, true, false, false>;
+    case 2: return k_reinit_march_ov<AR, false, true, false>;
+    case 3: return k_reinit_march_ov<AR, true, true, false>;
+    case 4: return k_reinit_march_ov<AR, false, false, true>;
+    case 5: return k_reinit_march_ov<AR, true, false, true>;
+    case 6: return k_reinit_march_ov<AR, false, true, true>;
+    default: return k_reinit_march_ov<AR, true, true, true>;
+    }
+}
+
 // Sweeps n_first .. n_first + nsweeps - 1 of the reinit loop in one launch, then their RMS / EXIT / NaN tests in order
 // (k_finalize per sweep: sweeps after an exit leave the history alone; phi then holds the state after the WHOLE batch and
 // the caller rolls back).  The shell array is phiN.  Returns LSF_OK or an allocation error.
@@ -266,13 +297,43 @@ int launch_reinit_sweeps_overlapped(Grid *g, int n_first, int nsweeps, const Cel
             p.prev_fb = P[s - 1].fb; p.prev_fc = P[s - 1].fc;
         }
     }
-    cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     const int ncta = ntiles < LSF_OCC * G.num_sms ? ntiles : LSF_OCC * G.num_sms;
+    static const bool pdl = getenv("LSF_OVERLAP_PDL") != nullptr && atoi(getenv("LSF_OVERLAP_PDL")) != 0;
+    if (pdl) {
+        // one ticket counter per sweep slot (a memset between two kernels would break their adjacency in the stream)
+        static unsigned *tickets = nullptr;
+        if (!tickets) LSF_CUDA(cudaMalloc(&tickets, sizeof(unsigned) * OV_BATCH));
+        LSF_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * OV_BATCH, G.stream));
+        static bool ov_attr_done = false;
+        if (!ov_attr_done) {
+            for (int o = 0; o < 8; ++o) {
+                LSF_CUDA(cudaFuncSetAttribute(march_kernel_ov<FastArith>(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+                LSF_CUDA(cudaFuncSetAttribute(march_kernel_ov<ExactArith>(o & 1, o & 2, o & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+            }
+            ov_attr_done = true;
+        }
+        for (int s = 0; s < nsweeps; ++s) {
+            P[s].ticket = tickets + s;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(CFG::THREADS);
+            cfg.dynamicSmemBytes = sizeof(MarchSmem<CFG>); cfg.stream = G.stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = s > 0 ? 1 : 0;            // the first sweep of a batch is an ordinary launch
+            MarchKernel kern = (G.arith_run == LSF_ARITH_EXACT) ? march_kernel_ov<ExactArith>(P[s].fa, P[s].fb, P[s].fc)
+                                                            : march_kernel_ov<FastArith>(P[s].fa, P[s].fb, P[s].fc);
+            LSF_CUDA(cudaLaunchKernelEx(&cfg, kern, P[s]));
+            G.n_launch++;
+        }
+    } else {
+    cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     if (G.arith_run == LSF_ARITH_EXACT)
         k_reinit_march_multi<ExactArith><<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(MP, nsweeps, g->march_ticket);
     else
         k_reinit_march_multi<FastArith><<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(MP, nsweeps, g->march_ticket);
     G.n_launch++;
+    }
     if (nsweeps & 1) launch_copy_boundary(g, g->phi, g->phiN);            // the last boundary block went to the shell array
     for (int s = 0; s < nsweeps; ++s)
         launch_finalize(g, 2 * ntiles, 0, tol, g->ov_partial + (size_t)s * 2 * ntiles);   // subs.f90:914-926, in sweep order

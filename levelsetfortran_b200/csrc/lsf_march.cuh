@@ -697,7 +697,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 }
 
 // Persistent CTA: take tickets until the tile list is exhausted.
-template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true>
+template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true, bool OV = false>
 LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid)
 {
     if (p.ctrl->done) return;
@@ -715,7 +715,7 @@ LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> 
         p_sync();
         if (tk >= p.ntiles) break;
         const int jk = p.order[tk];
-        march_tile<AR, FA, FB, FC, CFG, MG>(p, sm, tid, jk & 0xffff, jk >> 16);
+        march_tile<AR, FA, FB, FC, CFG, MG, OV>(p, sm, tid, jk & 0xffff, jk >> 16);
     }
 }
 
