@@ -236,6 +236,9 @@ k_reinit_march_ov(const MarchParams p)
     MarchSmem<CFG> &sm = *reinterpret_cast<MarchSmem<CFG> *>(smem_raw);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     march_cta<AR, FA, FB, FC, CFG, false, true>(p, sm, threadIdx.x);
+    // completion must be transitive along the chain (the batch's loop-control kernels follow the LAST sweep's kernel in the
+    // stream and read every sweep's RMS partials): do not retire before the previous sweep's grid has
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <class AR>
