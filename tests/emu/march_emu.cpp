@@ -752,3 +752,99 @@ extern "C" int emu_march_overlapped(double *phi, const double *phiS, int nx, int
         }
     return 0;
 }
+
+// The second packaging of the overlapped sweeps (one kernel per sweep, chained by programmatic dependent launch on the
+// GPU): here every sweep gets its own CTAs and its own ticket counter and ALL sweeps' CTAs run at once -- the most
+// aggressive overlap the flags have to cope with (on the GPU at most two sweeps are resident together).
+struct SweepArg { const MarchParams *p; Smem *sm; EmuCta *cta; int tid; int arith; };
+
+static void *thread_main_ov_sweep(void *v)
+{
+    SweepArg *a = (SweepArg *)v;
+    emu_cta = a->cta;
+    const MarchParams &p = *a->p;
+    const int o = (p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0);
+#define OVRUN(AR)                                                                                   \
+    switch (o) {                                                                                    \
+    case 0: march_cta<AR, false, false, false, CFG, false, true>(p, *a->sm, a->tid); break;         \
+    case 1: march_cta<AR, true, false, false, CFG, false, true>(p, *a->sm, a->tid); break;          \
+    case 2: march_cta<AR, false, true, false, CFG, false, true>(p, *a->sm, a->tid); break;          \
+    case 3: march_cta<AR, true, true, false, CFG, false, true>(p, *a->sm, a->tid); break;           \
+    case 4: march_cta<AR, false, false, true, CFG, false, true>(p, *a->sm, a->tid); break;          \
+    case 5: march_cta<AR, true, false, true, CFG, false, true>(p, *a->sm, a->tid); break;           \
+    case 6: march_cta<AR, false, true, true, CFG, false, true>(p, *a->sm, a->tid); break;           \
+    default: march_cta<AR, true, true, true, CFG, false, true>(p, *a->sm, a->tid); break;           \
+    }
+    if (a->arith == 1) { OVRUN(ExactArith) } else { OVRUN(FastArith) }
+#undef OVRUN
+    return nullptr;
+}
+
+extern "C" int emu_march_overlapped_per_sweep(double *phi, const double *phiS, int nx, int ny, int nz, int nsweeps, int first_raster,
+                                              double dx, double h, int arith, int ncta, double *rms_sum)
+{
+    const long long sx = nx + 1, sxy = sx * (ny + 1);
+    const size_t np = (size_t)sxy * (nz + 1);
+    std::vector<double> shell(np, NAN);
+    std::vector<MarchParams> P(nsweeps);
+    MarchParams p0;
+    memset(&p0, 0, sizeof(p0));
+    march_orient<CFG>(p0, nx, ny, nz, sx, sxy, 1);
+    const int ntiles = p0.ntiles;
+    std::vector<double> partial((size_t)nsweeps * ntiles, 0.), partial_bc((size_t)nsweeps * ntiles, 0.);
+    std::vector<long long> progress((size_t)nsweeps * ntiles, 0);
+    std::vector<int> order(ntiles);
+    march_fill_order(p0.ntb, p0.ntc, order.data());
+    std::vector<unsigned> tickets(nsweeps, 0u);
+    Ctrl ctrl = {0, 0, 0, 0, 0};
+    for (int s = 0; s < nsweeps; ++s) {
+        MarchParams &p = P[s];
+        memset(&p, 0, sizeof(p));
+        march_orient<CFG>(p, nx, ny, nz, sx, sxy, (first_raster - 1 + s) % 8 + 1);
+        p.phi = phi; p.phiS = phiS;
+        p.cc.dx = dx; p.cc.inv_dx = 1. / dx; p.cc.k12 = 1. / (12. * dx); p.cc.dx2 = dx * dx; p.cc.h = h;
+        p.partial = partial.data() + (size_t)s * ntiles; p.partial_bc = partial_bc.data() + (size_t)s * ntiles;
+        p.order = order.data(); p.progress = progress.data() + (size_t)s * ntiles;
+        p.ticket = &tickets[s]; p.ctrl = &ctrl; p.epoch = 1;
+        p.shell_rd_delta = (s & 1) ? shell.data() - phi : 0;
+        p.shell_wr_delta = ((s + 1) & 1) ? shell.data() - phi : 0;
+        p.fold_bc = 1;
+        if (s > 0) {
+            p.prev_progress = progress.data() + (size_t)(s - 1) * ntiles;
+            p.prev_fin = (p.epoch << 32) + M_BIAS + M_FIN;
+            p.prev_fb = P[s - 1].fb; p.prev_fc = P[s - 1].fc;
+        }
+    }
+    if (ncta > ntiles) ncta = ntiles;
+    const size_t nthreads = (size_t)nsweeps * ncta * M_THREADS;
+    std::vector<Smem> sm((size_t)nsweeps * ncta);
+    std::vector<EmuCta> ctas((size_t)nsweeps * ncta);
+    std::vector<SweepArg> args(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 512 * 1024);
+    for (size_t c = 0; c < ctas.size(); ++c) pthread_barrier_init(&ctas[c].bar, nullptr, M_THREADS);
+    size_t q = 0;
+    for (int s = 0; s < nsweeps; ++s)
+        for (int c = 0; c < ncta; ++c)
+            for (int t = 0; t < M_THREADS; ++t, ++q) {
+                args[q] = SweepArg{&P[s], &sm[(size_t)s * ncta + c], &ctas[(size_t)s * ncta + c], t, arith};
+                if (pthread_create(&th[q], &attr, thread_main_ov_sweep, &args[q]) != 0) return -1;
+            }
+    for (size_t i = 0; i < th.size(); ++i) pthread_join(th[i], nullptr);
+    for (size_t c = 0; c < ctas.size(); ++c) pthread_barrier_destroy(&ctas[c].bar);
+    if (ctrl.status != 0) return -3;
+    if (nsweeps & 1)
+        for (int k = 0; k <= nz; ++k)
+            for (int j = 0; j <= ny; ++j)
+                for (int i = 0; i <= nx; ++i)
+                    if (i == 0 || i == nx || j == 0 || j == ny || k == 0 || k == nz) phi[i + sx * j + sxy * k] = shell[i + sx * j + sxy * k];
+    if (rms_sum)
+        for (int s = 0; s < nsweeps; ++s) {
+            double t = 0.;
+            for (int i = 0; i < ntiles; ++i) t += partial[(size_t)s * ntiles + i] + partial_bc[(size_t)s * ntiles + i];
+            rms_sum[s] = t;
+        }
+    return 0;
+}

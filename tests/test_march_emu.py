@@ -291,3 +291,32 @@ def test_overlapped_sweeps_are_an_exact_reordering(emu, oracle, shape, ncta, nsw
     assert np.allclose(rms, ref, rtol=1e-12, atol=0)
     rc = emu.emu_march_overlapped(f.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, nsweeps, first, 0.05, 0.0014, 0, ncta, None)
     assert rc == 0 and np.abs(a - f).max() < 1e-13
+
+
+@pytest.mark.parametrize("shape,ncta,nsweeps,first,stall", [((24, 36, 22), 2, 4, 1, 0), ((40, 38, 36), 3, 6, 3, 10000),
+                                                            ((19, 50, 33), 2, 5, 6, 5000)])
+def test_overlapped_sweeps_one_kernel_per_sweep(emu, oracle, shape, ncta, nsweeps, first, stall):
+    """The second packaging (one kernel per sweep, chained by programmatic dependent launch on the GPU): here every sweep
+    has its own CTAs and ticket counter and ALL sweeps run at once -- more overlap than the GPU ever admits.  Bit-identical."""
+    emu.emu_march_overlapped_per_sweep.restype = C.c_int
+    emu.emu_march_overlapped_per_sweep.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                   C.c_int, C.c_int, dp]
+    p0 = synth_field(shape, seed=3)
+    pS = p0.copy(order="F")
+    a, b = p0.copy(order="F"), p0.copy(order="F")
+    nx, ny, nz = (s - 1 for s in shape)
+    ref = np.zeros(nsweeps)
+    for s in range(nsweeps):
+        before = a.copy(order="F")
+        oracle.reinit_sweep(a, pS, 0.05, 0.0014, (first - 1 + s) % 8 + 1)
+        oracle.bc(a, 0.05)
+        ref[s] = float(((a - before) ** 2).sum())
+    rms = np.zeros(nsweeps)
+    emu.emu_set_stall(stall)
+    try:
+        rc = emu.emu_march_overlapped_per_sweep(b.ctypes.data_as(dp), pS.ctypes.data_as(dp), nx, ny, nz, nsweeps, first, 0.05,
+                                                0.0014, 1, ncta, rms.ctypes.data_as(dp))
+    finally:
+        emu.emu_set_stall(0)
+    assert rc == 0 and np.array_equal(a, b)
+    assert np.allclose(rms, ref, rtol=1e-12, atol=0)
