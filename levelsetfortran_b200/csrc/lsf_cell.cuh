@@ -114,7 +114,7 @@ struct ExactArith {
     }
 
     // Godunov selection + |grad phi|, subs.f90:667-702.  g[3] receives gradX,gradY,gradZ.
-    static LSF_HD double godunov(double phic, double a, double b, double c, double d, double e, double f, double g[3])
+    static LSF_HD double godunov(double phic, double a, double b, double c, double d, double e, double f, double g[3], const CellConst &)
     {
         const double pa = fmax_f(a, 0.), pb = fmax_f(b, 0.), pc = fmax_f(c, 0.);
         const double pd = fmax_f(d, 0.), pe = fmax_f(e, 0.), pf = fmax_f(f, 0.);
@@ -176,6 +176,10 @@ struct FastArith {
     }
 #endif
 
+    // 1/x for the Jiang-Shu weights: MUFU seed (upper 32 bits of x: relative error <~ 2^-20) + ONE Newton step ->
+    // relative error <~ 1e-12.  The weights multiply third differences, so the one-sided derivatives move by
+    // < 1e-12 * |WENO correction| (< 2e-13 even at a kink); a phi update is h times that.  LSF_RCP_NEWTON2 restores
+    // the second step (round 1).
     static LSF_HD double rcp(double x)
     {
 #if defined(__CUDA_ARCH__)
@@ -183,28 +187,34 @@ struct FastArith {
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
         double e = fma(-x, r, 1.0);
         r = fma(r, e, r);
+#if defined(LSF_RCP_NEWTON2)
         e = fma(-x, r, 1.0);
         r = fma(r, e, r);
+#endif
         return r;
 #else
         return 1.0 / x;
 #endif
     }
 
-    // Jiang-Shu weights from E_k = eps + IS_k:  out 2*w0 and (w2 - 1/2)
-    static LSF_HD void weights(double E0, double E1, double E2, double &w0x2, double &w2mh)
+    // One side of one direction.  E_k = (eps + IS_k)/3 (a common factor cancels in the weights).  With q_k = E_k^2,
+    // n0 = q1 q2, x = q0 q2, P = q0 q1 and D = n0 + 6 x + 3 P the Jiang-Shu weights are w0 = n0/D, w2 = 3P/D, and the
+    // WENO correction  2 w0 A + (w2 - 1/2) s  equals  r (2 n0 A + 3 P s) - s/2,  r = 1/D.  Returns r*(n0*A4 + P*s6),
+    // i.e. TWICE the correction plus s (A4 = 4A, s6 = 6s): the caller adds it to cen -/+ s.
+    static LSF_HD double side(double E0, double E1, double E2, double A4, double s6)
     {
         const double q0 = E0 * E0, q1 = E1 * E1, q2 = E2 * E2;
-        const double n0 = q1 * q2, x = q0 * q2, y3 = 3.0 * (q0 * q1);
-        const double D = fma(6.0, x, y3 + n0);
-        const double r = rcp(D);
-        w0x2 = (n0 + n0) * r;
-        w2mh = fma(y3, r, -0.5);
+        const double n0 = q1 * q2, x = q0 * q2, P = q0 * q1;
+        const double D = fma(6.0, x, fma(3.0, P, n0));
+        return rcp(D) * fma(n0, A4, P * s6);
     }
 
+    // dminus / dplus are returned UNSCALED: 12 dx times the one-sided derivatives (godunov applies 1/(12 dx) once,
+    // to |grad phi|, instead of six times here)
     template <bool YQ>
     static LSF_HD void weno_dir(const double v[7], const CellConst &cc, double &dminus, double &dplus)
     {
+        (void)cc;
         const double e0 = v[1] - v[0], e1 = v[2] - v[1], e2 = v[3] - v[2];
         const double e3 = v[4] - v[3], e4 = v[5] - v[4], e5 = v[6] - v[5];
         const double am = e1 - e0, bm = e2 - e1, c = e3 - e2, bp = e4 - e3, ap = e5 - e4;
@@ -220,36 +230,34 @@ struct FastArith {
         const double mp = YQ ? mc : max_nn(mc, dabs(e5));
         const double mm = max_nn(mc, dabs(e0));
 #endif
-        const double tiny = 1.0e-60;
-        const double epsp = fma(1.0e-6 * mp, mp, tiny);
-        const double epsm = fma(1.0e-6 * mm, mm, tiny);
-        const double s13b = (13.0 * tpb) * tpb, s13c = (13.0 * tmc) * tmc;
+        // everything below is (eps + IS)/3: eps/3 = (1e-6/3) max e^2 + tiny, IS/3 = (13/3) u^2 + v^2
+        constexpr double k13 = 13.0 / 3.0, keps = 1.0e-6 / 3.0, tiny = 1.0e-60;
+        const double epsp = fma(keps * mp, mp, tiny);
+        const double epsm = fma(keps * mm, mm, tiny);
+        const double s13b = (k13 * tpb) * tpb, s13c = (k13 * tmc) * tmc;
         double t;
-        // E_k = eps + IS_k, the eps folded into the FMA chains
-        t = fma(-3.0, bp, ap); const double E0p = fma(13.0 * tpa, tpa, fma(3.0 * t, t, epsp));
-        t = bp + c;            const double E1p = fma(3.0 * t, t, s13b + epsp);
-        t = fma(3.0, c, -bm);  const double E2p = fma(3.0 * t, t, s13c + epsp);
-        t = fma(-3.0, bm, am); const double E0m = fma(13.0 * tma, tma, fma(3.0 * t, t, epsm));
-        t = bm + c;            const double E1m = fma(3.0 * t, t, s13c + epsm);
-        t = fma(3.0, c, -bp);  const double E2m = fma(3.0 * t, t, s13b + epsm);
-        double w0p2, w2ph, w0m2, w2mh;
-        weights(E0p, E1p, E2p, w0p2, w2ph);
-        weights(E0m, E1m, E2m, w0m2, w2mh);
-        const double s = tpb - tmc;
-        const double Yp = fma(w0p2, tpa - tpb, w2ph * s);
-        const double Ym = fma(w0m2, tma + tmc, w2mh * s);
+        t = fma(-3.0, bp, ap); const double E0p = fma(k13 * tpa, tpa, fma(t, t, epsp));
+        t = bp + c;            const double E1p = fma(t, t, s13b + epsp);
+        t = fma(3.0, c, -bm);  const double E2p = fma(t, t, s13c + epsp);
+        t = fma(-3.0, bm, am); const double E0m = fma(k13 * tma, tma, fma(t, t, epsm));
+        t = bm + c;            const double E1m = fma(t, t, s13c + epsm);
+        t = fma(3.0, c, -bp);  const double E2m = fma(t, t, s13b + epsm);
+        const double s = tpb - tmc, s6 = 6.0 * s;
         const double cen = fma(7.0, e2 + e3, -(e1 + e4));
-        dminus = cc.k12 * fma(-2.0, Ym, cen);
-        dplus = cc.k12 * fma(2.0, Yp, cen);
+        dplus = (cen - s) + side(E0p, E1p, E2p, 4.0 * (tpa - tpb), s6);
+        dminus = (cen + s) - side(E0m, E1m, E2m, 4.0 * (tma + tmc), s6);
     }
 
     static LSF_HD void lo_dir(double vm, double vc, double vp, const CellConst &cc, double &dminus, double &dplus)
     {
-        dminus = (vc - vm) * cc.inv_dx;
-        dplus = (vp - vc) * cc.inv_dx;
+        (void)cc;
+        dminus = 12.0 * (vc - vm);          // unscaled like weno_dir: 12 dx times the difference quotient
+        dplus = 12.0 * (vp - vc);
     }
 
-    static LSF_HD double godunov(double phic, double a, double b, double c, double d, double e, double f, double g[3])
+    // a..f: 12 dx times the one-sided derivatives.  g[] receives the reference's gradX/Y/Z (squared upwind terms),
+    // the return value is gM = sqrt(gradX+gradY+gradZ) (subs.f90:702)
+    static LSF_HD double godunov(double phic, double a, double b, double c, double d, double e, double f, double g[3], const CellConst &cc)
     {
         // upwind pair per axis: phi>0 -> (max(a,0), min(b,0)) else (max(b,0), min(a,0))
         const bool pos = phic > 0.;
@@ -259,10 +267,10 @@ struct FastArith {
         const double x1 = pos_part(ax), x2 = neg_part(bx);
         const double y1 = pos_part(ay), y2 = neg_part(by);
         const double z1 = pos_part(az), z2 = neg_part(bz);
-        g[0] = max_nn(x1 * x1, x2 * x2);
-        g[1] = max_nn(y1 * y1, y2 * y2);
-        g[2] = max_nn(z1 * z1, z2 * z2);
-        return sqrt(g[0] + g[1] + g[2]);
+        const double u0 = max_nn(x1 * x1, x2 * x2), u1 = max_nn(y1 * y1, y2 * y2), u2 = max_nn(z1 * z1, z2 * z2);
+        const double k2 = cc.k12 * cc.k12;
+        g[0] = k2 * u0; g[1] = k2 * u1; g[2] = k2 * u2;      // only stored by the WG plane kernel; dead code elsewhere
+        return cc.k12 * sqrt((u0 + u1) + u2);
     }
 
     // `sens` flags an ill-conditioned update: d(sgn (1-gM))/d(gM) contains  k1 * dx^2 / (2 D)  with
@@ -356,7 +364,7 @@ struct F32Arith {
         dplus = (vp - vc) * cc.inv_dx;
     }
 
-    static LSF_HD float godunov(float phic, float a, float b, float c, float d, float e, float f, float g[3])
+    static LSF_HD float godunov(float phic, float a, float b, float c, float d, float e, float f, float g[3], const CellConstT<float> &)
     {
         const bool pos = phic > 0.f;
         const float x1 = fmaxf(pos ? a : b, 0.f), x2 = fminf(pos ? b : a, 0.f);
@@ -396,7 +404,7 @@ LSF_HD typename AR::real reinit_cell(const typename AR::real vx[7], const typena
         AR::lo_dir(vy[2], vy[3], vy[4], cc, c, d);
         AR::lo_dir(vz[2], vz[3], vz[4], cc, e, f);
     }
-    gM = AR::godunov(vx[3], a, b, c, d, e, f, g);
+    gM = AR::godunov(vx[3], a, b, c, d, e, f, g, cc);
     return AR::update(vx[3], phiS, gM, cc, sens);
 }
 

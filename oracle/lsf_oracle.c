@@ -9,13 +9,16 @@
  * can check / time the reference algorithm; the product (levelsetfortran_b200/)
  * never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests or golden vectors and no
- * Fortran compiler exists in the build container, so this restatement could
- * not be checked against the gfortran binary.  It is pinned instead against
- * (a) the known-answer values in SURVEY.md section 6 (an independent
- * IEEE-faithful transcription made at survey time) and (b) internal
- * consistency checks (literal BC loop vs closed form, lexicographic vs
- * hyperplane sweep order).  See tests/test_oracle_pins.py.
+ * PARITY PINNED TO THE REFERENCE'S SOURCE TEXT (round 2): no Fortran compiler exists in the build
+ * container, so the reference's two files are machine-translated to C statement by statement
+ * (oracle/f90_to_c.py -> oracle/_ref/libref.so) and that translation -- the reference program
+ * itself, run on its own cube40.stl / twoCube10.stl -- is compared with this restatement bit for
+ * bit at every stage (stlRead, grid set-up, sign search, 2155 reinit sweeps, 406 min/max
+ * iterations, node projection, reinit #2, NaN STOP at n = 272): tests/golden/make_golden.py
+ * (verdicts in tests/golden/REF_PIN_REPORT.txt) and tests/test_ref_pins.py.  The golden fixtures
+ * are generated from libref.so.  What remains unverified is the translator's reading of gfortran's
+ * arithmetic (documented in f90_to_c.py), not this file.  Earlier pins stay: the known-answer
+ * values of SURVEY.md section 6 and the internal consistency checks (tests/test_oracle_pins.py).
  *
  * Arithmetic contract (mirrors `gfortran -O3 -fdefault-real-8` on x86-64,
  * reference Makefile:4): every REAL and real literal is IEEE binary64, no FMA

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py -- never by the product
-package `levelsetfortran_b200`.  PARITY UNPINNED (see lsf_oracle.c header).
+package `levelsetfortran_b200`.  Pinned bit for bit to the machine-translated reference (oracle/ref.py,
+see lsf_oracle.c header).
 
 All grid arrays are numpy float64/int32 in Fortran order with shape
 (nx+1, ny+1, nz+1), i.e. the reference's phi(0:nx,0:ny,0:nz).
