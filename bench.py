@@ -14,7 +14,14 @@ field fed to reinit is produced by the library's own sign search from the synthe
           H2D + 8 sweeps + D2H inside the timed region)
   roofline : the sweep kernel's algorithmic HBM bytes (24 B per cell update: read phi, read the
           frozen sign source, write phi) / its mean launch time, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the serial C restatement of the reference (oracle/) on a bounded slab sample
+  cpu_baseline : the reference itself -- subs.f90 `reinit`, machine-translated to C (oracle/_ref/libref.so, built where
+          /root/reference exists and shipped prebuilt; kind "reference") -- on a bounded slab sample of the same
+          workload, one host core (the reference is serial); falls back to the hand-written C port (kind "port")
+  parity : (a) the timed 8 sweeps repeated in EXACT arithmetic on a second 1024^3 grid: max|FAST - EXACT|; (b) the CPU
+          sample slab swept by the GPU as a grid of its own: max|GPU - reference|, EXACT bit-identical
+  strong : BASELINE config 4 -- ONE 1024^3 grid, reinit (8 sweeps) + 64 min/max iterations, cut into N z-slabs --
+          with a partition-independent digest of phi after each stage (equal for N = 1, 2, 4, 8 <=> bit-identical)
+  config3 : BASELINE config 3 -- 20k-triangle sphere on 512^3, reinit-only (N = 1)
 
 One JSON line is printed by rank 0.
 """
@@ -66,32 +73,69 @@ def analytic_sign_field(shape, dx=DX):
     return np.asfortranarray(d / np.sqrt(d * d + dx * dx))
 
 
-def cpu_sample(nxy, nzs, sweeps):
-    """Times the oracle (serial C restatement of subs.f90:717-931) on an nxy x nxy x nzs slab cut
-    through the torus of the same synthetic geometry.  Returns (Gcell-updates/s, description)."""
-    from oracle import oracle as O
-    O.build()
-    full = (nxy, nxy, max(nzs, 64))
-    # the torus sits at the low-z end of the bbox: take the slab around its mid-plane
+def slab_field(nxy, nzs):
+    """Smeared sign field on an nxy x nxy x nzs slab cut through the torus of the bench geometry (analytic, + - * / sqrt
+    only: reproducible bit for bit).  Returns (phi, h)."""
     r_cells = int(0.12 * (nxy - 22.2))
-    k0 = max(0, 10 + r_cells - nzs // 2)
-    shape = (nxy, nxy, nzs)
-    nxp, nyp, nzp = full
-    ex = (nxp - 22.2) * DX
-    s = ex
-    r = 0.12 * s
-    R = 0.5 * s - r
-    x = (np.arange(nxp) * DX - 10 * DX - 0.5 * ex)[:, None, None]
-    y = (np.arange(nyp) * DX - 10 * DX - 0.5 * ex)[None, :, None]
+    k0 = max(0, 10 + r_cells - nzs // 2)                      # the torus sits at the low-z end of the bbox
+    ex = (nxy - 22.2) * DX
+    r = 0.12 * ex
+    R = 0.5 * ex - r
+    x = (np.arange(nxy) * DX - 10 * DX - 0.5 * ex)[:, None, None]
+    y = (np.arange(nxy) * DX - 10 * DX - 0.5 * ex)[None, :, None]
     z = ((np.arange(nzs) + k0) * DX - 10 * DX - r)[None, None, :]
     d = np.sqrt((np.sqrt(x * x + y * y) - R) ** 2 + z ** 2) - r
     phi = np.asfortranarray(d / np.sqrt(d * d + DX * DX))
-    dxx = DX / (np.sqrt(3.0) * ex)
+    return phi, 0.1 * (DX / (np.sqrt(3.0) * ex))
+
+
+def cpu_sample(nxy, nzs, sweeps, keep=False):
+    """Times the reference's reinit (subs.f90:717-931) on the slab: libref.so (the reference's own text, machine-translated)
+    when it is there, else the hand-written port.  Returns (Gcell-updates/s, description, kind, phi_in, phi_out)."""
+    phi, h = slab_field(nxy, nzs)
+    phi_in = phi.copy(order="F") if keep else None
+    kind = "port"
+    try:
+        from oracle import ref as R
+        if R.available():
+            R.lib()
+            kind = "reference"
+    except Exception:
+        kind = "port"
     t0 = time.perf_counter()
-    O.reinit(phi, sweeps - 1, DX, 0.1 * dxx, tol=0.0)
+    if kind == "reference":
+        R.reinit(phi, sweeps - 1, DX, h)
+    else:
+        from oracle import oracle as O
+        O.build()
+        O.reinit(phi, sweeps - 1, DX, h, tol=0.0)
     dt = time.perf_counter() - t0
+    shape = phi.shape
     cells = (shape[0] - 2) * (shape[1] - 2) * (shape[2] - 2) * sweeps
-    return cells / dt / 1e9, f"{sweeps} sweep(s) on a {shape[0]}x{shape[1]}x{shape[2]} slab through the torus, {dt:.1f} s"
+    what = ("subs.f90 reinit machine-translated to C (oracle/_ref/libref.so: literal BC block, RMS pass, gradPhi stores)"
+            if kind == "reference" else "hand-written C port of the reference (oracle/lsf_oracle.c)")
+    return (cells / dt / 1e9, f"{sweeps} sweep(s) on a {shape[0]}x{shape[1]}x{shape[2]} slab through the torus, {dt:.1f} s, 1 core; {what}",
+            kind, phi_in, phi if keep else None)
+
+
+def dev_tensor(ptr, n, dtype="f8"):
+    """torch view of n elements of device memory at ptr (no copy)."""
+    import torch
+
+    class _A:
+        pass
+    a = _A()
+    a.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<" + dtype, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(a, device="cuda")
+
+
+def dev_max_abs_diff(pa, pb, n, chunk=1 << 27):
+    import torch
+    m = 0.0
+    for o in range(0, n, chunk):
+        k = min(chunk, n - o)
+        m = max(m, float((dev_tensor(pa + 8 * o, k) - dev_tensor(pb + 8 * o, k)).abs().max()))
+    return m
 
 
 class ClockSampler:
@@ -153,6 +197,14 @@ def ncu_traffic(grid, f32=False):
 
 
 # ----------------------------------------------------------------------------------- reference arm
+def workload_config(n, world, f32, ntri=None):
+    """The `config` object -- identical for this repo's arm and the reference arm."""
+    return {"workload": f"BASELINE config {'4' if world == 1 else '5'}: synthetic torus+cube STL on ONE {n}x{n}x{n * world} "
+                        f"{'fp32-mode' if f32 else 'fp64'} grid ({n}^3 points per GPU), reinit-only, one step = {SWEEPS_PER_STEP} "
+                        "Gauss-Seidel raster sweeps (+BC+RMS each)",
+            "global_grid": [n, n, n * world], "grid_per_gpu": [n, n, n], "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -160,21 +212,21 @@ def run_reference(args):
     nxy = args.grid
     nzs = args.ref_slab
     rates = []
-    desc = ""
+    desc, kind = "", "port"
     for q in range(args.warmup + args.steps):
-        v, desc = cpu_sample(nxy, nzs, 1)
+        v, desc, kind, _, _ = cpu_sample(nxy, nzs, 1)
         if q >= args.warmup:
             rates.append(v)
     value = float(np.mean(rates)) if rates else 0.0
     cells = (nxy - 2) * (nxy - 2) * (nzs - 2)
+    cfg = workload_config(nxy, max(args.gpus, 1), False)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cells / value / 1e6 if value else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"torus+cube sign field, {nxy}^3-class grid, reinit-only; each step = 1 GS sweep + BC + RMS "
-                                   f"on a {nxy}x{nxy}x{nzs} slab sample", "grid_per_gpu": [nxy, nxy, nxy]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": desc + " per step; serial C restatement of the serial reference (no Fortran "
-                                              "compiler in the image, reference cannot be built)"},
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": desc + f" per step: each step of this arm is ONE sweep (+BC+RMS) on that slab sample of the "
+                                              f"{nxy}^3 grid (the serial reference needs ~15 min per full 1024^3 sweep)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -258,29 +310,97 @@ def run_gpu(args):
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop()
+    main_arith = "exact" if L.lsf_last_arith() == _lib.ARITH_EXACT else "fast"
 
-    # ---- companion measurements on the same resident grid (not part of `value`): min/max flow ----
-    mm = None
+    # ---- BASELINE config 4 as a fixed protocol (not part of `value`): ONE n^3 grid, sign search -> 8 sweeps -> 64 min/max
+    # iterations, with a partition-independent digest of phi after each stage.  N = 1: the bench grid itself; N > 1: a
+    # second, strong-scaling grid cut into N z-slabs.  Equal digests for N = 1, 2, 4, 8 <=> the sharded results are
+    # bit-identical to the single-GPU one.  The EXACT-arithmetic repeat of the 8 sweeps gives the FAST-vs-EXACT parity
+    # number at full size (N = 1).
+    def allreduce_digest(d):
+        if dist is None:
+            return d
+        t = torch.tensor([d[0] - (1 << 64) if d[0] >= (1 << 63) else d[0]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)                     # int64 addition wraps like the uint64 sum
+        xs = [None] * world
+        dist.all_gather_object(xs, d[1])
+        x = 0
+        for v in xs:
+            x ^= v
+        return int(t.item()) & ((1 << 64) - 1), x
+
+    def hexd(d):
+        return "%016x:%016x" % d
+
+    mm = strong = parity = None
     if args.minmax_iters > 0 and not f32:
-        rc, n_mm, hist_mm = G.minMaxFlow(3, DX, 0.01 * g["dxx"], tol=0.0)          # warm-up
-        barrier()
-        rc, n_mm, hist_mm = G.minMaxFlow(args.minmax_iters, DX, 0.01 * g["dxx"], tol=0.0)
-        mm_ms, mm_launches = _lib.last_timing()
-        npts_all = (nx + 1) * (ny + 1) * (nz + 1)
-        mm_rate = npts_all * n_mm / (mm_ms * 1e-3) / 1e9
+        if world == 1:
+            SG, sg, sX, sE = G, g, surfX, surfElem
+        else:
+            stris = stl.torus_cube_config((n, n, n), DX)
+            sX, sE = stl.dedup_nodes(stris)
+            sg = stl.grid_from_surface(sX, DX)
+            SG = ShardedGrid(sg["nx"], sg["ny"], sg["nz"])
+        sh, sh1 = 0.1 * sg["dxx"], 0.01 * sg["dxx"]
+        scells = (sg["nx"] - 1) * (sg["ny"] - 1) * (sg["nz"] - 1) * SWEEPS_PER_STEP
+        spts = (sg["nx"] + 1) * (sg["ny"] + 1) * (sg["nz"] + 1)
+        for rep in range(2):                                             # the first pass warms up (allocations, order tables)
+            SG.fill(1.0)
+            SG.signSearch(sg["xLo"], DX, sX, sE, sg["box"])
+            barrier()
+            rc, ne, shist = SG.reinit(SWEEPS_PER_STEP - 1, DX, sh, tol=0.0)
+            s_ms, _ = _lib.last_timing()
+            s_arith = "exact" if L.lsf_last_arith() == _lib.ARITH_EXACT else "fast"
+            d_re = allreduce_digest(SG.checksum())
+            barrier()
+            rc2, n_mm, hist_mm = SG.minMaxFlow(args.minmax_iters, DX, sh1, tol=0.0)
+            mm_ms, mm_launches = _lib.last_timing()
+            d_mm = allreduce_digest(SG.checksum())
         active = int(L.lsf_last_minmax_active())
-        # active-list algorithm: an iteration visits only the cells that can still change (the narrow band); per
-        # visited cell it moves the list entry (8 B), the old value (8 B) and the new value (8 B) through HBM,
-        # the stencil neighbours are list neighbours and come from L1/L2
-        mm_bytes = 24.0 * active * n_mm / (mm_ms * 1e-3) / 1e9
+        tt = torch.tensor([s_ms, mm_ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        s_ms, mm_ms = (float(v) for v in tt.cpu())
+        strong = {"workload": f"BASELINE config 4: torus+cube STL on ONE {n}^3 fp64 grid cut into {world} z-slab(s): sign search, "
+                              f"{SWEEPS_PER_STEP} reinit sweeps, {n_mm} min/max iterations", "scaling": "strong", "n_gpus": world,
+                  "reinit_ms": s_ms, "value": scells / (s_ms * 1e-3) / 1e9, "unit": UNIT, "arith_used": s_arith,
+                  "minmax_ms": mm_ms, "minmax_iterations": n_mm,
+                  "digest_after_reinit": hexd(d_re), "digest_after_minmax": hexd(d_mm),
+                  "rms_reinit": [float(v) for v in shist], "rms_minmax_last": float(hist_mm[-1]) if len(hist_mm) else None,
+                  "digest": "sum over the points of bits(phi)*(2q+1) mod 2^64 : xor of bits(phi), q = global linear index "
+                            "(lsf_grid_checksum); identical across N <=> bit-identical fields"}
+        mm_rate = spts * n_mm / (mm_ms * 1e-3) / 1e9
         mm = {"metric": "min/max flow Gpoint-iterations/s (all grid points per iteration)", "value": mm_rate,
               "iterations": n_mm, "ms_per_iteration": mm_ms / max(n_mm, 1), "launches": mm_launches,
-              "active_cells_rank0": active, "active_fraction": active * world / npts_all,
+              "active_cells_rank0": active, "active_fraction": active * world / spts,
+              "bound": "launch/latency: the active-list algorithm touches only the narrow band (the cells that can still change, "
+                       "%.2f %% of the grid), 3 launches per iteration; counted over all grid points (SURVEY 8d) that is %.0fx the "
+                       "dense 16 B/point HBM roof, which therefore says nothing about this kernel"
+                       % (100.0 * active * world / spts, 16.0 * mm_rate / measured_peak()[0]),
               "note": "ms_per_iteration includes building the active list once per call",
-              "roofline": {"bound": "hbm", "bytes_per_active_cell": 24.0, "achieved": mm_bytes,
-                           "peak": measured_peak()[0], "unit": "GB/s", "frac": mm_bytes / measured_peak()[0],
-                           "dense_equivalent_GBs": 16.0 * mm_rate},
               "last_rms": float(hist_mm[-1]) if len(hist_mm) else None}
+        if world == 1:
+            # FAST (as timed) vs EXACT on the full grid: the same sign field, the same 8 sweeps, a second grid
+            G2 = DeviceGrid(nx, ny, nz)
+            G2.fill(1.0)
+            G2.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
+            _lib.check(L.lsf_set_arith(_lib.ARITH_EXACT))
+            rcx, nex, histx = G2.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)
+            x_ms, _ = _lib.last_timing()
+            _lib.check(L.lsf_set_arith({"exact": _lib.ARITH_EXACT, "fast": _lib.ARITH_FAST, "auto": _lib.ARITH_AUTO}[args.arith]))
+            G.fill(1.0)                                               # G: back to the state after the 8 FAST sweeps
+            G.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
+            rcf, nef, histf = G.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)
+            npts_all = (nx + 1) * (ny + 1) * (nz + 1)
+            parity = {"full_grid": {"what": f"{SWEEPS_PER_STEP} sweeps from the sign field on the {n}^3 bench grid: arith '{s_arith}' (as timed) vs "
+                                            "EXACT (bit-identical to the reference at every size tested against it)",
+                                    "max_abs_fast_vs_exact": dev_max_abs_diff(G.device_ptr(), G2.device_ptr(), npts_all),
+                                    "n_exit_equal": bool(nef == nex), "tolerance": 1e-10,
+                                    "rms_hist_max_rel_diff": float(np.max(np.abs(histf - histx) / np.abs(histx))),
+                                    "exact_ms_per_sweep": x_ms / SWEEPS_PER_STEP}}
+            G2.close()
+        if world > 1:
+            SG.close()
 
     # ---- companion: surface-node projection (set3d.f90:465-501) of the STL's own nodes on the resident field ----
     nodes = None
@@ -293,6 +413,56 @@ def run_gpu(args):
                      "reference_cost": "O(moves x nodes) trilinear interpolations: %.3g" % (float(n_moves) * len(surfX))}
         except Exception as e:      # e.g. a band point too close to the boundary: reported, not fatal for the bench line
             nodes = {"error": str(e)[:200]}
+
+    # ---- parity (b): the CPU sample slab swept by the GPU as a grid of its own, against the reference's result ----
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        v, desc, kind, slab_in, slab_ref = cpu_sample(n, args.ref_slab, 1, keep=(not f32))
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "sample": desc}
+        if not f32:
+            Gs = DeviceGrid(slab_in.shape[0] - 1, slab_in.shape[1] - 1, slab_in.shape[2] - 1)
+            _, hs = slab_field(n, args.ref_slab)
+            out = {}
+            for name, mode in (("exact", _lib.ARITH_EXACT), ("fast", _lib.ARITH_FAST)):
+                _lib.check(L.lsf_set_arith(mode))
+                Gs.upload(slab_in)
+                Gs.reinit(0, DX, hs, tol=0.0)
+                out[name] = float(np.abs(Gs.download() - slab_ref).max())
+            _lib.check(L.lsf_set_arith({"exact": _lib.ARITH_EXACT, "fast": _lib.ARITH_FAST, "auto": _lib.ARITH_AUTO}[args.arith]))
+            Gs.close()
+            parity = parity or {}
+            parity["cpu_sample_slab"] = {"what": f"one sweep (+BC) of the {slab_in.shape[0]}x{slab_in.shape[1]}x{slab_in.shape[2]} slab the "
+                                                 f"cpu_baseline leg timed, GPU vs that leg's own result (kind '{kind}')",
+                                         "max_abs_exact_vs_reference": out["exact"], "max_abs_fast_vs_reference": out["fast"],
+                                         "bit_identical_exact": out["exact"] == 0.0, "tolerance": 1e-10}
+        del slab_in, slab_ref
+
+    # ---- companion: BASELINE config 3 -- 20k-triangle sphere on 512^3, reinit-only (single GPU) ----
+    config3 = None
+    if world == 1 and not f32 and not args.no_config3:
+        tr3 = stl.sphere_config(512, DX)
+        X3, E3 = stl.dedup_nodes(tr3)
+        g3 = stl.grid_from_surface(X3, DX)
+        G3 = DeviceGrid(g3["nx"], g3["ny"], g3["nz"])
+        G3.fill(1.0)
+        G3.signSearch(g3["xLo"], DX, X3, E3, g3["box"])
+        sign3_ms, _ = _lib.last_timing()
+        h3 = 0.1 * g3["dxx"]
+        for _ in range(3):
+            G3.reinit(SWEEPS_PER_STEP - 1, DX, h3, tol=0.0)
+        barrier()
+        ms3 = 0.0
+        k3 = 5
+        for _ in range(k3):
+            rc3, ne3, hist3 = G3.reinit(SWEEPS_PER_STEP - 1, DX, h3, tol=0.0)
+            ms, _nl = _lib.last_timing()
+            ms3 += ms
+        G3.close()
+        c3 = (g3["nx"] - 1) * (g3["ny"] - 1) * (g3["nz"] - 1) * SWEEPS_PER_STEP
+        config3 = {"workload": f"BASELINE config 3: synthetic sphere STL ({len(E3)} triangles) on a {g3['nx'] + 1}x{g3['ny'] + 1}x{g3['nz'] + 1} fp64 grid, "
+                               "reinit-only (min/max iterations = 0), 1 B200", "value": c3 * k3 / (ms3 * 1e-3) / 1e9, "unit": UNIT,
+                   "ms_per_step": ms3 / k3, "steps": k3, "sign_search_ms": sign3_ms, "last_rms": float(hist3[-1]),
+                   "roofline_frac": 24.0 * c3 * k3 / (ms3 * 1e-3) / 1e9 / measured_peak()[0]}
 
     # ---- companion: the optional fp32 mode on the same geometry (single GPU; not part of `value`) ----
     fp32 = None
@@ -354,6 +524,28 @@ def run_gpu(args):
         barrier()
         e2e_s = (time.perf_counter() - t0) / k_e2e
         e2e = {"e2e_s": e2e_s, "bytes": npts * 8}
+        # the same call as the reference's Fortran driver would make it through fortran/lsf_b200_mod.f90: ALLOCATEd
+        # (pageable) arrays; (i) reinit_nograd_b200 -- phi only; (ii) reinit_b200 with the reference's full argument
+        # list -- gradPhi(0:nx,0:ny,0:nz,3) and gradPhiMag shipped both ways (dead downstream, set3d.f90:372-375)
+        if world == 1 and not f32 and not args.no_e2e_pageable:
+            try:
+                pg = np.empty(npts)                                 # pageable
+                pg[:] = host.numpy()
+                t0 = time.perf_counter()
+                _lib.check(L.lsf_reinit(pg.ctypes.data_as(_lib.c_double_p), None, None, nx, ny, nz, SWEEPS_PER_STEP - 1, DX, h,
+                                        C.byref(n_exit), hist_buf.ctypes.data_as(_lib.c_double_p)))
+                e2e["pageable_nograd_s"] = time.perf_counter() - t0
+                gp = np.zeros(3 * npts)
+                gm = np.zeros(npts)
+                pg[:] = host.numpy()
+                t0 = time.perf_counter()
+                _lib.check(L.lsf_reinit(pg.ctypes.data_as(_lib.c_double_p), gp.ctypes.data_as(_lib.c_double_p),
+                                        gm.ctypes.data_as(_lib.c_double_p), nx, ny, nz, SWEEPS_PER_STEP - 1, DX, h,
+                                        C.byref(n_exit), hist_buf.ctypes.data_as(_lib.c_double_p)))
+                e2e["pageable_grad_s"] = time.perf_counter() - t0
+                del pg, gp, gm
+            except (MemoryError, _lib.LsfError) as ex:
+                e2e["pageable_error"] = str(ex)[:200]
         if world > 1:
             G.close()
     else:
@@ -371,27 +563,36 @@ def run_gpu(args):
         launch_ms = sweep_ms / max(n_sweeps, 1)
         cells_per_launch = (nx - 1) * (ny - 1) * k_upd          # rank 0's sweep kernel
         achieved = bytes_per_update * cells_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
-        cpu = None
-        if not args.no_cpu:
-            v, desc = cpu_sample(n, args.ref_slab, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": desc + "; serial C restatement of the serial reference (reference itself is Fortran, no "
-                                    "compiler in the image)"}
+        cfg = workload_config(n, world, f32)
+        cfg.update({"triangles": int(len(surfElem)), "h": h,
+                    "overlapped_sweeps": bool(args.overlap), "arith": args.arith,
+                    "arith_used": main_arith, "sched": args.sched,
+                    "parallelism": "single GPU" if world == 1 else
+                    f"{world} z-slabs, Gauss-Seidel pipeline along k: streaming halo + ghost-plane exchange + RMS reduction "
+                    "as peer stores over NVLink from inside the kernels (bit-identical to 1 GPU: see strong.digest_*)",
+                    "l2": "inputs larger than L2 (%.1f GB per field)" % (8e-9 * n ** 3),
+                    "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
+                    "last_rms": float(hist[-1]) if hist is not None else None})
+        e2e_line = None
+        if e2e:
+            e2e_line = {"value": cells_per_step / e2e_s_max / 1e9, "unit": UNIT,
+                        "h2d_bytes_per_step": e2e["bytes"] * world, "d2h_bytes_per_step": e2e["bytes"] * world,
+                        "api": "lsf_reinit(phi, NULL, NULL, ...) from page-locked host memory (lsf_host_register / reinit_nograd_b200)"
+                               if world == 1 else "lsf_grid_upload + lsf_grid_reinit + lsf_grid_download on each rank's slab"}
+            if "pageable_nograd_s" in e2e:
+                e2e_line["as_fortran_driver"] = {
+                    "pageable_phi_only": {"value": cells_per_step / e2e["pageable_nograd_s"] / 1e9, "s": e2e["pageable_nograd_s"],
+                                          "api": "reinit_nograd_b200: ALLOCATEd (pageable) phi, no gradPhi"},
+                    "pageable_full_argument_list": {"value": cells_per_step / e2e["pageable_grad_s"] / 1e9, "s": e2e["pageable_grad_s"],
+                                                    "h2d_bytes": e2e["bytes"] * 5, "d2h_bytes": e2e["bytes"] * 5,
+                                                    "api": "reinit_b200(phi,gradPhi,gradPhiMag,...): the reference's argument list, pageable "
+                                                           "arrays, gradPhi/gradPhiMag shipped both ways + last sweep replayed"}}
+            if "pageable_error" in e2e:
+                e2e_line["as_fortran_driver"] = {"error": e2e["pageable_error"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if f32 else "f64", "data": "synthetic",
-                "config": {"workload": f"BASELINE config {'4' if world == 1 else '5'}: synthetic torus+cube STL ({len(surfElem)} triangles) on "
-                                       f"ONE {n}x{n}x{n * world} {'fp32-mode' if f32 else 'fp64'} grid ({n}^3 points per GPU), reinit-only, one step = "
-                                       f"{SWEEPS_PER_STEP} Gauss-Seidel raster sweeps (+BC+RMS each)",
-                           "global_grid": [n, n, n * world],
-                           "grid_per_gpu": list(shape_pts), "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX, "h": h,
-                           "overlapped_sweeps": bool(args.overlap), "arith": args.arith, "arith_used": "exact" if L.lsf_last_arith() == _lib.ARITH_EXACT else "fast", "sched": args.sched,
-                           "parallelism": "single GPU" if world == 1 else
-                           f"{world} z-slabs, Gauss-Seidel pipeline along k: streaming halo + ghost-plane exchange + RMS reduction "
-                           "as peer stores over NVLink from inside the kernels (bit-identical to 1 GPU)",
-                           "l2": "inputs larger than L2 (%.1f GB per field)" % (8e-9 * n ** 3),
-                           "wall_ms_per_step": wall_ms_max / args.steps, "sign_search_ms": sign_ms, "setup_s": setup_s,
-                           "last_rms": float(hist[-1]) if hist is not None else None},
+                "config": cfg,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(n, f32),
                              "traffic_note": "DRAM read+write bytes of one launch of a whole %d^3 grid, ncu --set full (profiles/%s_%d_full.txt); "
@@ -405,10 +606,10 @@ def run_gpu(args):
                                                % (FP64_PER_UPDATE, FP64_PIPE_PEAK / 1e12),
                              "note": "fp64 WENO5 is FP64-pipe bound (SURVEY.md fact 4); see DESIGN.md"},
                 "cpu_baseline": cpu,
-                "e2e": ({"value": cells_per_step / e2e_s_max / 1e9, "unit": UNIT,
-                         "h2d_bytes_per_step": e2e["bytes"] * world, "d2h_bytes_per_step": e2e["bytes"] * world,
-                         "api": "lsf_reinit (host-buffer drop-in)" if world == 1 else
-                                "lsf_grid_upload + lsf_grid_reinit + lsf_grid_download on each rank's slab"} if e2e else None),
+                "e2e": e2e_line,
+                "parity": parity,
+                "strong": strong,
+                "config3": config3,
                 "minmax_flow": mm,
                 "fp32_mode": fp32,
                 "node_projection": nodes,
@@ -430,7 +631,10 @@ def main():
     ap.add_argument("--grid", type=int, default=1024, help="grid points per axis per GPU")
     ap.add_argument("--arith", default="auto", choices=["auto", "fast", "exact"])
     ap.add_argument("--sched", default="march", choices=["march", "plane"])
-    ap.add_argument("--ref-slab", type=int, default=64, help="z thickness of the CPU sample slab (64: ~18 s of serial CPU work per sweep)")
+    ap.add_argument("--ref-slab", type=int, default=16, help="z thickness of the CPU sample slab (16: ~10 s of serial CPU work per sweep "
+                                                             "of the machine-translated reference)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE config 3 companion (sphere, 512^3)")
+    ap.add_argument("--no-e2e-pageable", action="store_true", help="skip the pageable-memory / full-argument-list e2e variants")
     ap.add_argument("--minmax-iters", type=int, default=64, help="min/max iterations of the companion measurement (0 = skip)")
     ap.add_argument("--overlap", action="store_true", help="run the sweeps in overlapped batches (lsf_set_overlap; opt-in)")
     ap.add_argument("--no-e2e", action="store_true")

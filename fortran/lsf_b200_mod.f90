@@ -20,7 +20,8 @@
 !            -Wl,-rpath,<repo>/levelsetfortran_b200
 !
 ! NOTE: no Fortran compiler exists in the image this library was developed in; this file is kept
-! small and conservative (F2003 only) and has been reviewed but not compiled there.  The same C
+! small and conservative (F2003 only) and has been reviewed but not compiled there (its statements are restricted to the subset the
+! translator oracle/f90_to_c.py understands wherever that was possible).  The same C
 ! symbols are exercised by the ctypes mirror levelsetfortran_b200/set_subs.py in the test-suite.
 !*************************************************************************************!
 MODULE lsf_b200
@@ -31,7 +32,11 @@ PRIVATE
 
 PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched, lsf_set_minmax_algo, lsf_set_precision
 PUBLIC :: lsf_slab_range, lsf_sgrid_create, lsf_sgrid_create_f32, lsf_sgrid_ipc_handle, lsf_sgrid_attach, lsf_grid_destroy
-PUBLIC :: signSearch_b200, reinit_b200, narrowBand_b200, minMaxFlow_b200, advectNodes_b200
+PUBLIC :: lsf_sgrid_sync_ghosts, lsf_grid_create, lsf_grid_create_f32, lsf_grid_fill, lsf_grid_upload, lsf_grid_download
+PUBLIC :: lsf_grid_download_phiN, lsf_grid_sign_init, lsf_grid_reinit, lsf_grid_narrowband, lsf_grid_minmax
+PUBLIC :: lsf_grid_advect_nodes, lsf_grid_checksum, lsf_host_register, lsf_host_unregister
+PUBLIC :: signSearch_b200, reinit_b200, reinit_nograd_b200, narrowBand_b200, minMaxFlow_b200, advectNodes_b200
+PUBLIC :: gridReinit_b200, gridMinMaxFlow_b200
 PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT, LSF_ARITH_AUTO, LSF_PREC_F64, LSF_PREC_F32
 
 INTEGER(c_int), PARAMETER :: LSF_OK = 0, LSF_NAN = 1
@@ -119,6 +124,134 @@ INTERFACE
       INTEGER(c_int) :: rc
    END FUNCTION lsf_grid_destroy
 
+   FUNCTION lsf_sgrid_sync_ghosts(g) BIND(C, NAME='lsf_sgrid_sync_ghosts') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr), VALUE :: g
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_sgrid_sync_ghosts
+
+   ! ---- device-resident grids (whole grid: lsf_grid_create; z-slab: lsf_sgrid_create): the same calls drive both.
+   ! On a z-slab the host arrays hold the rank's OWNED planes k0..k1-1, i.e. phi(0:nx,0:ny,k0:k1-1). ----
+   FUNCTION lsf_grid_create(g,nx,ny,nz) BIND(C, NAME='lsf_grid_create') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr) :: g                        ! lsf_grid**
+      INTEGER(c_int), VALUE :: nx,ny,nz
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_create
+
+   FUNCTION lsf_grid_create_f32(g,nx,ny,nz) BIND(C, NAME='lsf_grid_create_f32') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr) :: g
+      INTEGER(c_int), VALUE :: nx,ny,nz
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_create_f32
+
+   FUNCTION lsf_grid_fill(g,value) BIND(C, NAME='lsf_grid_fill') RESULT(rc)       ! phi = value (set3d.f90:161)
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: g
+      REAL(c_double), VALUE :: value
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_fill
+
+   FUNCTION lsf_grid_upload(g,phi) BIND(C, NAME='lsf_grid_upload') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: g
+      REAL(c_double), INTENT(IN) :: phi(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_upload
+
+   FUNCTION lsf_grid_download(g,phi) BIND(C, NAME='lsf_grid_download') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: g
+      REAL(c_double) :: phi(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_download
+
+   FUNCTION lsf_grid_download_phiN(g,phiN) BIND(C, NAME='lsf_grid_download_phiN') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: g
+      REAL(c_double) :: phiN(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_download_phiN
+
+   FUNCTION lsf_grid_sign_init(g,xLo,dx,surfX,nSurfNode,surfElem,nSurfElem,im,ip,jm,jp,km,kp) &
+                               BIND(C, NAME='lsf_grid_sign_init') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double, c_int32_t
+      TYPE(c_ptr), VALUE :: g
+      REAL(c_double), INTENT(IN) :: xLo(3)
+      REAL(c_double), VALUE :: dx
+      REAL(c_double), INTENT(IN) :: surfX(*)
+      INTEGER(c_int), VALUE :: nSurfNode
+      INTEGER(c_int32_t), INTENT(IN) :: surfElem(*)
+      INTEGER(c_int), VALUE :: nSurfElem,im,ip,jm,jp,km,kp      ! GLOBAL sub-box (set3d.f90:180-186) on every rank
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_sign_init
+
+   FUNCTION lsf_grid_reinit(g,iter,dx,h,tol,n_exit,rms_hist) BIND(C, NAME='lsf_grid_reinit') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: g
+      INTEGER(c_int), VALUE :: iter
+      REAL(c_double), VALUE :: dx,h,tol        ! tol = 1.E-5 in the reference (subs.f90:915)
+      INTEGER(c_int) :: n_exit
+      REAL(c_double) :: rms_hist(*)            ! 0:iter
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_reinit
+
+   FUNCTION lsf_grid_narrowband(g,dx,phiNB,phiSB) BIND(C, NAME='lsf_grid_narrowband') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double, c_int32_t
+      TYPE(c_ptr), VALUE :: g
+      REAL(c_double), VALUE :: dx
+      INTEGER(c_int32_t) :: phiNB(*), phiSB(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_narrowband
+
+   FUNCTION lsf_grid_minmax(g,iter,dx,h1,tol,n_exit,rms_hist) BIND(C, NAME='lsf_grid_minmax') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: g
+      INTEGER(c_int), VALUE :: iter
+      REAL(c_double), VALUE :: dx,h1,tol       ! tol = 1.E-7 in the reference (set3d.f90:448)
+      INTEGER(c_int) :: n_exit
+      REAL(c_double) :: rms_hist(*)            ! 1:iter
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_minmax
+
+   FUNCTION lsf_grid_advect_nodes(g,xLo,dx,surfXX,nSurfNode,phiSurf,gradPhiSurf,iter,n_moves) &
+                                  BIND(C, NAME='lsf_grid_advect_nodes') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double, c_long_long
+      TYPE(c_ptr), VALUE :: g
+      REAL(c_double), INTENT(IN) :: xLo(3)
+      REAL(c_double), VALUE :: dx
+      REAL(c_double) :: surfXX(*), phiSurf(*), gradPhiSurf(*)
+      INTEGER(c_int), VALUE :: nSurfNode, iter
+      INTEGER(c_long_long) :: n_moves
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_advect_nodes
+
+   ! digest(1) = sum of bits(phi(q))*(2q+1) mod 2**64, digest(2) = xor of the bit patterns, over the OWNED points;
+   ! the ranks' digests add / xor up to the single-GPU digest (MPI_Allreduce with MPI_SUM on INTEGER(8) wraps the same way)
+   FUNCTION lsf_grid_checksum(g,digest) BIND(C, NAME='lsf_grid_checksum') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_int64_t
+      TYPE(c_ptr), VALUE :: g
+      INTEGER(c_int64_t) :: digest(2)
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_checksum
+
+   ! Page-lock a host array for the lifetime of its allocation: the host-buffer entry points (reinit_b200, ...) then
+   ! move it at PCIe speed instead of through the driver's pageable staging path.  Call right after ALLOCATE, and
+   ! lsf_host_unregister before DEALLOCATE.  nbytes = 8*SIZE(phi).
+   FUNCTION lsf_host_register(ptr,nbytes) BIND(C, NAME='lsf_host_register') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_size_t
+      TYPE(c_ptr), VALUE :: ptr
+      INTEGER(c_size_t), VALUE :: nbytes
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_host_register
+
+   FUNCTION lsf_host_unregister(ptr) BIND(C, NAME='lsf_host_unregister') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr), VALUE :: ptr
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_host_unregister
+
    FUNCTION lsf_last_error() BIND(C, NAME='lsf_last_error') RESULT(msg)
       IMPORT :: c_ptr
       TYPE(c_ptr) :: msg
@@ -140,8 +273,9 @@ INTERFACE
 
    FUNCTION c_lsf_reinit(phi,gradPhi,gradPhiMag,nx,ny,nz,iter,dx,h,n_exit,rms_hist) &
                          BIND(C, NAME='lsf_reinit') RESULT(rc)
-      IMPORT :: c_int, c_double
-      REAL(c_double) :: phi(*), gradPhi(*), gradPhiMag(*)
+      IMPORT :: c_int, c_double, c_ptr
+      REAL(c_double) :: phi(*)
+      TYPE(c_ptr), VALUE :: gradPhi, gradPhiMag       ! C_NULL_PTR: not wanted (both are dead downstream, set3d.f90:372-375)
       INTEGER(c_int), VALUE :: nx,ny,nz,iter
       REAL(c_double), VALUE :: dx,h
       INTEGER(c_int) :: n_exit
@@ -238,15 +372,48 @@ END SUBROUTINE signSearch_b200
 SUBROUTINE reinit_b200(phi,gradPhi,gradPhiMag,nx,ny,nz,iter,dx,h)
    INTEGER, INTENT(IN) :: nx,ny,nz,iter
    REAL(c_double), INTENT(IN) :: dx,h
-   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phi,gradPhiMag
-   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz,3), INTENT(INOUT) :: gradPhi
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phi
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT), TARGET :: gradPhiMag
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz,3), INTENT(INOUT), TARGET :: gradPhi
+   CALL reinit_core_b200(phi,C_LOC(gradPhi),C_LOC(gradPhiMag),nx,ny,nz,iter,dx,h)
+END SUBROUTINE reinit_b200
+
+!*************************************************************************************!
+! reinit without the gradPhi / gradPhiMag outputs.  Both are dead at the reference's two
+! call sites (zeroed at set3d.f90:372-375 after the first call, never read after the second,
+! :582), and shipping them costs 4 x 8 B per point over PCIe in each direction plus a replay
+! of the last sweep; a driver that does not need them calls this instead of reinit_b200.
+!*************************************************************************************!
+SUBROUTINE reinit_nograd_b200(phi,nx,ny,nz,iter,dx,h)
+   INTEGER, INTENT(IN) :: nx,ny,nz,iter
+   REAL(c_double), INTENT(IN) :: dx,h
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phi
+   CALL reinit_core_b200(phi,C_NULL_PTR,C_NULL_PTR,nx,ny,nz,iter,dx,h)
+END SUBROUTINE reinit_nograd_b200
+
+SUBROUTINE reinit_core_b200(phi,pGrad,pGradMag,nx,ny,nz,iter,dx,h)
+   INTEGER, INTENT(IN) :: nx,ny,nz,iter
+   REAL(c_double), INTENT(IN) :: dx,h
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(INOUT) :: phi
+   TYPE(c_ptr), INTENT(IN) :: pGrad,pGradMag
    REAL(c_double), ALLOCATABLE :: hist(:)
    INTEGER(c_int) :: rc, n_exit
-   INTEGER :: n
    ALLOCATE(hist(0:iter))
-   rc = c_lsf_reinit(phi,gradPhi,gradPhiMag,INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),INT(iter,c_int), &
+   rc = c_lsf_reinit(phi,pGrad,pGradMag,INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),INT(iter,c_int), &
                      dx,h,n_exit,hist)
    IF (rc < 0) CALL lsf_fail("reinit_b200", rc)
+   CALL print_reinit_history(hist,iter,n_exit,rc)
+   DEALLOCATE(hist)
+   IF (rc == LSF_NAN) STOP
+   PRINT*,
+END SUBROUTINE reinit_core_b200
+
+! the reference's per-sweep lines (subs.f90:916,923) from the returned RMS history
+SUBROUTINE print_reinit_history(hist,iter,n_exit,rc)
+   INTEGER, INTENT(IN) :: iter
+   REAL(c_double), INTENT(IN) :: hist(0:iter)
+   INTEGER(c_int), INTENT(IN) :: n_exit, rc
+   INTEGER :: n
    DO n = 0,n_exit
       IF (n == n_exit .AND. rc == LSF_OK .AND. hist(n) < 1.E-5) THEN
          PRINT*, " Distance function time integration has reached steady state "
@@ -254,10 +421,55 @@ SUBROUTINE reinit_b200(phi,gradPhi,gradPhiMag,nx,ny,nz,iter,dx,h)
          PRINT*, " Iteration: ",n," ", " RMS Error: ",hist(n)
       END IF
    END DO
+END SUBROUTINE print_reinit_history
+
+!*************************************************************************************!
+! reinit (subs.f90:717-931) on a device-resident grid -- whole (lsf_grid_create) or z-slab
+! (lsf_sgrid_create, one MPI rank per GPU; every rank makes the same call and gets the same
+! n_exit / history).  iprint /= 0: this rank prints the reference's lines (rank 0 in an MPI run).
+!*************************************************************************************!
+SUBROUTINE gridReinit_b200(g,iter,dx,h,iprint)
+   TYPE(c_ptr), INTENT(IN) :: g
+   INTEGER, INTENT(IN) :: iter,iprint
+   REAL(c_double), INTENT(IN) :: dx,h
+   REAL(c_double), ALLOCATABLE :: hist(:)
+   INTEGER(c_int) :: rc, n_exit
+   ALLOCATE(hist(0:iter))
+   rc = lsf_grid_reinit(g,INT(iter,c_int),dx,h,1.E-5_c_double,n_exit,hist)
+   IF (rc < 0) CALL lsf_fail("gridReinit_b200", rc)
+   IF (iprint /= 0) CALL print_reinit_history(hist,iter,n_exit,rc)
    DEALLOCATE(hist)
    IF (rc == LSF_NAN) STOP
-   PRINT*,
-END SUBROUTINE reinit_b200
+   IF (iprint /= 0) PRINT*,
+END SUBROUTINE gridReinit_b200
+
+!*************************************************************************************!
+! the min/max flow loop (set3d.f90:394-462) on a device-resident grid; nDone = loop index at exit
+!*************************************************************************************!
+SUBROUTINE gridMinMaxFlow_b200(g,iter,dx,h1,tol,nDone,iprint)
+   TYPE(c_ptr), INTENT(IN) :: g
+   INTEGER, INTENT(IN) :: iter,iprint
+   REAL(c_double), INTENT(IN) :: dx,h1,tol
+   INTEGER, INTENT(OUT) :: nDone
+   REAL(c_double), ALLOCATABLE :: hist(:)
+   INTEGER(c_int) :: rc, n_exit
+   INTEGER :: n
+   ALLOCATE(hist(MAX(iter,1)))
+   rc = lsf_grid_minmax(g,INT(iter,c_int),dx,h1,tol,n_exit,hist)
+   IF (rc < 0) CALL lsf_fail("gridMinMaxFlow_b200", rc)
+   nDone = n_exit
+   IF (iprint /= 0) THEN
+      DO n = 1,n_exit
+         IF (n == n_exit .AND. rc == LSF_OK .AND. hist(n) < tol) THEN
+            PRINT*, " Min/max time integration has reached steady state "
+         ELSE
+            PRINT*, " Iteration: ",n," ", " RMS Error: ",hist(n)
+         END IF
+      END DO
+   END IF
+   DEALLOCATE(hist)
+   IF (rc == LSF_NAN) STOP
+END SUBROUTINE gridMinMaxFlow_b200
 
 !*************************************************************************************!
 ! SUBROUTINE narrowBand(nx,ny,nz,dx,phi,phiNB,phiSB), subs.f90:178-207

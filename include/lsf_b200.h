@@ -24,6 +24,7 @@
 #ifndef LSF_B200_H
 #define LSF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -84,6 +85,12 @@ int lsf_last_sweep_timing(double *sweep_ms, int *n_sweeps);
 
 /* ---- host-buffer entry points (the drop-in boundary) ------------------------------------ */
 
+/* Optional: page-lock a caller-owned host array (e.g. the driver's ALLOCATEd phi, set3d.f90:160) for the lifetime of
+ * its allocation, so that the entry points below move it at PCIe speed instead of through the driver's pageable
+ * staging path.  Explicit because only the caller knows when the array is freed: unregister BEFORE DEALLOCATE. */
+int lsf_host_register(void *ptr, size_t nbytes);
+int lsf_host_unregister(void *ptr);
+
 /* Inside/outside sign search, replaces the inline loop set3d.f90:196-268 (+ phiSign,
  * subs.f90:169).  phi must already hold the caller's fill value (reference: 1., set3d.f90:161);
  * only points of the sub-box [im..ip]x[jm..jp]x[km..kp] are overwritten.
@@ -137,7 +144,14 @@ int lsf_grid_fill(lsf_grid *g, double value);                       /* phi = val
 int lsf_grid_upload(lsf_grid *g, const double *phi_host);           /* H2D, dense Fortran layout */
 int lsf_grid_download(lsf_grid *g, double *phi_host);               /* D2H */
 int lsf_grid_download_phiN(lsf_grid *g, double *phiN_host);
-void *lsf_grid_device_ptr(lsf_grid *g);                             /* device address of phi(0,0,0) */
+void *lsf_grid_device_ptr(lsf_grid *g);                             /* device address of phi(0,0,0) of the local array; valid until
+                                                                       the next lsf_grid_minmax call on g (that call ping-pongs
+                                                                       between two buffers and may leave phi in the other one) */
+/* Partition-independent digest of the OWNED points of phi: digest[0] = sum of bits(phi(q)) * (2q+1) mod 2^64 over the
+ * points, q = global linear index (i + (nx+1)(j + (ny+1)k)); digest[1] = xor of the bit patterns.  The per-rank digests
+ * of a sharded grid add / xor up to the digest of the same field on one GPU -- how bench.py and the multi-GPU tests
+ * show that an N-GPU result is bit-identical to the single-GPU one without moving the field. */
+int lsf_grid_checksum(lsf_grid *g, uint64_t digest[2]);
 int lsf_grid_sign_init(lsf_grid *g, const double xLo[3], double dx,
                        const double *surfX, int nSurfNode, const int32_t *surfElem, int nSurfElem,
                        int im, int ip, int jm, int jp, int km, int kp);

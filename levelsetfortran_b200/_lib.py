@@ -56,6 +56,9 @@ SYMBOLS = {
     "lsf_grid_download": (_I, [_V, _V]),
     "lsf_grid_download_phiN": (_I, [_V, _V]),
     "lsf_grid_device_ptr": (_V, [_V]),
+    "lsf_grid_checksum": (_I, [_V, C.POINTER(C.c_uint64)]),
+    "lsf_host_register": (_I, [_V, C.c_size_t]),
+    "lsf_host_unregister": (_I, [_V]),
     "lsf_grid_sign_init": (_I, [_V, c_double_p, _D, c_double_p, _I, c_i32_p, _I] + [_I] * 6),
     "lsf_grid_reinit": (_I, [_V, _I, _D, _D, _D, c_int_p, c_double_p]),
     "lsf_grid_narrowband": (_I, [_V, _D, c_i32_p, c_i32_p]),
@@ -86,6 +89,8 @@ def lib():
                               "(python -m levelsetfortran_b200.build); there is no CPU fallback")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
+            if "LSF_LIB_PATH" in os.environ and not hasattr(L, name):
+                continue           # a tuning variant built from an older source tree (tools/build_variant.sh)
             f = getattr(L, name)   # AttributeError if the .so does not export it
             f.restype = res
             f.argtypes = args

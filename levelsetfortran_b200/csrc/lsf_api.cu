@@ -714,6 +714,7 @@ int lsf_grid_destroy(lsf_grid *g)
 int lsf_grid_fill(lsf_grid *g, double value)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    g->sb_from_phiN = false;
     if (g->f32) return f32_fill(g, value);
     launch_fill(g, g->phi, value);                                      // ghost planes included: consistent on all ranks
     LSF_CUDA(cudaStreamSynchronize(G.stream));
@@ -758,6 +759,42 @@ int lsf_grid_download_phiN(lsf_grid *g, double *phiN_host)
     return LSF_OK;
 }
 
+int lsf_grid_checksum(lsf_grid *g, uint64_t digest[2])
+{
+    if (!g || !digest) return set_error(LSF_ERR_ARG, "null argument");
+    unsigned long long *d = nullptr;
+    LSF_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), G.stream);
+    const long long base = (long long)g->sg.k0 * g->dm.sxy;            // global linear index of this rank's first owned point
+    if (g->f32) launch_checksum(g->phi_f + owned_off(g), 4, (long long)owned_elems(g), base, d);
+    else launch_checksum(g->phi + owned_off(g), 8, (long long)owned_elems(g), base, d);
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, G.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "checksum: %s", cudaGetErrorString(e));
+    digest[0] = h[0]; digest[1] = h[1];
+    return LSF_OK;
+}
+
+// Page-locking of caller-owned host arrays (the Fortran driver's ALLOCATEd phi): explicit, because only the caller knows
+// the lifetime of the allocation -- memory must be unregistered before it is freed.
+int lsf_host_register(void *ptr, size_t nbytes)
+{
+    if (!ptr || !nbytes) return set_error(LSF_ERR_ARG, "null argument");
+    int rc = ensure_init();
+    if (rc) return rc;
+    LSF_CUDA(cudaHostRegister(ptr, nbytes, cudaHostRegisterDefault));
+    return LSF_OK;
+}
+
+int lsf_host_unregister(void *ptr)
+{
+    if (!ptr) return set_error(LSF_ERR_ARG, "null argument");
+    LSF_CUDA(cudaHostUnregister(ptr));
+    return LSF_OK;
+}
+
 void *lsf_grid_device_ptr(lsf_grid *g) { return g ? (g->f32 ? (void *)g->phi_f : (void *)g->phi) : nullptr; }
 
 int lsf_grid_is_f32(lsf_grid *g) { return g && g->f32 ? 1 : 0; }
@@ -766,6 +803,7 @@ int lsf_grid_sign_init(lsf_grid *g, const double xLo[3], double dx, const double
                        const int32_t *surfElem, int nSurfElem, int im, int ip, int jm, int jp, int km, int kp)
 {
     if (!g || !xLo || !surfX || !surfElem) return set_error(LSF_ERR_ARG, "null argument");
+    g->sb_from_phiN = false;
     return sign_core(g, xLo, dx, surfX, nSurfNode, surfElem, nSurfElem, im, ip, jm, jp, km, kp);
 }
 

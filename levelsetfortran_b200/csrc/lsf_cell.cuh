@@ -155,8 +155,12 @@ struct FastArith {
     static LSF_HD double dabs(double x) { return __longlong_as_double(__double_as_longlong(x) & 0x7fffffffffffffffLL); }
     static LSF_HD double max_nn(double a, double b)                                              // a, b >= 0
     {
+#if defined(LSF_MAX_DSETP)      // one DSETP on the FP64 pipe + 2 selects instead of 2 ISETP + 2 selects (experiment)
+        return a > b ? a : b;
+#else
         const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
         return __longlong_as_double(ia > ib ? ia : ib);
+#endif
     }
     static LSF_HD double rsq(double x) { return rsqrt(x); }
 #else
@@ -406,6 +410,34 @@ LSF_HD typename AR::real reinit_cell(const typename AR::real vx[7], const typena
     }
     gM = AR::godunov(vx[3], a, b, c, d, e, f, g, cc);
     return AR::update(vx[3], phiS, gM, cc, sens);
+}
+
+// The same update in two parts, for schedules that compute the x direction ahead of the y/z gathers (lsf_march.cuh,
+// split step barrier): the operations and their order are those of reinit_cell, so ExactArith stays bit-identical.
+template <class AR>
+LSF_HD void reinit_dir_x(const typename AR::real vx[7], bool hi, const CellConstT<typename AR::real> &cc,
+                         typename AR::real &a, typename AR::real &b)
+{
+    if (hi) AR::template weno_dir<false>(vx, cc, a, b);
+    else AR::lo_dir(vx[2], vx[3], vx[4], cc, a, b);
+}
+
+template <class AR>
+LSF_HD typename AR::real reinit_cell_rest(typename AR::real a, typename AR::real b, const typename AR::real vy[7],
+                                          const typename AR::real vz[7], typename AR::real phiS, bool hi,
+                                          const CellConstT<typename AR::real> &cc, typename AR::real g[3],
+                                          typename AR::real &gM, bool &sens)
+{
+    typename AR::real c, d, e, f;
+    if (hi) {
+        AR::template weno_dir<true>(vy, cc, c, d);
+        AR::template weno_dir<false>(vz, cc, e, f);
+    } else {
+        AR::lo_dir(vy[2], vy[3], vy[4], cc, c, d);
+        AR::lo_dir(vz[2], vz[3], vz[4], cc, e, f);
+    }
+    gM = AR::godunov(vy[3], a, b, c, d, e, f, g, cc);
+    return AR::update(vy[3], phiS, gM, cc, sens);
 }
 
 }  // namespace lsf

@@ -105,6 +105,7 @@ void launch_narrowband(Grid *g, const double *phi, double dx, int32_t *nb, int32
 void launch_minmax_iteration_plane(Grid *g, double dx, double h1, bool mask_given);
 void launch_mask_from_i32(Grid *g, const int32_t *nb);
 void launch_fill(Grid *g, double *p, double v);
+void launch_checksum(const void *p, size_t elem_bytes, long long n, long long first_global_index, unsigned long long *d_out);
 void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode,
                       const int32_t *d_surfElem, int nElem, double *d_cen,
                       int im, int ip, int jm, int jp, int km, int kp);

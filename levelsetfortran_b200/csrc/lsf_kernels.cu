@@ -392,6 +392,30 @@ __global__ void k_fill(double *__restrict__ p, long long np, double v)
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < np; q += (long long)gridDim.x * blockDim.x) p[q] = v;
 }
 
+// Partition-independent digest of a field: out[0] = sum over the points of bits(v) * (2*q + 1) modulo 2^64 with q the
+// GLOBAL linear index of the point (odd weights: a permutation of values changes the sum), out[1] = xor of the bit
+// patterns.  Integer addition is associative, so neither depends on the reduction order or on how the grid is cut
+// into slabs: the digests of the ranks' slabs add / xor up to the digest of the whole grid.
+template <class U>
+__global__ void k_checksum(const U *__restrict__ p, long long n, long long base, unsigned long long *out)
+{
+    unsigned long long s = 0, x = 0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long v = (unsigned long long)p[q];
+        s += v * (2ull * (unsigned long long)(q + base) + 1ull);
+        x ^= v;
+    }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); x ^= __shfl_down_sync(0xffffffffu, x, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, s); atomicXor(out + 1, x); }
+}
+
+void launch_checksum(const void *p, size_t elem_bytes, long long n, long long first_global_index, unsigned long long *d_out)
+{
+    if (elem_bytes == 8) k_checksum<unsigned long long><<<RMS_BLOCKS, 256, 0, G.stream>>>((const unsigned long long *)p, n, first_global_index, d_out);
+    else k_checksum<unsigned int><<<RMS_BLOCKS, 256, 0, G.stream>>>((const unsigned int *)p, n, first_global_index, d_out);
+    G.n_launch++;
+}
+
 void launch_fill(Grid *g, double *p, double v)
 {
     k_fill<<<RMS_BLOCKS, 256, 0, G.stream>>>(p, g->np, v);

@@ -18,10 +18,15 @@ namespace lsf {
 #define LSF_OCC 2      // resident CTAs per SM (register budget 65536 / (OCC * THREADS))
 #endif
 typedef MarchCfg<LSF_TB, LSF_TC> CFG;
+#ifndef LSF_OCC_EXACT
+#define LSF_OCC_EXACT 2   // ExactArith (IEEE division / sqrt sequences) does not fit the 80-register budget of 3 CTAs per SM
+#endif
+template <class AR> struct MarchOcc { static constexpr int v = LSF_OCC; };
+template <> struct MarchOcc<ExactArith> { static constexpr int v = LSF_OCC_EXACT; };
 
 // MG: z-slab variant (peer stores / peer flags compiled in)
 template <class AR, bool FA, bool FB, bool FC, bool MG>
-__global__ void __launch_bounds__(CFG::THREADS, LSF_OCC)
+__global__ void __launch_bounds__(CFG::THREADS, MarchOcc<AR>::v)
 k_reinit_march(const MarchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,12 +149,18 @@ int march_prepare(Grid *g)
     }
     static bool attr_done = false;
     if (!attr_done) {
+        // LSF_OCC resident CTAs of 68.5 KB each need (almost) the whole 228 KB of an SM as shared memory
+        const int carve = (int)cudaSharedmemCarveoutMaxShared;
         for (int o = 0; o < 16; ++o) {
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         }
-        for (int o = 0; o < 16; ++o)
+        for (int o = 0; o < 16; ++o) {
             LSF_CUDA(cudaFuncSetAttribute(march_kernel_f32(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG32>)));
+            LSF_CUDA(cudaFuncSetAttribute(march_kernel_f32(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        }
         attr_done = true;
     }
     return LSF_OK;
@@ -214,7 +225,7 @@ struct MultiParams {
 };
 
 template <class AR>
-__global__ void __launch_bounds__(CFG::THREADS, LSF_OCC)
+__global__ void __launch_bounds__(CFG::THREADS, MarchOcc<AR>::v)
 k_reinit_march_multi(const __grid_constant__ MultiParams mp, int nsweeps, unsigned *ticket)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -222,14 +233,15 @@ k_reinit_march_multi(const __grid_constant__ MultiParams mp, int nsweeps, unsign
     march_multi_cta<AR, CFG>(mp.p, nsweeps, ticket, sm, threadIdx.x);
 }
 
+#if defined(LSF_EXP_PDL)
 // Second packaging of the same schedule (LSF_OVERLAP_PDL=1): ONE KERNEL PER SWEEP as in the production path -- compile-
 // time orientation, by-value parameters -- with the overlapped-sweeps hooks, chained by programmatic dependent launch:
 // every CTA executes griddepcontrol.launch_dependents as soon as it is resident, so the next sweep's kernel is admitted
 // when all CTAs of this one hold their SM slots and its CTAs move in as these run out of tickets.  No
-// griddepcontrol.wait: the tile flags carry the data dependences.  (Written in the last hour of round 1; the tile code
-// is the one verified above, the launch mechanics have not run on a GPU yet.)
+// griddepcontrol.wait: the tile flags carry the data dependences.  Compiled only with -DLSF_EXP_PDL (tools/build_variant.sh) until it has
+// passed the GPU parity tests: a wrong ordering assumption would corrupt data silently.
 template <class AR, bool FA, bool FB, bool FC>
-__global__ void __launch_bounds__(CFG::THREADS, LSF_OCC)
+__global__ void __launch_bounds__(CFG::THREADS, MarchOcc<AR>::v)
 k_reinit_march_ov(const MarchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -255,6 +267,8 @@ static MarchKernel march_kernel_ov(int fa, int fb, int fc)
     default: return k_reinit_march_ov<AR, true, true, true>;
     }
 }
+
+#endif   // LSF_EXP_PDL
 
 // Sweeps n_first .. n_first + nsweeps - 1 of the reinit loop in one launch, then their RMS / EXIT / NaN tests in order
 // (k_finalize per sweep: sweeps after an exit leave the history alone; phi then holds the state after the WHOLE batch and
@@ -300,9 +314,15 @@ int launch_reinit_sweeps_overlapped(Grid *g, int n_first, int nsweeps, const Cel
             p.prev_fb = P[s - 1].fb; p.prev_fc = P[s - 1].fc;
         }
     }
-    const int ncta = ntiles < LSF_OCC * G.num_sms ? ntiles : LSF_OCC * G.num_sms;
+    const int occ_ov = (G.arith_run == LSF_ARITH_EXACT) ? MarchOcc<ExactArith>::v : MarchOcc<FastArith>::v;
+    const int ncta = ntiles < occ_ov * G.num_sms ? ntiles : occ_ov * G.num_sms;
+#if defined(LSF_EXP_PDL)
     static const bool pdl = getenv("LSF_OVERLAP_PDL") != nullptr && atoi(getenv("LSF_OVERLAP_PDL")) != 0;
+#else
+    const bool pdl = false;
+#endif
     if (pdl) {
+#if defined(LSF_EXP_PDL)
         // one ticket counter per sweep slot (a memset between two kernels would break their adjacency in the stream)
         static unsigned *tickets = nullptr;
         if (!tickets) LSF_CUDA(cudaMalloc(&tickets, sizeof(unsigned) * OV_BATCH));
@@ -329,6 +349,7 @@ int launch_reinit_sweeps_overlapped(Grid *g, int n_first, int nsweeps, const Cel
             LSF_CUDA(cudaLaunchKernelEx(&cfg, kern, P[s]));
             G.n_launch++;
         }
+#endif
     } else {
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     if (G.arith_run == LSF_ARITH_EXACT)
@@ -364,7 +385,8 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
     }
 #endif
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
-    const int ncta = p.ntiles < LSF_OCC * G.num_sms ? p.ntiles : LSF_OCC * G.num_sms;
+    const int occ = (G.arith_run == LSF_ARITH_EXACT) ? MarchOcc<ExactArith>::v : MarchOcc<FastArith>::v;
+    const int ncta = p.ntiles < occ * G.num_sms ? p.ntiles : occ * G.num_sms;
     MarchKernel kern = (G.arith_run == LSF_ARITH_EXACT) ? march_kernel<ExactArith>(p.fa, p.fb, p.fc, sharded(g))
                                                     : march_kernel<FastArith>(p.fa, p.fb, p.fc, sharded(g));
     kern<<<ncta, CFG::THREADS, sizeof(MarchSmem<CFG>), G.stream>>>(p);

@@ -100,6 +100,28 @@ LSF_DEV void p_st_release_sys(long long *p, long long v)
 LSF_DEV void p_st_peer(double *p, double v) { __stcg(p, v); }
 LSF_DEV void p_st_peer(float *p, float v) { __stcg(p, v); }
 LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
+// split-phase CTA barrier (mbarrier in shared memory): every warp arrives once per phase (one elected lane after a
+// __syncwarp, release), a waiter spins on the phase parity (acquire).  Between arrive and wait a thread may do anything
+// that touches neither the slot ring nor another thread's data.
+LSF_DEV void p_bar_init(unsigned long long *bar, int nthreads)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(nthreads / 32) : "memory");
+}
+LSF_DEV void p_bar_arrive(unsigned long long *bar)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(phase & 1u) : "memory");
+    } while (!ok);
+}
 }  // namespace lsf
 #endif
 
@@ -129,6 +151,9 @@ LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 #ifndef LSF_ASYNC_POLL
 #define LSF_ASYNC_POLL 0        // 1: the predecessor flags are read one step before the chunk start that tests them
 #endif
+#ifndef LSF_SPLIT_BAR
+#define LSF_SPLIT_BAR 0         // 1: split step barrier -- a thread ARRIVES after its deposits, computes the x direction of its NEXT
+#endif                          //    cell from a register window of its own row, and only then WAITS for the other threads' deposits
 // LSF_EXP_NOSTG / LSF_EXP_NOSYNC: no global stores / no CTA barrier per step (timing experiments, results wrong)
 
 namespace lsf {
@@ -279,6 +304,7 @@ template <class CFG>
 struct MarchSmem {
     typename CFG::real S[CFG::SMEM_DOUBLES];
     double red[CFG::THREADS];
+    unsigned long long bar;      // split step barrier (LSF_SPLIT_BAR)
     int tile;
 };
 
@@ -353,12 +379,41 @@ LSF_DEV typename AR::real march_cell(const typename AR::real *Sown, int t, typen
     return pn;
 }
 
+// SPLIT variant of march_cell: the x direction (a, b) was computed ahead from the thread's register window; only the 12
+// y/z stencil values come from the ring.  phic = the cell's current value (window centre).
+template <class AR, bool FB, bool FC, class CFG>
+LSF_DEV typename AR::real march_cell_yz(const typename AR::real *Sown, int t, typename AR::real phic, typename AR::real a, typename AR::real b,
+                                        typename AR::real ps, bool hi, const CellConstT<typename AR::real> &cc, bool &sens,
+                                        typename AR::real &df2)
+{
+    typedef typename AR::real real;
+    constexpr int W = CFG::W, RP = CFG::RP;
+    const real *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
+    real vy[7], vz[7];
+#pragma unroll
+    for (int m = -3; m <= 3; ++m) {
+        if (m != 0) {
+            vy[FB ? 3 - m : 3 + m] = Wn[m * W + 3 + m];
+            vz[FC ? 3 - m : 3 + m] = Wn[m * RP + 3 + m];
+        }
+    }
+    vy[3] = phic; vz[3] = phic;
+    real g[3], gM;
+    const real pn = reinit_cell_rest<AR>(a, b, vy, vz, ps, hi, cc, g, gM, sens);
+    const real df = pn - phic;
+    df2 = df * df;
+    return pn;
+}
+
 // MG = false compiles the z-slab hooks (peer stores, peer flags) out of the single-GPU kernel.
 // OV = true compiles the overlapped-sweeps hooks in (cross-sweep tile wait, boundary values from the shell array,
 // folded boundary block); single GPU only.
 template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true, bool OV = false>
-LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K)
+LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid, const int J, const int K,
+                        unsigned &bar_phase)
 {
+    // split step barrier + own-row register window (scalar loads, one row per thread, one sweep per launch)
+    constexpr bool SPLIT = (LSF_SPLIT_BAR != 0) && CFG::R == 1 && CFG::VEC == 1 && !OV;
     static_assert(!(OV && MG), "overlapped sweeps are a single-GPU schedule");
     static_assert(!OV || (CFG::VEC == 1 && CFG::R == 1), "overlapped sweeps use scalar loads, one row per thread");
     typedef typename AR::real real;
@@ -478,6 +533,11 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         hp[r] = hrow[r] + (long long)(1 - M_LOOK + (hlow[r] ? 0 : M_LOOK) - hsig[r]) * SA;
 
     long long preB = 0, preC = 0;           // LSF_ASYNC_POLL: flag values read ahead of the wait
+    // SPLIT: xw[k] = what slot t-3+k of the own row holds when step t is computed (the thread's own new values behind,
+    // its own look-ahead loads ahead), xa/xb = the x-direction one-sided derivatives of the cell of step t, computed at
+    // the end of step t-1 between the arrive and the wait of that step's barrier
+    real xw[7] = {0, 0, 0, 0, 0, 0, 0};
+    real xa = 0, xb = 0;
     for (int t = -M_LOOK; t <= p.tend; ++t) {
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
         if (t >= 0 && (t % M_CHUNK) == 0) {
@@ -580,7 +640,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
                 if (active[r]) {
                     bool s0;
                     real d0;
-                    pn[r] = march_cell<AR, FA, FB, FC, CFG, false>(Sown[r], t, ps[r], hi[r], p.cc, s0, d0);
+                    if constexpr (SPLIT) pn[r] = march_cell_yz<AR, FB, FC, CFG>(Sown[r], t, xw[3], xa, xb, ps[r], hi[r], p.cc, s0, d0);
+                    else pn[r] = march_cell<AR, FA, FB, FC, CFG, false>(Sown[r], t, ps[r], hi[r], p.cc, s0, d0);
                     sens = sens || s0;
                     acc += d0;
                 }
@@ -611,7 +672,20 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 #if defined(LSF_EXP_NOSYNC)          // timing experiment only (results are wrong): no CTA barrier per step
         __syncwarp();
 #else
-        p_sync();
+        if constexpr (SPLIT) {
+            p_bar_arrive(&sm.bar);                 // this thread's deposits of step t are done
+            // advance the own-row window to step t+1 and compute that cell's x direction: registers only
+            const real c0 = active[0] ? pn[0] : xw[3];
+            xw[0] = xw[1]; xw[1] = xw[2]; xw[2] = c0; xw[3] = xw[4]; xw[4] = xw[5]; xw[5] = xw[6]; xw[6] = la[0];
+            const int an = 2 + t - sig[0];
+            if (compValid[0] && (an >= 1) && (an <= p.nx - 1)) {
+                real vxn[7];
+#pragma unroll
+                for (int m = -3; m <= 3; ++m) vxn[FA ? 3 - m : 3 + m] = xw[3 + m];
+                reinit_dir_x<AR>(vxn, hiBC[0] && (an >= p.lo_a) && (an <= p.hi_a), p.cc, xa, xb);
+            }
+            p_bar_wait(&sm.bar, bar_phase++);      // every thread's deposits of step t are visible
+        } else p_sync();
 #endif
         if (pub && tid == 0) {
             p_fence(); p_st_release(mine, ebase + M_BIAS + t);
@@ -701,6 +775,11 @@ template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true, bool O
 LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid)
 {
     if (p.ctrl->done) return;
+    unsigned bar_phase = 0;
+    if (LSF_SPLIT_BAR) {
+        if (tid == 0) p_bar_init(&sm.bar, CFG::THREADS);
+        p_sync();
+    }
     if (MG && p.halo_seq) {          // z-slab: both neighbours must have refreshed this rank's ghost planes
         if (tid == 0) {
             if (p.halo_need[0]) wait_ge<true>(p.halo_seq + 0, p.halo_need[0], p.ctrl);
@@ -715,7 +794,7 @@ LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> 
         p_sync();
         if (tk >= p.ntiles) break;
         const int jk = p.order[tk];
-        march_tile<AR, FA, FB, FC, CFG, MG, OV>(p, sm, tid, jk & 0xffff, jk >> 16);
+        march_tile<AR, FA, FB, FC, CFG, MG, OV>(p, sm, tid, jk & 0xffff, jk >> 16, bar_phase);
     }
 }
 
@@ -728,6 +807,7 @@ LSF_DEV void march_multi_cta(const MarchParamsT<typename AR::real> *sweeps, int 
                              const int tid)
 {
     if (sweeps[0].ctrl->done) return;
+    unsigned bar_phase = 0;          // unused: the split barrier is a one-sweep-per-launch feature
     const int ntiles = sweeps[0].ntiles;
     for (;;) {
         if (tid == 0) sm.tile = (int)p_ticket(ticket);
@@ -739,14 +819,14 @@ LSF_DEV void march_multi_cta(const MarchParamsT<typename AR::real> *sweeps, int 
         const int jk = p.order[tk % ntiles];
         const int J = jk & 0xffff, K = jk >> 16;
         switch ((p.fa ? 1 : 0) | (p.fb ? 2 : 0) | (p.fc ? 4 : 0)) {
-        case 0: march_tile<AR, false, false, false, CFG, false, true>(p, sm, tid, J, K); break;
-        case 1: march_tile<AR, true, false, false, CFG, false, true>(p, sm, tid, J, K); break;
-        case 2: march_tile<AR, false, true, false, CFG, false, true>(p, sm, tid, J, K); break;
-        case 3: march_tile<AR, true, true, false, CFG, false, true>(p, sm, tid, J, K); break;
-        case 4: march_tile<AR, false, false, true, CFG, false, true>(p, sm, tid, J, K); break;
-        case 5: march_tile<AR, true, false, true, CFG, false, true>(p, sm, tid, J, K); break;
-        case 6: march_tile<AR, false, true, true, CFG, false, true>(p, sm, tid, J, K); break;
-        default: march_tile<AR, true, true, true, CFG, false, true>(p, sm, tid, J, K); break;
+        case 0: march_tile<AR, false, false, false, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
+        case 1: march_tile<AR, true, false, false, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
+        case 2: march_tile<AR, false, true, false, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
+        case 3: march_tile<AR, true, true, false, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
+        case 4: march_tile<AR, false, false, true, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
+        case 5: march_tile<AR, true, false, true, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
+        case 6: march_tile<AR, false, true, true, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
+        default: march_tile<AR, true, true, true, CFG, false, true>(p, sm, tid, J, K, bar_phase); break;
         }
     }
 }

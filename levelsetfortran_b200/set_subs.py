@@ -198,6 +198,13 @@ class DeviceGrid:
     def device_ptr(self) -> int:
         return int(lib().lsf_grid_device_ptr(self._h))
 
+    def checksum(self):
+        """(sum, xor) digest of this rank's owned points of phi (lsf_grid_checksum): position-weighted wrapping sum and xor
+        of the bit patterns; the ranks' digests of a sharded grid add / xor up to the single-GPU digest."""
+        d = (C.c_uint64 * 2)()
+        check(lib().lsf_grid_checksum(self._h, d))
+        return int(d[0]), int(d[1])
+
     def signSearch(self, xLo, dx, surfX, surfElem, box):
         surfX = np.asfortranarray(surfX, dtype=np.float64)
         surfElem = np.asfortranarray(surfElem, dtype=np.int32)

@@ -32,4 +32,16 @@ inline void p_fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void p_st_release_sys(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void p_st_peer(double *p, double v) { *(volatile double *)p = v; }
 inline void p_st_peer(float *p, float v) { *(volatile float *)p = v; }
+// split-phase barrier: one arrival per emulated thread, phases counted up (faithful: a waiter only waits for ARRIVALS);
+// the word holds the thread count in its top 16 bits and the number of arrivals so far below
+inline void p_bar_init(unsigned long long *bar, int nthreads) { __atomic_store_n(bar, (unsigned long long)nthreads << 48, __ATOMIC_SEQ_CST); }
+inline void p_bar_arrive(unsigned long long *bar) { __atomic_fetch_add(bar, 1ull, __ATOMIC_RELEASE); }
+inline void p_bar_wait(unsigned long long *bar, unsigned phase)
+{
+    for (;;) {
+        const unsigned long long v = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+        if ((v & 0xffffffffffffull) >= (v >> 48) * ((unsigned long long)phase + 1ull)) return;
+        sched_yield();
+    }
+}
 }  // namespace lsf
