@@ -37,6 +37,7 @@ PUBLIC :: lsf_grid_download_phiN, lsf_grid_sign_init, lsf_grid_reinit, lsf_grid_
 PUBLIC :: lsf_grid_advect_nodes, lsf_grid_checksum, lsf_host_register, lsf_host_unregister
 PUBLIC :: signSearch_b200, reinit_b200, reinit_nograd_b200, narrowBand_b200, minMaxFlow_b200, advectNodes_b200
 PUBLIC :: gridReinit_b200, gridMinMaxFlow_b200
+PUBLIC :: stlRead_b200, writeVti_b200, writeS3d_b200
 PUBLIC :: LSF_OK, LSF_NAN, LSF_ARITH_FAST, LSF_ARITH_EXACT, LSF_ARITH_AUTO, LSF_PREC_F64, LSF_PREC_F32
 
 INTEGER(c_int), PARAMETER :: LSF_OK = 0, LSF_NAN = 1
@@ -251,6 +252,52 @@ INTERFACE
       TYPE(c_ptr), VALUE :: ptr
       INTEGER(c_int) :: rc
    END FUNCTION lsf_host_unregister
+
+   ! ---- host-side pieces either side of the path (no device work): .vti / .s3d writers, stlRead de-duplication ----
+   FUNCTION c_lsf_write_vti(path,phi,nx,ny,nz,xLo,dx) BIND(C, NAME='lsf_write_vti') RESULT(rc)
+      IMPORT :: c_int, c_double, c_char
+      CHARACTER(KIND=c_char), INTENT(IN) :: path(*)          ! NUL-terminated
+      REAL(c_double), INTENT(IN) :: phi(*)
+      INTEGER(c_int), VALUE :: nx,ny,nz
+      REAL(c_double), INTENT(IN) :: xLo(3)
+      REAL(c_double), VALUE :: dx
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_write_vti
+
+   FUNCTION c_lsf_write_s3d(path,nSurfElem,nSurfNode,nBndElem,nBndComp,surfOrder,surfElem,surfElemTag,surfXX,bndNormal) &
+                            BIND(C, NAME='lsf_write_s3d') RESULT(rc)
+      IMPORT :: c_int, c_double, c_char, c_int32_t
+      CHARACTER(KIND=c_char), INTENT(IN) :: path(*)
+      INTEGER(c_int), VALUE :: nSurfElem,nSurfNode,nBndElem,nBndComp
+      INTEGER(c_int32_t), INTENT(IN) :: surfOrder(*), surfElem(*), surfElemTag(*)
+      REAL(c_double), INTENT(IN) :: surfXX(*), bndNormal(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_write_s3d
+
+   FUNCTION c_lsf_stl_count(path,ntri) BIND(C, NAME='lsf_stl_count') RESULT(rc)
+      IMPORT :: c_int, c_char
+      CHARACTER(KIND=c_char), INTENT(IN) :: path(*)
+      INTEGER(c_int) :: ntri
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_stl_count
+
+   FUNCTION c_lsf_stl_read_triangles(path,ntri,tri) BIND(C, NAME='lsf_stl_read_triangles') RESULT(rc)
+      IMPORT :: c_int, c_char, c_float
+      CHARACTER(KIND=c_char), INTENT(IN) :: path(*)
+      INTEGER(c_int), VALUE :: ntri
+      REAL(c_float) :: tri(*)                                 ! triangles(3,ntri*3) of subs.f90:38
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_stl_read_triangles
+
+   FUNCTION c_lsf_stl_dedup(tri,ntri,nodes,surfElem,nSurfNode) BIND(C, NAME='lsf_stl_dedup') RESULT(rc)
+      IMPORT :: c_int, c_float, c_int32_t
+      REAL(c_float), INTENT(IN) :: tri(*)
+      INTEGER(c_int), VALUE :: ntri
+      REAL(c_float) :: nodes(*)                               ! nodesT(3,k)
+      INTEGER(c_int32_t) :: surfElem(*)                       ! (ntri,3), 1-based
+      INTEGER(c_int) :: nSurfNode
+      INTEGER(c_int) :: rc
+   END FUNCTION c_lsf_stl_dedup
 
    FUNCTION lsf_last_error() BIND(C, NAME='lsf_last_error') RESULT(msg)
       IMPORT :: c_ptr
@@ -540,5 +587,101 @@ SUBROUTINE advectNodes_b200(xLo,nx,ny,nz,dx,phi,phiSB,nSurfNode,surfX,surfXX,phi
                            INT(nSurfNode,c_int),phiSurf,gradPhiSurf,INT(iter,c_int),n_moves)
    IF (rc < 0) CALL lsf_fail("advectNodes_b200", rc)
 END SUBROUTINE advectNodes_b200
+
+!*************************************************************************************!
+! SUBROUTINE stlRead(...), subs.f90:17-121, same argument list and results; the vertex
+! de-duplication (:68-93, O(ntri*nSurfNode) in the reference) runs hash-based in the library
+! with the reference's own match predicate and numbering.  (nBndComp is set BEFORE bndNormal is
+! allocated here; the reference allocates with nBndComp still undefined, :112-117.)
+!*************************************************************************************!
+SUBROUTINE stlRead_b200(surfX,nSurfNode,surfElem,filename,nSurfElem,surfElemTag,surfOrder,nBndComp,nBndElem,bndNormal)
+   CHARACTER, INTENT(IN) :: filename*80
+   INTEGER(c_int32_t) :: nSurfNode,nSurfElem
+   INTEGER(c_int32_t),ALLOCATABLE,DIMENSION(:,:),INTENT(OUT) :: surfElem
+   REAL(c_double),ALLOCATABLE,DIMENSION(:,:),INTENT(OUT) :: surfX
+   INTEGER,ALLOCATABLE,DIMENSION(:),INTENT(OUT) :: surfElemTag,surfOrder
+   REAL(c_double),ALLOCATABLE,DIMENSION(:,:),INTENT(OUT) :: bndNormal
+   INTEGER,INTENT(OUT) :: nBndComp,nBndElem
+   REAL(c_float),ALLOCATABLE,DIMENSION(:,:) :: triangles,nodesT
+   CHARACTER(KIND=c_char) :: cpath(81)
+   INTEGER(c_int) :: rc,ntri,nn
+   INTEGER :: k
+   PRINT*,
+   PRINT*, " Reading in .stl Mesh "
+   PRINT*,
+   CALL c_path(filename,cpath)
+   rc = c_lsf_stl_count(cpath,ntri)
+   IF (rc < 0) CALL lsf_fail("stlRead_b200", rc)
+   ALLOCATE(triangles(3,MAX(ntri*3,1)))
+   ALLOCATE(nodesT(3,MAX(ntri*3,1)))
+   ALLOCATE(surfElem(ntri,3))
+   rc = c_lsf_stl_read_triangles(cpath,ntri,triangles)
+   IF (rc < 0) CALL lsf_fail("stlRead_b200", rc)
+   rc = c_lsf_stl_dedup(triangles,ntri,nodesT,surfElem,nn)
+   IF (rc < 0) CALL lsf_fail("stlRead_b200", rc)
+   nSurfElem = ntri
+   nSurfNode = nn
+   ALLOCATE(surfX(nSurfNode,3))
+   DO k = 1,nSurfNode                                                 ! subs.f90:99-103
+      surfX(k,1) = nodesT(1,k)
+      surfX(k,2) = nodesT(2,k)
+      surfX(k,3) = nodesT(3,k)
+   END DO
+   DEALLOCATE(nodesT)
+   DEALLOCATE(triangles)
+   nBndElem = 0
+   nBndComp = 1
+   ALLOCATE(surfOrder(nSurfElem))
+   ALLOCATE(surfElemTag(nSurfElem))
+   ALLOCATE(bndNormal(nBndComp,3))
+   surfOrder = 1
+   surfElemTag = 0
+   bndNormal = 0.
+END SUBROUTINE stlRead_b200
+
+!*************************************************************************************!
+! The ParaView writer of set3d.f90:320-351 / :539-569 (byte-identical file, including the
+! 4-byte nbytePhi = (nx+1)**3*24 of :330): CALL writeVti_b200('signedDistanceFunction.vti',...)
+!*************************************************************************************!
+SUBROUTINE writeVti_b200(fname,phi,nx,ny,nz,xLo,dx)
+   CHARACTER(LEN=*), INTENT(IN) :: fname
+   INTEGER, INTENT(IN) :: nx,ny,nz
+   REAL(c_double), DIMENSION(0:nx,0:ny,0:nz), INTENT(IN) :: phi
+   REAL(c_double), INTENT(IN) :: xLo(3),dx
+   CHARACTER(KIND=c_char) :: cpath(LEN(fname)+1)
+   INTEGER(c_int) :: rc
+   CALL c_path(fname,cpath)
+   rc = c_lsf_write_vti(cpath,phi,INT(nx,c_int),INT(ny,c_int),INT(nz,c_int),xLo,dx)
+   IF (rc < 0) CALL lsf_fail("writeVti_b200", rc)
+END SUBROUTINE writeVti_b200
+
+!*************************************************************************************!
+! The .s3d writer of set3d.f90:600-614; surfElem is passed 0-based, i.e. after :590-594
+!*************************************************************************************!
+SUBROUTINE writeS3d_b200(meshname,nSurfElem,nSurfNode,nBndElem,nBndComp,surfOrder,surfElem,surfElemTag,surfXX,bndNormal)
+   CHARACTER(LEN=*), INTENT(IN) :: meshname
+   INTEGER(c_int32_t), INTENT(IN) :: nSurfElem,nSurfNode
+   INTEGER, INTENT(IN) :: nBndElem,nBndComp
+   INTEGER(c_int32_t), INTENT(IN) :: surfOrder(nSurfElem),surfElem(nSurfElem,3),surfElemTag(nSurfElem)
+   REAL(c_double), INTENT(IN) :: surfXX(nSurfNode,3),bndNormal(nBndComp,3)
+   CHARACTER(KIND=c_char) :: cpath(LEN(meshname)+1)
+   INTEGER(c_int) :: rc
+   CALL c_path(meshname,cpath)
+   rc = c_lsf_write_s3d(cpath,INT(nSurfElem,c_int),INT(nSurfNode,c_int),INT(nBndElem,c_int),INT(nBndComp,c_int), &
+                        surfOrder,surfElem,surfElemTag,surfXX,bndNormal)
+   IF (rc < 0) CALL lsf_fail("writeS3d_b200", rc)
+END SUBROUTINE writeS3d_b200
+
+! blank-padded Fortran name -> NUL-terminated C string
+SUBROUTINE c_path(fname,cpath)
+   CHARACTER(LEN=*), INTENT(IN) :: fname
+   CHARACTER(KIND=c_char), INTENT(OUT) :: cpath(*)
+   INTEGER :: q,n
+   n = LEN_TRIM(fname)
+   DO q = 1,n
+      cpath(q) = fname(q:q)
+   END DO
+   cpath(n+1) = C_NULL_CHAR
+END SUBROUTINE c_path
 
 END MODULE lsf_b200

@@ -131,6 +131,23 @@ int lsf_minmax(double *phi, double *phiN, int32_t *phiNB, int32_t *phiSB,
 int lsf_advect_nodes(const double *phi, const int32_t *phiSB, int nx, int ny, int nz, const double xLo[3], double dx,
                      double *surfXX, int nSurfNode, double *phiSurf, double *gradPhiSurf, int iter, long long *n_moves);
 
+/* ---- host-side pieces either side of the path (no device work) ---------------------------- */
+
+/* The reference's ParaView writer, byte for byte (set3d.f90:320-351 signedDistanceFunction.vti, :539-569
+ * smoothedDistanceFunction.vti), including the wrong 4-byte length field nbytePhi = (nx+1)**3*24 (:330). */
+int lsf_write_vti(const char *path, const double *phi, int nx, int ny, int nz, const double xLo[3], double dx);
+/* The .s3d mesh file of set3d.f90:604-614 (list-directed records, gfortran spacing).  surfElem (nSurfElem,3) is
+ * 0-based here, as the reference makes it at :590-594 before writing; surfXX (nSurfNode,3); bndNormal (nBndComp,3). */
+int lsf_write_s3d(const char *path, int nSurfElem, int nSurfNode, int nBndElem, int nBndComp, const int32_t *surfOrder,
+                  const int32_t *surfElem, const int32_t *surfElemTag, const double *surfXX, const double *bndNormal);
+/* stlRead (subs.f90:17-121) without its O(ntri * nSurfNode) search: count, read the raw REAL*4 triangles
+ * (9*ntri floats, vertex-major = the reference's triangles(3,ntri*3)), de-duplicate with the reference's own match
+ * predicate and first-occurrence numbering.  nodes: work array of 9*ntri floats receiving nodesT(3,k); surfElem:
+ * (ntri,3) column-major, 1-based; the caller then fills surfX(k,c) = nodes(c,k) as subs.f90:99-103 does. */
+int lsf_stl_count(const char *path, int *ntri);
+int lsf_stl_read_triangles(const char *path, int ntri, float *tri);
+int lsf_stl_dedup(const float *tri, int ntri, float *nodes, int32_t *surfElem, int *nSurfNode);
+
 /* ---- device-resident pipeline (no host round trip between stages) ------- */
 int lsf_grid_create(lsf_grid **g, int nx, int ny, int nz);
 /* fp32 mode: phi is stored as float on the device; the same lsf_grid_* calls apply (upload / download convert

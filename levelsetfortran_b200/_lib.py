@@ -59,6 +59,11 @@ SYMBOLS = {
     "lsf_grid_checksum": (_I, [_V, C.POINTER(C.c_uint64)]),
     "lsf_host_register": (_I, [_V, C.c_size_t]),
     "lsf_host_unregister": (_I, [_V]),
+    "lsf_write_vti": (_I, [C.c_char_p, c_double_p, _I, _I, _I, c_double_p, _D]),
+    "lsf_write_s3d": (_I, [C.c_char_p, _I, _I, _I, _I, c_i32_p, c_i32_p, c_i32_p, c_double_p, c_double_p]),
+    "lsf_stl_count": (_I, [C.c_char_p, c_int_p]),
+    "lsf_stl_read_triangles": (_I, [C.c_char_p, _I, C.POINTER(C.c_float)]),
+    "lsf_stl_dedup": (_I, [C.POINTER(C.c_float), _I, C.POINTER(C.c_float), c_i32_p, c_int_p]),
     "lsf_grid_sign_init": (_I, [_V, c_double_p, _D, c_double_p, _I, c_i32_p, _I] + [_I] * 6),
     "lsf_grid_reinit": (_I, [_V, _I, _D, _D, _D, c_int_p, c_double_p]),
     "lsf_grid_narrowband": (_I, [_V, _D, c_i32_p, c_i32_p]),

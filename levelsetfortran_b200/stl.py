@@ -71,6 +71,33 @@ def stlRead(path):
     return surfX, surfX.shape[0], surfElem, surfElem.shape[0]
 
 
+def stlRead_native(path):
+    """stlRead through the library's host entry points (lsf_stl_count / lsf_stl_read_triangles / lsf_stl_dedup, the ones
+    a Fortran driver binds): same four results, the reference's exact match predicate, O(n)."""
+    import ctypes as C
+    from ._lib import check, lib
+    L = lib()
+    ntri = C.c_int(0)
+    check(L.lsf_stl_count(str(path).encode(), C.byref(ntri)))
+    tri = np.empty(9 * ntri.value, dtype=np.float32)
+    check(L.lsf_stl_read_triangles(str(path).encode(), ntri.value, tri.ctypes.data_as(C.POINTER(C.c_float))))
+    return dedup_native(tri.reshape(ntri.value, 3, 3))
+
+
+def dedup_native(tris):
+    import ctypes as C
+    from ._lib import check, lib
+    tri = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1)
+    ntri = tri.size // 9
+    nodes = np.empty(max(9 * ntri, 1), dtype=np.float32)
+    elem = np.zeros((ntri, 3), dtype=np.int32, order="F")
+    nn = C.c_int(0)
+    check(lib().lsf_stl_dedup(tri.ctypes.data_as(C.POINTER(C.c_float)), ntri, nodes.ctypes.data_as(C.POINTER(C.c_float)),
+                              elem.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nn)))
+    surfX = np.asfortranarray(nodes[: 3 * nn.value].reshape(nn.value, 3).astype(np.float64))    # surfX(k,c) = nodesT(c,k), subs.f90:99-103
+    return surfX, nn.value, elem, ntri
+
+
 def grid_from_surface(surfX, dx=0.05, dd=10):
     """Grid definition of set3d.f90:90-186 and the normalised step of :301.
     Returns dict(nx, ny, nz, xLo, xHi, box=(im,ip,jm,jp,km,kp), dx, dxx)."""

@@ -77,3 +77,29 @@ def read_vti(path):
     n = (nx + 1) * (ny + 1) * (nz + 1)
     phi = np.frombuffer(raw, dtype="<f8", count=n, offset=start).reshape((nx + 1, ny + 1, nz + 1), order="F")
     return np.asfortranarray(phi), origin, dx
+
+
+def write_vti_native(path, phi, xLo, dx):
+    """The same file through the library's host entry point lsf_write_vti (what a Fortran driver would bind)."""
+    import ctypes as C
+    from ._lib import c_double_p, check, lib
+    phi = np.asarray(phi)
+    if phi.dtype != np.float64 or phi.ndim != 3 or not phi.flags.f_contiguous:
+        raise ValueError("phi must be a Fortran-ordered float64 array phi(0:nx,0:ny,0:nz)")
+    nx, ny, nz = (s - 1 for s in phi.shape)
+    x = np.ascontiguousarray(xLo, dtype=np.float64)
+    check(lib().lsf_write_vti(str(path).encode(), phi.ctypes.data_as(c_double_p), nx, ny, nz, x.ctypes.data_as(c_double_p), float(dx)))
+
+
+def write_s3d_native(path, surfOrder, surfElem0, surfElemTag, surfXX, bndNormal, nBndElem=0):
+    """set3d.f90:604-614 through lsf_write_s3d.  surfElem0: (nSurfElem,3) ZERO-based (the reference decrements at :590-594)."""
+    import ctypes as C
+    from ._lib import c_double_p, c_i32_p, check, lib
+    so = np.ascontiguousarray(surfOrder, dtype=np.int32)
+    se = np.asfortranarray(surfElem0, dtype=np.int32)
+    st = np.ascontiguousarray(surfElemTag, dtype=np.int32)
+    xx = np.asfortranarray(surfXX, dtype=np.float64)
+    bn = np.asfortranarray(bndNormal, dtype=np.float64).reshape(-1, 3, order="F")
+    check(lib().lsf_write_s3d(str(path).encode(), se.shape[0], xx.shape[0], int(nBndElem), bn.shape[0], so.ctypes.data_as(c_i32_p),
+                              se.ctypes.data_as(c_i32_p), st.ctypes.data_as(c_i32_p), xx.ctypes.data_as(c_double_p),
+                              bn.ctypes.data_as(c_double_p) if bn.size else None))

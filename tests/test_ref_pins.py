@@ -162,7 +162,10 @@ def test_vti_writer_bytes(tmp_path):
     p.set("phi", phi, lower=(0, 0, 0))
     assert p.run(*P.VTI1) == 0
     vti.write_vti(tmp_path / "mirror.vti", phi, (-1.5, 0.25, 3.0), DX)
-    assert (tmp_path / "signedDistanceFunction.vti").read_bytes() == (tmp_path / "mirror.vti").read_bytes()
+    want = (tmp_path / "signedDistanceFunction.vti").read_bytes()
+    assert want == (tmp_path / "mirror.vti").read_bytes()
+    vti.write_vti_native(tmp_path / "native.vti", phi, (-1.5, 0.25, 3.0), DX)          # the C entry point a Fortran driver binds
+    assert want == (tmp_path / "native.vti").read_bytes()
     files = np.load(f"{GOLDEN}/cube40_files.npz")
     assert bytes(files["vti_header"]) == vti.header(61, 61, 61, (-1.5, -1.5, -1.5), DX) + vti.nbyte_field(61)
 
@@ -176,7 +179,50 @@ def test_stlread_dedup_matches(tmp_path):
     X, E = R.stl_read(str(path))
     X2, _, E2, _ = stl.stlRead(str(path))
     assert X.shape[0] < 3 * E.shape[0] and np.array_equal(X, X2) and np.array_equal(E, E2)
+    X3, n3, E3, nt3 = stl.stlRead_native(str(path))                                     # lsf_stl_* host entry points
+    assert (n3, nt3) == X.shape[:1] + E.shape[:1] and np.array_equal(X, X3) and np.array_equal(E, E3)
+    # the corner the hash must not get wrong: distinct near-zero floats closer than 1e-13 match in the reference
+    # (abs(REAL*4 difference) < 1.e-13), the relation is not transitive, and a vertex repeated inside one triangle
+    # beyond the search window is stored twice
+    t = np.float32
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]],
+                    [[3e-14, 0, 0], [1, 0, -2e-14], [7, 7, 7]],
+                    [[7, 7, 7], [9, 9, 9], [9, 9, 9]],
+                    [[6e-14, 1e-20, 0], [9, 9, 9], [1.1e-13, 0, 0]],
+                    [[-0.0, 0, 0], [1, 0, 0], [5e-7, 0, 0]]], dtype=t)
+    stl.stl_write(tmp_path / "tiny.stl", tri)
+    Xr, Er = R.stl_read(str(tmp_path / "tiny.stl"))
+    Xn, nn, En, _ = stl.stlRead_native(str(tmp_path / "tiny.stl"))
+    assert np.array_equal(Er, En) and np.array_equal(Xr, Xn), (Er.T, En.T)
     Xg, Eg = load_mesh("twoCube10")
     if os.path.exists(f"{R.REFERENCE_DIR}/twoCube10.stl"):
         X, E = R.stl_read(f"{R.REFERENCE_DIR}/twoCube10.stl")
         assert np.array_equal(X, Xg) and np.array_equal(E, Eg)
+
+
+def test_s3d_writer_records(tmp_path):
+    """the .s3d file (set3d.f90:584-614) as the translated reference writes it == lsf_write_s3d.  Which values go into
+    which record comes from the reference's text; the list-directed SPACING is libgfortran's and is restated in both the
+    oracle's run time and the library -- this test cannot pin it, only gfortran could."""
+    from levelsetfortran_b200 import stl, vti
+    path = tmp_path / "mesh.stl"
+    stl.stl_write(path, stl.sphere_tris(2.0, n_lat=7, n_lon=6))
+    p = P(outdir=str(tmp_path))
+    p.set_arg(str(path))
+    assert len(str(path)) <= 80 and p.run(*P.IMPORT) == 0
+    X, E = p.get("surfX"), p.get("surfElem")
+    rng = np.random.default_rng(3)
+    XX = np.asfortranarray(X * (1.0 + 0.05 * rng.standard_normal(X.shape)))
+    XX[0, :] = (0.0, -0.0, 1.0e-3)
+    XX[1, :] = (123456.789, -2.5e-12, 0.1)
+    p.set("surfXX", XX)
+    assert p.run(*P.S3D) == 0
+    got = (tmp_path / "mesh.s3d").read_bytes()
+    vti.write_s3d_native(tmp_path / "native.s3d", p.get("surfOrder"), E - 1, p.get("surfElemTag"), XX, np.zeros((1, 3)))
+    want = (tmp_path / "native.s3d").read_bytes()
+    # the reference's last loop prints bndNormal(1,:) of an array it allocated with nBndComp still undefined (subs.f90:112-117):
+    # an out-of-bounds read in the real binary; compare everything before that record
+    n_lines = 1 + E.shape[0] + XX.shape[0]
+    assert got.split(b"\n")[:n_lines] == want.split(b"\n")[:n_lines]
+    first = got.split(b"\n")[0].decode()
+    assert first == "%12d%12d%12d%12d" % (E.shape[0], X.shape[0], 0, 1)
