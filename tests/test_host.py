@@ -99,3 +99,25 @@ def test_synthetic_configs_hit_the_named_grid_sizes():
     X, E = stl.dedup_nodes(stl.torus_cube_config((1024, 1024, 2048)))
     g = stl.grid_from_surface(X)
     assert (g["nx"] + 1, g["ny"] + 1, g["nz"] + 1) == (1024, 1024, 2048)
+
+
+def test_fortran_module_binds_every_symbol_of_the_header():
+    """fortran/lsf_b200_mod.f90 cannot be compiled here (no Fortran compiler): at least every function include/lsf_b200.h
+    declares must have a BIND(C, NAME='...') interface in it, and the library must export it."""
+    import re
+    from conftest import ROOT
+    from levelsetfortran_b200 import _lib
+    hdr = open(f"{ROOT}/include/lsf_b200.h").read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lsf_[A-Za-z0-9_]+)\s*\(", hdr))
+    mod = open(f"{ROOT}/fortran/lsf_b200_mod.f90").read()
+    bound = set(re.findall(r"BIND\(C,\s*NAME='(lsf_[A-Za-z0-9_]+)'\)", mod))
+    # profiling / tuning switches of the test harness are deliberately not part of the Fortran interface
+    harness_only = {"lsf_last_timing", "lsf_set_profile", "lsf_last_sweep_timing", "lsf_last_arith", "lsf_set_overlap",
+                    "lsf_last_minmax_active", "lsf_grid_device_ptr", "lsf_grid_is_f32"}
+    assert declared - bound - harness_only == set(), sorted(declared - bound - harness_only)
+    assert bound <= declared, sorted(bound - declared)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SYMBOLS), sorted(declared ^ set(_lib.SYMBOLS))
