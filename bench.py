@@ -332,7 +332,7 @@ def run_gpu(args):
     def hexd(d):
         return "%016x:%016x" % d
 
-    mm = strong = parity = None
+    mm = strong = parity = nodes = None
     if args.minmax_iters > 0 and not f32:
         if world == 1:
             SG, sg, sX, sE = G, g, surfX, surfElem
@@ -379,6 +379,17 @@ def run_gpu(args):
                        % (100.0 * active * world / spts, 16.0 * mm_rate / measured_peak()[0]),
               "note": "ms_per_iteration includes building the active list once per call",
               "last_rms": float(hist_mm[-1]) if len(hist_mm) else None}
+        # ---- companion: surface-node projection (set3d.f90:465-501) of the STL's own nodes on the resident field ----
+        if world == 1 and not f32 and args.minmax_iters > 0:
+            try:
+                XX, ps_n, gs_n, n_moves = G.advectNodes(g["xLo"], DX, surfX, 1000)
+                nd_ms, _nl = _lib.last_timing()
+                nodes = {"metric": "surface-node projection (lsf_grid_advect_nodes), kernel ms", "ms": nd_ms, "nodes": int(len(surfX)),
+                         "moves": int(n_moves), "max_displacement": float(np.abs(XX - surfX).max()),
+                         "reference_cost": "O(moves x nodes) trilinear interpolations: %.3g" % (float(n_moves) * len(surfX))}
+            except Exception as e:      # e.g. a band point too close to the boundary: reported, not fatal for the bench line
+                nodes = {"error": str(e)[:200]}
+
         if world == 1:
             # FAST (as timed) vs EXACT on the full grid: the same sign field, the same 8 sweeps, a second grid
             G2 = DeviceGrid(nx, ny, nz)
@@ -401,18 +412,6 @@ def run_gpu(args):
             G2.close()
         if world > 1:
             SG.close()
-
-    # ---- companion: surface-node projection (set3d.f90:465-501) of the STL's own nodes on the resident field ----
-    nodes = None
-    if world == 1 and not f32 and args.minmax_iters > 0:
-        try:
-            XX, ps_n, gs_n, n_moves = G.advectNodes(g["xLo"], DX, surfX, 1000)
-            nd_ms, _nl = _lib.last_timing()
-            nodes = {"metric": "surface-node projection (lsf_grid_advect_nodes), kernel ms", "ms": nd_ms, "nodes": int(len(surfX)),
-                     "moves": int(n_moves), "max_displacement": float(np.abs(XX - surfX).max()),
-                     "reference_cost": "O(moves x nodes) trilinear interpolations: %.3g" % (float(n_moves) * len(surfX))}
-        except Exception as e:      # e.g. a band point too close to the boundary: reported, not fatal for the bench line
-            nodes = {"error": str(e)[:200]}
 
     # ---- parity (b): the CPU sample slab swept by the GPU as a grid of its own, against the reference's result ----
     cpu = None
@@ -491,6 +490,30 @@ def run_gpu(args):
                              "frac": a32 / measured_peak()[0] if a32 else None, "launch_ms": l32, "kernel": "k_reinit_march_f32",
                              "traffic": ncu_traffic(n, True)},
                 "last_rms": float(hist32[-1]), "last_rms_fp64": float(hist[-1]) if hist is not None else None}
+
+    # ---- companion at N > 1: the fp32-mode variant of config 5 (BASELINE configs[4] "plus fp32-mode variant") ----
+    if world > 1 and not f32 and not args.no_f32:
+        G32 = ShardedGrid(nx, ny, nz, f32=True)
+        G32.fill(1.0)
+        G32.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
+        for _ in range(2):
+            G32.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)
+        barrier()
+        ms32 = 0.0
+        k32 = max(1, min(args.steps, 3))
+        for _ in range(k32):
+            rc, n_exit32, hist32 = G32.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)
+            assert rc == 0 and n_exit32 == SWEEPS_PER_STEP - 1
+            ms, _nl = _lib.last_timing()
+            ms32 += ms
+        d32 = allreduce_digest(G32.checksum()) if args.minmax_iters > 0 else None
+        G32.close()
+        t32 = torch.tensor([ms32], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+        ms32 = float(t32.item())
+        fp32 = {"metric": METRIC + " (fp32 mode, config 5 weak scaling)", "value": cells_per_step * k32 / (ms32 * 1e-3) / 1e9, "unit": UNIT,
+                "dtype": "f32", "n_gpus": world, "steps": k32, "ms_per_step": ms32 / k32, "last_rms": float(hist32[-1]),
+                "digest": hexd(d32) if d32 else None}
 
     # ---- e2e: the host-buffer drop-in call, pinned host memory, H2D + compute + D2H timed ------
     e2e = None

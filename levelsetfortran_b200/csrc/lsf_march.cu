@@ -15,7 +15,7 @@ namespace lsf {
 #define LSF_TC 16
 #endif
 #ifndef LSF_OCC
-#define LSF_OCC 2      // resident CTAs per SM (register budget 65536 / (OCC * THREADS))
+#define LSF_OCC 2      // resident CTAs per SM (register budget 65536 / (OCC * THREADS)); 3 fits 80 registers without spills (FastArith)
 #endif
 typedef MarchCfg<LSF_TB, LSF_TC> CFG;
 #ifndef LSF_OCC_EXACT
@@ -149,8 +149,14 @@ int march_prepare(Grid *g)
     }
     static bool attr_done = false;
     if (!attr_done) {
-        // LSF_OCC resident CTAs of 68.5 KB each need (almost) the whole 228 KB of an SM as shared memory
+        // Shared-memory carve-out: left to the driver unless LSF_CARVEOUT_MAX is defined.  Measured (round 2, session 1):
+        // forcing the maximum carve-out halves the sweep rate of BOTH the fp64 and the fp32 kernel -- the L1 that is left is too
+        // small to hold the in-flight global loads of 16-24 warps.
+#if defined(LSF_CARVEOUT_MAX)
         const int carve = (int)cudaSharedmemCarveoutMaxShared;
+#else
+        const int carve = (int)cudaSharedmemCarveoutDefault;
+#endif
         for (int o = 0; o < 16; ++o) {
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<FastArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));
             LSF_CUDA(cudaFuncSetAttribute(march_kernel<ExactArith>(o & 1, o & 2, o & 4, o & 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem<CFG>)));

@@ -151,6 +151,9 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
 #ifndef LSF_ASYNC_POLL
 #define LSF_ASYNC_POLL 0        // 1: the predecessor flags are read one step before the chunk start that tests them
 #endif
+#ifndef LSF_RING_DUP
+#define LSF_RING_DUP 1          // 1: every ring slot is stored twice (window loads need no wrap arithmetic; 66 KB per fp64 CTA);
+#endif                          // 0: stored once, 7 wrapped slot offsets computed per step (35 KB per fp64 CTA -> 3 CTAs/SM leave the L1 its size)
 #ifndef LSF_SPLIT_BAR
 #define LSF_SPLIT_BAR 0         // 1: split step barrier -- a thread ARRIVES after its deposits, computes the x direction of its NEXT
 #endif                          //    cell from a register window of its own row, and only then WAITS for the other threads' deposits
@@ -187,7 +190,8 @@ LSF_DEV int m_imin(int a, int b) { return a < b ? a : b; }
 
 constexpr int M_H = 3;                       // stencil half-width
 constexpr int M_NSLOT = 8;                   // hyperplane slots in the ring (each stored twice)
-constexpr int M_SLOTW = 2 * M_NSLOT + 1;     // doubles per position: 16 + 1 pad (bank spread)
+constexpr bool M_DUP = (LSF_RING_DUP != 0);
+constexpr int M_SLOTW = (M_DUP ? 2 : 1) * M_NSLOT + 1;   // doubles per position: 16 (8 slots stored twice) or 8, + 1 pad (bank spread)
 constexpr int M_CHUNK = LSF_CHUNK;           // publish / wait granularity in steps
 constexpr int M_LOOK = 4;                    // old values are deposited this many steps ahead
 constexpr long long M_FIN = 1LL << 30;       // "tile finished" progress value
@@ -207,7 +211,7 @@ struct MarchCfg {
     static constexpr int SW = TB + 2 * M_H, SH = TC + 2 * M_H;
     // elements per position: 16 slots + pad.  fp32 may use a different pad (LSF_W32) so that the column-halo
     // deposits (stride = row pitch) do not all fall on two banks
-    static constexpr int W = sizeof(T_) == 4 ? LSF_W32 : M_SLOTW;
+    static constexpr int W = sizeof(T_) == 4 ? (M_DUP ? LSF_W32 : M_SLOTW) : M_SLOTW;
     // cells per global vector load of a row walk (RowReader); 1 = scalar loads
     static constexpr int VEC = (R_ > 1) ? 1 : (sizeof(T_) == 4 ? LSF_VEC32 : LSF_VEC64);
     // pitch of one c-row of positions, in doubles; for TB = 8 a warp spans 4 c-rows and the pitch
@@ -353,6 +357,23 @@ inline void march_fill_order(int ntb, int ntc, int *order, int m = 1)
         }
 }
 
+// Ring access.  DUP: slot h lives at [h&7] and [(h&7)+8], the window t-3..t+3 is the contiguous run starting at (t-3)&7.
+// Single copy: slot h lives at [h&7]; the caller computes the 7 wrapped offsets of the window once per step.
+template <class real> LSF_DEV void ring_put(real *pos, int h, real v)
+{
+    real *d = pos + (h & (M_NSLOT - 1));
+    d[0] = v;
+    if (M_DUP) d[M_NSLOT] = v;
+}
+struct RingWin {
+    int o[7];                        // DUP: o[k] = ((t-3)&7) + k ; single copy: (t-3+k)&7
+    LSF_DEV explicit RingWin(int t)
+    {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) o[k] = M_DUP ? ((t - M_H) & (M_NSLOT - 1)) + k : ((t - M_H + k) & (M_NSLOT - 1));
+    }
+};
+
 // One cell of row `Sown` at step t: gather the 19 stencil values from the ring (orientation resolved at
 // compile time) and update.  HI: the caller knows the high-order branch applies (compile-time), else `hi`.
 template <class AR, bool FA, bool FB, bool FC, class CFG, bool HI>
@@ -361,14 +382,14 @@ LSF_DEV typename AR::real march_cell(const typename AR::real *Sown, int t, typen
 {
     typedef typename AR::real real;
     constexpr int W = CFG::W, RP = CFG::RP;
-    const real *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
+    const RingWin w(t);                                       // window t-3..t+3
     real vx[7], vy[7], vz[7];
 #pragma unroll
     for (int m = -3; m <= 3; ++m) {
-        vx[FA ? 3 - m : 3 + m] = Wn[3 + m];
+        vx[FA ? 3 - m : 3 + m] = Sown[w.o[3 + m]];
         if (m != 0) {
-            vy[FB ? 3 - m : 3 + m] = Wn[m * W + 3 + m];
-            vz[FC ? 3 - m : 3 + m] = Wn[m * RP + 3 + m];
+            vy[FB ? 3 - m : 3 + m] = Sown[m * W + w.o[3 + m]];
+            vz[FC ? 3 - m : 3 + m] = Sown[m * RP + w.o[3 + m]];
         }
     }
     vy[3] = vx[3]; vz[3] = vx[3];
@@ -388,13 +409,13 @@ LSF_DEV typename AR::real march_cell_yz(const typename AR::real *Sown, int t, ty
 {
     typedef typename AR::real real;
     constexpr int W = CFG::W, RP = CFG::RP;
-    const real *Wn = Sown + ((t - M_H) & (M_NSLOT - 1));      // window t-3..t+3 -> Wn[0..6]
+    const RingWin w(t);                                       // window t-3..t+3
     real vy[7], vz[7];
 #pragma unroll
     for (int m = -3; m <= 3; ++m) {
         if (m != 0) {
-            vy[FB ? 3 - m : 3 + m] = Wn[m * W + 3 + m];
-            vz[FC ? 3 - m : 3 + m] = Wn[m * RP + 3 + m];
+            vy[FB ? 3 - m : 3 + m] = Sown[m * W + w.o[3 + m]];
+            vz[FC ? 3 - m : 3 + m] = Sown[m * RP + w.o[3 + m]];
         }
     }
     vy[3] = phic; vz[3] = phic;
@@ -657,14 +678,14 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 #endif
                 if (pushRow[r]) p_st_peer(pOut[r] + p.push_delta, pn[r]);
                 if (pushUpRow[r]) p_st_peer(pOut[r] + p.push_up_delta, pn[r]);
-                real *d = Sown[r] + (t & (M_NSLOT - 1)); d[0] = pn[r]; d[M_NSLOT] = pn[r];
+                ring_put(Sown[r], t, pn[r]);
             }
-            if (ldLook[r]) { real *d = Sown[r] + ((t + M_LOOK) & (M_NSLOT - 1)); d[0] = la[r]; d[M_NSLOT] = la[r]; }
+            if (ldLook[r]) ring_put(Sown[r], t + M_LOOK, la[r]);
             pOut[r] += SA; pSgn[r] += SA;
         }
 #pragma unroll
         for (int r = 0; r < CFG::HR; ++r)
-            if (hdep[r]) { real *d = hS[r] + (hh[r] & (M_NSLOT - 1)); d[0] = hv[r]; d[M_NSLOT] = hv[r]; }
+            if (hdep[r]) ring_put(hS[r], hh[r], hv[r]);
         // ---- (4) publish progress every CHUNK steps -----------------------------------------
         // (all threads' stores -> CTA barrier -> one thread's gpu-scope release: cumulative, so the
         // whole tile's stores of this chunk are visible to whoever acquires the flag)
