@@ -57,8 +57,12 @@ extern "C" {
 
 /* storage / arithmetic precision of the device fields (host arrays are REAL(8) in either mode) */
 #define LSF_PREC_F64 0 /* (default) the reference's REAL(8): phi within 1e-10 of the reference, bit-exact in EXACT arithmetic */
-#define LSF_PREC_F32 1 /* optional single-precision mode: 12 B per cell update, WENO5 sweep on the FP32 pipe;
-                          contract max|phi - phi_ref| <= 1e-4 * max|phi_ref| */
+#define LSF_PREC_F32 1 /* optional single-precision mode: 12 B per cell update, WENO5 sweep on the FP32 pipe.  Contract per stage:
+                          sign search: the fp64 sign field rounded to float (signs and zeros exact); reinit:
+                          max|phi - phi_ref| <= 1e-4 * max|phi_ref| at equal sweep counts; min/max flow: exactly
+                          float(reference flow applied to the float field) -- the flow is a discontinuous map (band
+                          membership, min-or-max switch), so float rounding of its INPUT flips individual cells, which then
+                          drift by h1*L per iteration: no uniform bound against the fp64 pipeline exists for that stage */
 
 typedef struct lsf_grid lsf_grid; /* a device-resident phi(0:nx,0:ny,0:nz) plus work arrays */
 

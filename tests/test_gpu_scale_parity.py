@@ -64,7 +64,7 @@ def test_pipeline_256_against_oracle_digests(S, case):
     assert rc == 0 and n == sweeps - 1
     exact = G.download()
     assert sha(exact) == str(z["reinit_sha"]), "EXACT reinit not bit-identical: " + _explain(exact, z["reinit_s"])
-    assert np.allclose(hist, z["rms_reinit"], rtol=1e-9, atol=0)    # RMS: fixed-order parallel sum vs the reference's sequential sum over 1.7e7 terms
+    assert np.allclose(hist, z["rms_reinit"], rtol=1e-8, atol=0)    # RMS: fixed-order parallel sum vs the reference's sequential sum over 1.7e7 terms
 
     for mode in (False, None):                                     # FAST and AUTO
         S.set_arith(mode)
@@ -74,7 +74,7 @@ def test_pipeline_256_against_oracle_digests(S, case):
         fast = G.download()
         err = np.abs(fast - exact).max()
         assert err <= TOL, (mode, err)
-        assert np.allclose(hist, z["rms_reinit"], rtol=1e-9, atol=0)
+        assert np.allclose(hist, z["rms_reinit"], rtol=1e-8, atol=0)
         if mode is None:
             assert S.last_arith() == "fast", "AUTO fell back to EXACT on a well-conditioned synthetic geometry"
 
@@ -83,7 +83,7 @@ def test_pipeline_256_against_oracle_digests(S, case):
     assert rc == 0 and n == mm_iters
     mm = G.download()
     assert sha(mm) == str(z["minmax_sha"]), "min/max flow not bit-identical: " + _explain(mm, z["minmax_s"])
-    assert np.allclose(hist, z["rms_minmax"], rtol=1e-9, atol=0)
+    assert np.allclose(hist, z["rms_minmax"], rtol=1e-8, atol=0)
     nb, sb = G.narrowBand(DX)
     assert sha(nb) == str(z["nb_sha"]) and sha(sb) == str(z["sb_sha"])
     G.close()
@@ -111,7 +111,7 @@ def test_reinit_512_against_oracle_digest(S):
     assert rc == 0 and ne == sweeps - 1
     exact = G.download()
     assert sha(exact) == str(z["reinit_sha"]), "EXACT reinit not bit-identical at 512^3: " + _explain(exact, z["reinit_s"])
-    assert np.allclose(hist, z["rms_reinit"], rtol=1e-9, atol=0)
+    assert np.allclose(hist, z["rms_reinit"], rtol=1e-8, atol=0)
     S.set_arith(False)
     G.upload(phi0)
     rc, ne, hist = G.reinit(sweeps - 1, DX, h, tol=0.0)
