@@ -34,7 +34,7 @@ PUBLIC :: lsf_init, lsf_finalize, lsf_set_arith, lsf_set_sched, lsf_set_minmax_a
 PUBLIC :: lsf_slab_range, lsf_sgrid_create, lsf_sgrid_create_f32, lsf_sgrid_ipc_handle, lsf_sgrid_attach, lsf_grid_destroy
 PUBLIC :: lsf_sgrid_sync_ghosts, lsf_grid_create, lsf_grid_create_f32, lsf_grid_fill, lsf_grid_upload, lsf_grid_download
 PUBLIC :: lsf_grid_download_phiN, lsf_grid_sign_init, lsf_grid_reinit, lsf_grid_narrowband, lsf_grid_minmax
-PUBLIC :: lsf_grid_advect_nodes, lsf_grid_checksum, lsf_host_register, lsf_host_unregister
+PUBLIC :: lsf_grid_reinit_rk3, lsf_grid_advect_nodes, lsf_grid_checksum, lsf_host_register, lsf_host_unregister
 PUBLIC :: signSearch_b200, reinit_b200, reinit_nograd_b200, narrowBand_b200, minMaxFlow_b200, advectNodes_b200
 PUBLIC :: gridReinit_b200, gridMinMaxFlow_b200
 PUBLIC :: stlRead_b200, writeVti_b200, writeS3d_b200
@@ -197,6 +197,17 @@ INTERFACE
       REAL(c_double) :: rms_hist(*)            ! 0:iter
       INTEGER(c_int) :: rc
    END FUNCTION lsf_grid_reinit
+
+   ! K2' throughput mode: Jacobi WENO5 + TVD-RK3 -- NOT the reference's Gauss-Seidel algorithm (include/lsf_b200.h)
+   FUNCTION lsf_grid_reinit_rk3(g,steps,dx,dt,tol,n_exit,rms_hist) BIND(C, NAME='lsf_grid_reinit_rk3') RESULT(rc)
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: g
+      INTEGER(c_int), VALUE :: steps
+      REAL(c_double), VALUE :: dx,dt,tol
+      INTEGER(c_int) :: n_exit
+      REAL(c_double) :: rms_hist(*)
+      INTEGER(c_int) :: rc
+   END FUNCTION lsf_grid_reinit_rk3
 
    FUNCTION lsf_grid_narrowband(g,dx,phiNB,phiSB) BIND(C, NAME='lsf_grid_narrowband') RESULT(rc)
       IMPORT :: c_int, c_ptr, c_double, c_int32_t

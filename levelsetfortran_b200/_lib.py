@@ -68,6 +68,7 @@ SYMBOLS = {
     "lsf_grid_reinit": (_I, [_V, _I, _D, _D, _D, c_int_p, c_double_p]),
     "lsf_grid_narrowband": (_I, [_V, _D, c_i32_p, c_i32_p]),
     "lsf_grid_minmax": (_I, [_V, _I, _D, _D, _D, c_int_p, c_double_p]),
+    "lsf_grid_reinit_rk3": (_I, [_V, _I, _D, _D, _D, c_int_p, c_double_p]),
     "lsf_slab_range": (_I, [_I, _I, _I, c_int_p, c_int_p]),
     "lsf_sgrid_create": (_I, [C.POINTER(_V), _I, _I, _I, _I, _I]),
     "lsf_sgrid_create_f32": (_I, [C.POINTER(_V), _I, _I, _I, _I, _I]),

@@ -816,6 +816,61 @@ int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol, int 
     return reinit_core(g, iter, dx, h, tol, nullptr, nullptr, n_exit, rms_hist);
 }
 
+// K2' throughput mode (lsf_rk.cu): `steps` TVD-RK3 steps of the Jacobi WENO5 reinitialisation equation.  NOT the reference's
+// scheme (see lsf_rk.cu); offered because the north_star names it.  Per step: 3 stage kernels, the boundary block after each,
+// RMS of (phi_new - phi_old) over all points / EXIT / NaN tests as in subs.f90:902-926.
+int lsf_grid_reinit_rk3(lsf_grid *g, int steps, double dx, double dt, double tol, int *n_exit, double *rms_hist)
+{
+    if (!g) return set_error(LSF_ERR_ARG, "null grid");
+    if (g->f32 || sharded(g)) return set_error(LSF_ERR_ARG, "reinit_rk3: fp64 single-GPU grids only");
+    if (steps < 1 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "reinit_rk3: bad steps/dx");
+    if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "reinit_rk3: grid too small");
+    int rc = ensure_hist(g, steps);
+    if (rc) return rc;
+    g->sb_from_phiN = false;
+    const size_t bytes = sizeof(double) * (size_t)g->np;
+    double *phi2 = nullptr, *scratch = nullptr;
+    const long long nblk = rk_nblocks(g);
+    LSF_CUDA(cudaMalloc(&phi2, bytes));
+    cudaError_t e = cudaMalloc(&scratch, sizeof(double) * (size_t)nblk);
+    if (e != cudaSuccess) { cudaFree(phi2); return set_error(LSF_ERR_CUDA, "reinit_rk3: %s", cudaGetErrorString(e)); }
+    double *phi1 = g->phiN;
+    LSF_CUDA(cudaMemcpyAsync(g->phiS, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));       // frozen sign source
+    LSF_CUDA(cudaMemcpyAsync(phi1, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));          // boundary points of the stage buffers
+    LSF_CUDA(cudaMemcpyAsync(phi2, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));
+    LSF_CUDA(cudaMemsetAsync(g->ctrl, 0, sizeof(Ctrl), G.stream));
+    CellConst cc;
+    cc.dx = dx; cc.inv_dx = 1. / dx; cc.k12 = 1. / (12. * dx); cc.dx2 = dx * dx; cc.h = dt;
+    G.arith_run = (G.arith == LSF_ARITH_EXACT) ? LSF_ARITH_EXACT : LSF_ARITH_FAST;
+    Timer tm;
+    tm.start();
+    Ctrl hc = {0, 0, 0, 0, 0};
+    for (int n = 0; n < steps; ++n) {
+        launch_rk_stage(g, g->phi, g->phi, phi1, cc, 0., 1., scratch, nullptr);
+        launch_reinit_bc_buf(g, phi1, dx);
+        launch_rk_stage(g, phi1, g->phi, phi2, cc, 0.75, 0.25, scratch, nullptr);
+        launch_reinit_bc_buf(g, phi2, dx);
+        launch_rk_stage(g, phi2, g->phi, g->phi, cc, 1. / 3., 2. / 3., scratch, g->partial);    // interior part of the RMS -> partial[0]
+        launch_reinit_bc_rms(g, dx, 1);                                                          // boundary block + its part -> partial[1..]
+        launch_finalize(g, 1 + BC_BLOCKS, 0, tol);
+        if ((n + 1) % 16 == 0 || n == steps - 1) {
+            rc = read_ctrl(g, &hc);
+            if (rc) break;
+            if (hc.done) break;
+        }
+    }
+    cudaFree(phi2); cudaFree(scratch);
+    if (rc) return rc;
+    LSF_CUDA(cudaGetLastError());
+    G.arith_last = G.arith_run;
+    rc = tm.stop();
+    if (rc) return rc;
+    const int ne = hc.done ? hc.n_exit : steps - 1;
+    if (n_exit) *n_exit = ne;
+    if (rms_hist) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)(ne + 1), cudaMemcpyDeviceToHost));
+    return hc.done ? hc.status : LSF_OK;
+}
+
 static int narrowband_to_host(Grid *g, const double *d_phi, double dx, int32_t *nb_host, int32_t *sb_host)
 {
     int32_t *d_nb = nullptr, *d_sb = nullptr;

@@ -96,6 +96,7 @@ int set_error(int code, const char *fmt, ...);
 // lsf_kernels.cu
 void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double *gradPhi, double *gradPhiMag, double *phi = nullptr);
 void launch_reinit_bc(Grid *g, double dx);
+void launch_reinit_bc_buf(Grid *g, double *buf, double dx);
 void launch_reinit_bc_rms(Grid *g, double dx, int partial_off);
 void launch_rms(Grid *g, bool copy);
 void launch_finalize(Grid *g, int npart, int hist_off, double tol, const double *partial = nullptr);
@@ -147,6 +148,11 @@ int f32_narrowband(Grid *g, double dx, int32_t *d_nb, int32_t *d_sb);
 int f32_reinit(Grid *g, int iter, double dx, double h, double tol, int *n_exit, double *rms_hist);
 int f32_shadow_open(Grid *g, lsf_grid **shadow);
 int f32_shadow_close(Grid *g, lsf_grid *shadow, bool write_back);
+
+// lsf_rk.cu -- K2' throughput mode (Jacobi WENO5 + TVD-RK3; not the reference's algorithm)
+long long rk_nblocks(const Grid *g);
+void launch_rk_stage(Grid *g, const double *in, const double *phin, double *out, const CellConst &cc, double a, double b,
+                     double *scratch_partial, double *rms_out);
 
 // lsf_mm_march.cu
 int mm_march_prepare(Grid *g);

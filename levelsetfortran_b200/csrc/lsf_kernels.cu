@@ -106,6 +106,15 @@ __global__ void k_reinit_bc(double *__restrict__ phi, Dims dm, double dx, const 
     phi[i + dm.sx * j + dm.sxy * k] = v;
 }
 
+void launch_reinit_bc_buf(Grid *g, double *buf, double dx)      // the same block on any field of the grid's shape (lsf_rk.cu stages)
+{
+    const Dims &dm = g->dm;
+    const long long nxp = dm.nx + 1, nyp = dm.ny + 1, nzp = dm.nz + 1;
+    const long long tot = 2 * (nxp * nyp + nxp * nzp + nyp * nzp);
+    k_reinit_bc<<<(unsigned)((tot + 255) / 256), 256, 0, G.stream>>>(buf, dm, dx, g->ctrl);
+    G.n_launch++;
+}
+
 void launch_reinit_bc(Grid *g, double dx)
 {
     const Dims &dm = g->dm;

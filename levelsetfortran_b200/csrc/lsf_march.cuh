@@ -152,10 +152,10 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
 #define LSF_ASYNC_POLL 0        // 1: the predecessor flags are read one step before the chunk start that tests them
 #endif
 #ifndef LSF_RING_DUP
-#define LSF_RING_DUP 1          // 1: every ring slot is stored twice (window loads need no wrap arithmetic; 66 KB per fp64 CTA);
-#endif                          // 0: stored once, 7 wrapped slot offsets computed per step (35 KB per fp64 CTA -> 3 CTAs/SM leave the L1 its size)
+#define LSF_RING_DUP 0          // 0 (default): every ring slot stored once, 7 wrapped slot offsets computed per step (35 KB per fp64 CTA:
+#endif                          // 3 CTAs/SM leave the L1 its size); 1: stored twice, window loads need no wrap arithmetic (66 KB per CTA; round 1)
 #ifndef LSF_SPLIT_BAR
-#define LSF_SPLIT_BAR 0         // 1: split step barrier -- a thread ARRIVES after its deposits, computes the x direction of its NEXT
+#define LSF_SPLIT_BAR 1         // 1 (default): split step barrier -- a thread ARRIVES after its deposits, computes the x direction of its NEXT
 #endif                          //    cell from a register window of its own row, and only then WAITS for the other threads' deposits
 // LSF_EXP_NOSTG / LSF_EXP_NOSYNC: no global stores / no CTA barrier per step (timing experiments, results wrong)
 

@@ -1,0 +1,128 @@
+// lsf_rk.cu -- K2' (SURVEY.md section 2): the north_star's LITERAL reinitialisation scheme -- Jacobi WENO5 right-hand side with
+// TVD Runge-Kutta-3 pseudo-time stages -- as a separately reported throughput mode.
+//
+// THIS IS NOT THE REFERENCE'S ALGORITHM.  The reference (subs.f90:717-931) is forward Euler with in-place Gauss-Seidel
+// sweeps in 8 rotating raster orders; its RK scaffolding (phi1/phi2/phi3, k1..k4, set3d.f90:28,285-287) is allocated and
+// never used.  A Jacobi update differs from the reference by ~4e-4 and exits at a different iteration,
+// so nothing computed here can claim reference parity; it is checked against a Jacobi/RK3 restatement built from the
+// oracle's own per-cell `weno` / `phiSign` (tests/test_gpu_rk.py).  What it shares with the parity path: the per-cell
+// arithmetic (lsf_cell.cuh: ExactArith / FastArith), the high-order window of subs.f90:506, the extrapolation boundary
+// block (subs.f90:858-897, applied after every stage) and the RMS / EXIT / NaN tests (subs.f90:902-926, per RK step).
+//
+//   phi1 = phi + dt L(phi);   phi2 = 3/4 phi + 1/4 (phi1 + dt L(phi1));   phi <- 1/3 phi + 2/3 (phi2 + dt L(phi2))
+//   L(u) = sgn(phiS) (1 - |grad u|_Godunov-WENO5),  phiS = phi at entry (the frozen sign source, subs.f90:731)
+//
+// Kernel: no data dependence between cells of a stage, so the schedule is the plain one -- a 32 x 8 thread tile in
+// (x, y) marches along z with the 7 z-stencil values in a register queue; the x / y neighbours are read through L1
+// (the x line of a warp is one 256-B row; the y lines are the rows of the tile's other warps).  One read of u and phiS
+// and one write per cell and stage reach HBM (24 B, 32 B in stages 2 and 3 which also read phi).  fp64 WENO5 stays
+// FP64-pipe bound here as in the sweep kernel (about 260 FP64 instructions per cell, lsf_cell.cuh).
+#include "lsf_internal.cuh"
+#include "lsf_cell.cuh"
+
+namespace lsf {
+
+constexpr int RK_TX = 32, RK_TY = 8, RK_ZC = 32;
+
+template <class AR>
+__global__ void __launch_bounds__(RK_TX *RK_TY, 2)
+k_rk_stage(const double *in, const double *phin, const double *__restrict__ phiS, double *out, Dims dm, CellConst cc,
+           double a, double b, double *__restrict__ partial, const Ctrl *__restrict__ ctrl, int want_rms)
+{
+    if (ctrl->done) return;
+    const int i = 1 + blockIdx.x * RK_TX + threadIdx.x;
+    const int j = 1 + blockIdx.y * RK_TY + threadIdx.y;
+    const int k0 = 1 + blockIdx.z * RK_ZC;
+    const int k1 = min(k0 + RK_ZC - 1, dm.nz - 1);
+    double acc = 0.;
+    if (i <= dm.nx - 1 && j <= dm.ny - 1) {
+        const bool hij = (i > 3) && (i < dm.nx - 4) && (j > 3) && (j < dm.ny - 4);      // subs.f90:506
+        const long long base = i + dm.sx * j;
+        double q[7];
+#pragma unroll
+        for (int m = -3; m <= 3; ++m) {
+            const int kk = min(max(k0 + m, 0), dm.nz);
+            q[m + 3] = __ldg(in + base + dm.sxy * kk);
+        }
+        for (int k = k0; k <= k1; ++k) {
+            const long long c = base + dm.sxy * k;
+            double vx[7], vy[7];
+            if (hij) {
+#pragma unroll
+                for (int m = -3; m <= 3; ++m) {
+                    vx[m + 3] = (m == 0) ? q[3] : __ldg(in + c + m);
+                    vy[m + 3] = (m == 0) ? q[3] : __ldg(in + c + m * dm.sx);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 7; ++m) { vx[m] = 0.; vy[m] = 0.; }
+                vx[2] = __ldg(in + c - 1); vx[3] = q[3]; vx[4] = __ldg(in + c + 1);
+                vy[2] = __ldg(in + c - dm.sx); vy[3] = q[3]; vy[4] = __ldg(in + c + dm.sx);
+            }
+            const bool hi = hij && (k > 3) && (k < dm.nz - 4);
+            double g[3], gM;
+            bool sens;
+            const double e = reinit_cell<AR>(vx, vy, q, __ldg(phiS + c), hi, cc, g, gM, sens);      // u + dt sgn (1 - |grad u|)
+            const double pold = (a != 0. || want_rms) ? phin[c] : 0.;
+            const double o = (a != 0.) ? fma(a, pold, b * e) : e;
+            out[c] = o;
+            if (want_rms) { const double d = o - pold; acc = fma(d, d, acc); }
+#pragma unroll
+            for (int m = 0; m < 6; ++m) q[m] = q[m + 1];
+            q[6] = __ldg(in + base + dm.sxy * min(k + 4, dm.nz));
+        }
+    }
+    if (want_rms) {
+        __shared__ double sh[RK_TX * RK_TY];
+        const int t = threadIdx.x + RK_TX * threadIdx.y;
+        sh[t] = acc;
+        __syncthreads();
+        for (int w = RK_TX * RK_TY / 2; w > 0; w >>= 1) {
+            if (t < w) sh[t] = sh[t] + sh[t + w];
+            __syncthreads();
+        }
+        if (t == 0) partial[blockIdx.x + gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z)] = sh[0];
+    }
+}
+
+// fixed-order sum of the stage's per-block partials into ONE partial slot (k_finalize then adds the boundary part)
+__global__ void k_rk_sum(const double *__restrict__ partial, long long n, double *__restrict__ out, const Ctrl *__restrict__ ctrl)
+{
+    if (ctrl->done) return;
+    __shared__ double sh[1024];
+    double acc = 0.;
+    for (long long q = threadIdx.x; q < n; q += 1024) acc += partial[q];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+long long rk_nblocks(const Grid *g)
+{
+    const long long bx = (g->dm.nx - 1 + RK_TX - 1) / RK_TX, by = (g->dm.ny - 1 + RK_TY - 1) / RK_TY, bz = (g->dm.nz - 1 + RK_ZC - 1) / RK_ZC;
+    return bx * by * bz;
+}
+
+// one stage: out = a*phin + b*(in + dt L(in)); with want_rms the sum over the interior of (out - phin)^2 lands in rms_out[0]
+void launch_rk_stage(Grid *g, const double *in, const double *phin, double *out, const CellConst &cc, double a, double b,
+                     double *scratch_partial, double *rms_out)
+{
+    dim3 grid((g->dm.nx - 1 + RK_TX - 1) / RK_TX, (g->dm.ny - 1 + RK_TY - 1) / RK_TY, (g->dm.nz - 1 + RK_ZC - 1) / RK_ZC);
+    dim3 block(RK_TX, RK_TY);
+    const int want = rms_out != nullptr;
+    if (G.arith_run == LSF_ARITH_EXACT)
+        k_rk_stage<ExactArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want);
+    else
+        k_rk_stage<FastArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want);
+    G.n_launch++;
+    if (want) {
+        k_rk_sum<<<1, 1024, 0, G.stream>>>(scratch_partial, rk_nblocks(g), rms_out, g->ctrl);
+        G.n_launch++;
+    }
+}
+
+}  // namespace lsf

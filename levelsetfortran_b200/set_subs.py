@@ -218,6 +218,14 @@ class DeviceGrid:
         rc = check(lib().lsf_grid_reinit(self._h, int(iter), float(dx), float(h), float(tol), C.byref(n_exit), _dp(hist)))
         return rc, n_exit.value, hist[: n_exit.value + 1]
 
+    def reinitRK3(self, steps, dx, dt, tol=1.0e-5):
+        """K2' throughput mode (lsf_grid_reinit_rk3): Jacobi WENO5 + TVD-RK3 -- the north_star's literal scheme, NOT the
+        reference's Gauss-Seidel algorithm.  Returns (rc, n_exit, rms_hist[:n_exit+1])."""
+        hist = np.zeros(max(int(steps), 1))
+        n_exit = C.c_int(-1)
+        rc = check(lib().lsf_grid_reinit_rk3(self._h, int(steps), float(dx), float(dt), float(tol), C.byref(n_exit), _dp(hist)))
+        return rc, n_exit.value, hist[: n_exit.value + 1]
+
     def narrowBand(self, dx):
         nb = np.empty(self.shape, dtype=np.int32, order="F")
         sb = np.empty(self.shape, dtype=np.int32, order="F")
