@@ -110,6 +110,14 @@ int march_ntiles(const Grid *g)
 // Tilt of the ticket fronts (march_fill_order).  One GPU: anti-diagonals.  z-slabs: the downstream rank can
 // only start once this rank's sweep has crossed the slab in c, so the fronts are tilted as far as the
 // LAG between successive tiles of a column allows without starving the resident CTAs.
+// start slack of a tile over its predecessors, in steps (MarchParamsT::slack): LSF_SLACK overrides
+static int march_slack(const Grid *g)
+{
+    static const int env = getenv("LSF_SLACK") ? atoi(getenv("LSF_SLACK")) : -1;
+    if (env >= 0) return env;
+    return sharded(g) ? 0 : 16;      // z-slabs: the slack would lengthen the lag between ranks (every k flip pays it twice per rank)
+}
+
 static int march_order_tilt(const Grid *g)
 {
     if (const char *e = getenv("LSF_ORDER_TILT")) { const int m = atoi(e); if (m >= 1 && m <= 64) return m; }
@@ -214,7 +222,7 @@ void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc)
     MarchParamsF p;
     memset(&p, 0, sizeof(p));
     march_orient_grid(p, g, raster);
-    p.phi = g->phi_f; p.phiS = g->phiS_f;
+    p.phi = g->phi_f; p.phiS = g->phiS_f; p.slack = march_slack(g);
     p.cc.dx = (float)cc.dx; p.cc.inv_dx = (float)cc.inv_dx; p.cc.k12 = (float)cc.k12; p.cc.dx2 = (float)cc.dx2; p.cc.h = (float)cc.h;
     p.partial = g->partial; p.ticket = g->march_ticket; p.order = MH.d_order;
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
@@ -376,7 +384,7 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
 {
     MarchParams p;
     march_orient_grid(p, g, raster);
-    p.phi = g->phi; p.phiS = g->phiS; p.cc = cc;
+    p.phi = g->phi; p.phiS = g->phiS; p.cc = cc; p.slack = march_slack(g);
     p.partial = g->partial; p.ticket = g->march_ticket; p.order = MH.d_order;
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
     p.dbg = nullptr;

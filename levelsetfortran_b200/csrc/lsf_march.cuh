@@ -242,6 +242,9 @@ struct MarchParamsT {
                                    // (whole grid on one GPU: 1, nz-1, nz; a z-slab with ghost planes: lsf_slab.cu)
     int ntb, ntc, ntiles;
     int tend;                      // last step index
+    int slack;                     // a tile STARTS only once its two predecessors are this many steps further ahead than the data
+                                   // dependence (TB/TC + CHUNK) needs: an elastic buffer against per-chunk timing jitter, which
+                                   // otherwise couples all resident tiles like a barrier per chunk (27 % of warp time, round-2 ncu)
     CellConstT<T> cc;
     double *partial;               // per tile: sum over its cells of (new-old)^2
     unsigned *ticket;
@@ -340,6 +343,7 @@ inline void march_orient(MarchParamsT<T> &p, int nx, int ny, int nz, long long s
     p.ntc = (p.c_hi - p.c_lo + 1 + CFG::TC - 1) / CFG::TC;
     p.ntiles = p.ntb * p.ntc;
     p.tend = (nx - 1) - 1 + (CFG::TB - 1) + (CFG::TC - 1) + M_H;
+    p.slack = 0;
 }
 
 // ticket order: fronts m*J + K ascending (m = 1: anti-diagonals of the tile grid).  Topological for
@@ -533,6 +537,16 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             const int be = bq < p.ny - 1 ? bq : p.ny - 1;                       // clamp to the updated range
             const int bp = (p.edge_prev_fb != (FB ? 1 : 0)) ? p.ny - be : be;    // same physical j in the previous orientation
             wait_ge<true>(p.edge_wait + (bp - 1) / TB, p.edge_need, p.ctrl);
+        }
+        p_sync();
+    }
+
+    // start slack (see MarchParamsT::slack): same flags, a larger head start
+    if (p.slack > 0) {
+        if (tid == 0 && predB) wait_ge<false>(predB, ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + p.slack), p.ctrl);
+        if (tid == 32 % THREADS && predC) {
+            const long long need = ebase + M_BIAS + (M_CHUNK - 1 + TC + (CFG::VEC - 1) + p.slack);
+            if (predCpeer) wait_ge<true>(predC, need, p.ctrl); else wait_ge<false>(predC, need, p.ctrl);
         }
         p_sync();
     }

@@ -61,8 +61,8 @@ def test_rk3_matches_the_jacobi_restatement(lsf, oracle, exact):
 
 
 def test_rk3_is_a_different_scheme_from_the_reference(lsf, oracle):
-    """3 RK3 steps (9 Jacobi right-hand sides) vs 9 Gauss-Seidel sweeps of the reference: both reduce |grad phi| - 1, and they
-    differ by far more than the parity tolerance -- which is why this mode is reported separately."""
+    """3 RK3 steps vs 3 Gauss-Seidel sweeps of the reference (the same pseudo-time 3 dt): the two schemes differ by far more than
+    the parity tolerance (measured 4e-3 on this field) -- which is why this mode is reported separately."""
     from levelsetfortran_b200 import set_subs as S
     shape = (36, 34, 35)
     p0 = synth_field(shape, seed=5, noise=0.0)
@@ -72,9 +72,9 @@ def test_rk3_is_a_different_scheme_from_the_reference(lsf, oracle):
     rk = G.download()
     G.close()
     gs = p0.copy(order="F")
-    oracle.reinit(gs, 8, DX, 0.0014, tol=0.0)
+    oracle.reinit(gs, 2, DX, 0.0014, tol=0.0)
     d = np.abs(rk - gs).max()
-    assert 1e-7 < d < 1e-2, d
+    assert 1e-6 < d < 5e-2, d
 
 
 def test_rk3_throughput_smoke_256(lsf):
