@@ -154,6 +154,12 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
 #ifndef LSF_RING_DUP
 #define LSF_RING_DUP 0          // 0 (default): every ring slot stored once, 7 wrapped slot offsets computed per step (35 KB per fp64 CTA:
 #endif                          // 3 CTAs/SM leave the L1 its size); 1: stored twice, window loads need no wrap arithmetic (66 KB per CTA; round 1)
+#ifndef LSF_FOLD_FLAGS
+#define LSF_FOLD_FLAGS 1        // (with LSF_SPLIT_BAR) the predecessor-flag check of a chunk is folded into the step barrier before it
+#endif
+#ifndef LSF_NO_ACQ_FENCE
+#define LSF_NO_ACQ_FENCE 0      // experiment: no acquire fence after a flag that was already satisfied when pre-read
+#endif
 #ifndef LSF_SPLIT_BAR
 #define LSF_SPLIT_BAR 1         // 1 (default): split step barrier -- a thread ARRIVES after its deposits, computes the x direction of its NEXT
 #endif                          //    cell from a register window of its own row, and only then WAITS for the other threads' deposits
@@ -575,7 +581,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     real xa = 0, xb = 0;
     for (int t = -M_LOOK; t <= p.tend; ++t) {
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
-        if (t >= 0 && (t % M_CHUNK) == 0) {
+        // (SPLIT && LSF_FOLD_FLAGS: folded into the previous step's barrier instead, see below)
+        if (!(SPLIT && LSF_FOLD_FLAGS) && t >= 0 && (t % M_CHUNK) == 0) {
             // (a vector load of a -b/-c halo row fetches the predecessor's cells of up to VEC-1 later steps)
             const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + TB + (VEC - 1));
             const long long need_c = ebase + M_BIAS + (t + M_CHUNK - 1 + TC + (VEC - 1));
@@ -595,7 +602,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             if (tid == 0) dbg_wait += clock64() - tw0;
 #endif
         }
-        if (LSF_ASYNC_POLL && t + 1 >= 0 && ((t + 1) % M_CHUNK) == 0) {   // the flags the next chunk start will test: the
+        const bool chunk_next = (t + 1 >= 0) && (((t + 1) % M_CHUNK) == 0);       // the next step starts a chunk
+        if ((LSF_ASYNC_POLL || (SPLIT && LSF_FOLD_FLAGS)) && chunk_next) {          // the flags the next chunk start will test: the
             if (tid == 0 && predB) preB = p_ld_relaxed(predB);            // L2 round trip overlaps this step's arithmetic
             if (tid == 32 % THREADS && predC) preC = predCpeer ? p_ld_relaxed_sys(predC) : p_ld_relaxed(predC);
         }
@@ -708,6 +716,27 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         __syncwarp();
 #else
         if constexpr (SPLIT) {
+            if (LSF_FOLD_FLAGS && chunk_next) {
+                // The predecessor flags of the chunk that starts with step t+1 were read at the top of this step (the L2 round
+                // trip is long over).  The two polling threads settle them BEFORE they arrive: whoever passes this step's
+                // barrier knows the flags hold -- no separate CTA barrier at the chunk start.
+                const long long need_b = ebase + M_BIAS + (t + 1 + M_CHUNK - 1 + TB + (VEC - 1));
+                const long long need_c = ebase + M_BIAS + (t + 1 + M_CHUNK - 1 + TC + (VEC - 1));
+#if defined(LSF_EXP_TIMING)
+                long long tw0 = 0;
+                if (tid == 0) tw0 = clock64();
+#endif
+                if (tid == 0 && predB) {
+                    if (preB >= need_b) { if (!LSF_NO_ACQ_FENCE) p_fence_acquire(); } else wait_ge<false>(predB, need_b, p.ctrl);
+                }
+                if (tid == 32 % THREADS && predC) {
+                    if (preC >= need_c) { if (predCpeer) p_fence_sys(); else if (!LSF_NO_ACQ_FENCE) p_fence_acquire(); }
+                    else if (predCpeer) wait_ge<true>(predC, need_c, p.ctrl); else wait_ge<false>(predC, need_c, p.ctrl);
+                }
+#if defined(LSF_EXP_TIMING)
+                if (tid == 0) dbg_wait += clock64() - tw0;
+#endif
+            }
             p_bar_arrive(&sm.bar);                 // this thread's deposits of step t are done
             // advance the own-row window to step t+1 and compute that cell's x direction: registers only
             const real c0 = active[0] ? pn[0] : xw[3];
