@@ -154,6 +154,9 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
 #ifndef LSF_RING_DUP
 #define LSF_RING_DUP 0          // 0 (default): every ring slot stored once, 7 wrapped slot offsets computed per step (35 KB per fp64 CTA:
 #endif                          // 3 CTAs/SM leave the L1 its size); 1: stored twice, window loads need no wrap arithmetic (66 KB per CTA; round 1)
+#ifndef LSF_SPREAD_DUTIES
+#define LSF_SPREAD_DUTIES 1     // flag polling / progress publishing by lanes of the warps that feed no halo rows
+#endif
 #ifndef LSF_FOLD_FLAGS
 #define LSF_FOLD_FLAGS 1        // (with LSF_SPLIT_BAR) the predecessor-flag check of a chunk is folded into the step barrier before it
 #endif
@@ -445,6 +448,11 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 {
     // split step barrier + own-row register window (scalar loads, one row per thread, one sweep per launch)
     constexpr bool SPLIT = (LSF_SPLIT_BAR != 0) && CFG::R == 1 && CFG::VEC == 1 && !OV;
+    // Per-chunk duties go to warps WITHOUT halo duty (halo rows are fed by threads 0..NHALO-1): the warp that polls a flag or
+    // publishes (fence + release store) is the one every other warp of the CTA waits for at the next barrier.
+    constexpr int TID_PB = (LSF_SPREAD_DUTIES && CFG::THREADS >= 256) ? CFG::THREADS - 96 : 0;                    // polls predB
+    constexpr int TID_PC = (LSF_SPREAD_DUTIES && CFG::THREADS >= 256) ? CFG::THREADS - 64 : 32 % CFG::THREADS;    // polls predC
+    constexpr int TID_PUB = (LSF_SPREAD_DUTIES && CFG::THREADS >= 256) ? CFG::THREADS - 32 : 0;                   // publishes progress
     static_assert(!(OV && MG), "overlapped sweeps are a single-GPU schedule");
     static_assert(!OV || (CFG::VEC == 1 && CFG::R == 1), "overlapped sweeps use scalar loads, one row per thread");
     typedef typename AR::real real;
@@ -549,8 +557,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 
     // start slack (see MarchParamsT::slack): same flags, a larger head start
     if (p.slack > 0) {
-        if (tid == 0 && predB) wait_ge<false>(predB, ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + p.slack), p.ctrl);
-        if (tid == 32 % THREADS && predC) {
+        if (tid == TID_PB && predB) wait_ge<false>(predB, ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + p.slack), p.ctrl);
+        if (tid == TID_PC && predC) {
             const long long need = ebase + M_BIAS + (M_CHUNK - 1 + TC + (CFG::VEC - 1) + p.slack);
             if (predCpeer) wait_ge<true>(predC, need, p.ctrl); else wait_ge<false>(predC, need, p.ctrl);
         }
@@ -590,10 +598,10 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             long long tw0 = 0;
             if (tid == 0) tw0 = clock64();
 #endif
-            if (tid == 0 && predB) {
+            if (tid == TID_PB && predB) {
                 if (LSF_ASYNC_POLL && preB >= need_b) p_fence_acquire(); else wait_ge<false>(predB, need_b, p.ctrl);
             }
-            if (tid == 32 % THREADS && predC) {
+            if (tid == TID_PC && predC) {
                 if (LSF_ASYNC_POLL && preC >= need_c) { if (predCpeer) p_fence_sys(); else p_fence_acquire(); }
                 else if (predCpeer) wait_ge<true>(predC, need_c, p.ctrl); else wait_ge<false>(predC, need_c, p.ctrl);
             }
@@ -604,8 +612,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         }
         const bool chunk_next = (t + 1 >= 0) && (((t + 1) % M_CHUNK) == 0);       // the next step starts a chunk
         if ((LSF_ASYNC_POLL || (SPLIT && LSF_FOLD_FLAGS)) && chunk_next) {          // the flags the next chunk start will test: the
-            if (tid == 0 && predB) preB = p_ld_relaxed(predB);            // L2 round trip overlaps this step's arithmetic
-            if (tid == 32 % THREADS && predC) preC = predCpeer ? p_ld_relaxed_sys(predC) : p_ld_relaxed(predC);
+            if (tid == TID_PB && predB) preB = p_ld_relaxed(predB);            // L2 round trip overlaps this step's arithmetic
+            if (tid == TID_PC && predC) preC = predCpeer ? p_ld_relaxed_sys(predC) : p_ld_relaxed(predC);
         }
         p_emu_hook(tid == 0 && t == 6);
         // ---- (1) issue the global loads of this step --------------------------------------
@@ -726,10 +734,10 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
                 long long tw0 = 0;
                 if (tid == 0) tw0 = clock64();
 #endif
-                if (tid == 0 && predB) {
+                if (tid == TID_PB && predB) {
                     if (preB >= need_b) { if (!LSF_NO_ACQ_FENCE) p_fence_acquire(); } else wait_ge<false>(predB, need_b, p.ctrl);
                 }
-                if (tid == 32 % THREADS && predC) {
+                if (tid == TID_PC && predC) {
                     if (preC >= need_c) { if (predCpeer) p_fence_sys(); else if (!LSF_NO_ACQ_FENCE) p_fence_acquire(); }
                     else if (predCpeer) wait_ge<true>(predC, need_c, p.ctrl); else wait_ge<false>(predC, need_c, p.ctrl);
                 }
@@ -751,7 +759,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             p_bar_wait(&sm.bar, bar_phase++);      // every thread's deposits of step t are visible
         } else p_sync();
 #endif
-        if (pub && tid == 0) {
+        if (pub && tid == TID_PUB) {
             p_fence(); p_st_release(mine, ebase + M_BIAS + t);
             if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + t); }
         }
