@@ -122,7 +122,10 @@ static int march_slack(const Grid *g)
 static int march_order_tilt(const Grid *g)
 {
     if (const char *e = getenv("LSF_ORDER_TILT")) { const int m = atoi(e); if (m >= 1 && m <= 64) return m; }
-    return sharded(g) ? 8 : 1;
+    // round 2 (session 7, one GPU, 1024^3): tilt 1 / 2 / 4 / 8 cost 0 / 1 / 3.3 / 7.6 % at 2 CTAs/SM and 0 / 1 / 5 / 16 % at 3 CTAs/SM:
+    // the tilt caps the number of tiles that can run concurrently at (tile length / lag) x (ntc / m) = 44 x 64/m.  With 2 CTAs/SM
+    // (296 CTAs) the first ~1060 steps hand out the tickets of the J = 0 column chain fast enough for m = 4.
+    return sharded(g) ? 4 : 1;
 }
 
 template <class T>
@@ -229,7 +232,8 @@ void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc)
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
     if (sharded(g)) march_fill_slab(p, g, g->phi_f);
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
-    static const int occ = getenv("LSF_OCC32_RUN") ? atoi(getenv("LSF_OCC32_RUN")) : LSF_OCC32;   // experiments: fewer resident CTAs
+    static const int occ_env32 = getenv("LSF_OCC32_RUN") ? atoi(getenv("LSF_OCC32_RUN")) : 0;   // experiments: fewer resident CTAs
+    const int occ = occ_env32 > 0 ? occ_env32 : (sharded(g) ? 2 : LSF_OCC32);                   // z-slabs: see launch_reinit_sweep_march
     const int ncta = p.ntiles < occ * G.num_sms ? p.ntiles : occ * G.num_sms;
     march_kernel_f32(p.fa, p.fb, p.fc, sharded(g))<<<ncta, CFG32::THREADS, sizeof(MarchSmem<CFG32>), G.stream>>>(p);
     G.n_launch++;
@@ -406,7 +410,7 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
     static const int occ_env = getenv("LSF_OCC_RUN") ? atoi(getenv("LSF_OCC_RUN")) : 0;
     int occ = (G.arith_run == LSF_ARITH_EXACT) ? MarchOcc<ExactArith>::v : MarchOcc<FastArith>::v;
     if (occ_env > 0) occ = occ_env < occ ? occ_env : occ;
-    else if (p.ntiles < 2048 && occ > 2) occ = 2;
+    else if ((p.ntiles < 2048 || sharded(g)) && occ > 2) occ = 2;      // z-slabs: the tilted ticket order cannot feed more CTAs
     const int ncta = p.ntiles < occ * G.num_sms ? p.ntiles : occ * G.num_sms;
     MarchKernel kern = (G.arith_run == LSF_ARITH_EXACT) ? march_kernel<ExactArith>(p.fa, p.fb, p.fc, sharded(g))
                                                     : march_kernel<FastArith>(p.fa, p.fb, p.fc, sharded(g));
