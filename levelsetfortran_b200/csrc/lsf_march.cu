@@ -125,7 +125,10 @@ static int march_order_tilt(const Grid *g)
     // round 2 (session 7, one GPU, 1024^3): tilt 1 / 2 / 4 / 8 cost 0 / 1 / 3.3 / 7.6 % at 2 CTAs/SM and 0 / 1 / 5 / 16 % at 3 CTAs/SM:
     // the tilt caps the number of tiles that can run concurrently at (tile length / lag) x (ntc / m) = 44 x 64/m.  With 2 CTAs/SM
     // (296 CTAs) the first ~1060 steps hand out the tickets of the J = 0 column chain fast enough for m = 4.
-    return sharded(g) ? 4 : 1;
+    // z-slabs: the downstream rank lags by (ntc-1) fronts = (ntc-1) ntb/m tickets (measured L = 7.5 ms at m = 4, 4.8 ms at m = 8,
+    // 1024^3 per rank) and every k flip costs (P-1) L per sweep cycle: 8 T(m) + 2 (P-1) L(m) is smallest at m = 4 for P <= 3, m = 8 beyond
+    if (!sharded(g)) return 1;
+    return g->sg.nranks <= 3 ? 4 : 8;
 }
 
 template <class T>
