@@ -704,7 +704,7 @@ int lsf_grid_destroy(lsf_grid *g)
     cudaFree(g->phiS_f);
     cudaFree(g->phiS); cudaFree(g->lap); cudaFree(g->mask);
     cudaFree(g->partial); cudaFree(g->hist); cudaFree(g->ctrl);
-    cudaFree(g->march_ticket); cudaFree(g->march_progress);
+    cudaFree(g->march_ticket); cudaFree(g->march_progress); cudaFree(g->march_colnext);
     cudaFree(g->ov_progress); cudaFree(g->ov_partial); cudaFree(g->ov_snap);
     cudaFree(g->mml_list); cudaFree(g->mml_unres); cudaFree(g->mml_work); cudaFree(g->mml_work_count);
     free(g);

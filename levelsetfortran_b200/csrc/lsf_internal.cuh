@@ -18,6 +18,8 @@ struct lsf_grid {
     lsf::Ctrl *ctrl;          // device control block
     // march schedule state (lsf_march.cu)
     unsigned int *march_ticket;   // tile ticket counter
+    int *march_colnext;           // dynamic tile scheduler: next tile row of every tile column (lsf_march.cuh: march_pick)
+    int march_colnext_cap;
     long long *march_progress;    // per column-tile progress, epoch-encoded
     int march_tiles_cap;
     long long march_epoch;

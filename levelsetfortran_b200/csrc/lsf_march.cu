@@ -110,6 +110,15 @@ int march_ntiles(const Grid *g)
 // Tilt of the ticket fronts (march_fill_order).  One GPU: anti-diagonals.  z-slabs: the downstream rank can
 // only start once this rank's sweep has crossed the slab in c, so the fronts are tilted as far as the
 // LAG between successive tiles of a column allows without starving the resident CTAs.
+// Dynamic tile scheduler (march_pick, lsf_march.cuh) unless LSF_STATIC_TICKETS=1: the per-column counters are zeroed before the sweep.
+static int *march_colnext_for_sweep(Grid *g, int ntb)
+{
+    static const bool stat = getenv("LSF_STATIC_TICKETS") != nullptr && atoi(getenv("LSF_STATIC_TICKETS")) != 0;
+    if (stat) return nullptr;
+    cudaMemsetAsync(g->march_colnext, 0, sizeof(int) * (size_t)ntb, G.stream);
+    return g->march_colnext;
+}
+
 // start slack of a tile over its predecessors, in steps (MarchParamsT::slack): LSF_SLACK overrides
 static int march_slack(const Grid *g)
 {
@@ -146,6 +155,12 @@ int march_prepare(Grid *g)
     if (sharded(g) && p.ntb > SLAB_MAX_NTB) return set_error(LSF_ERR_ARG, "march: more than %d tile columns on a sharded grid", SLAB_MAX_NTB);
     const int tilt = march_order_tilt(g);
     if (!g->march_ticket) LSF_CUDA(cudaMalloc(&g->march_ticket, sizeof(unsigned)));
+    if (g->march_colnext_cap < p.ntb) {
+        cudaFree(g->march_colnext);
+        g->march_colnext = nullptr; g->march_colnext_cap = 0;
+        LSF_CUDA(cudaMalloc(&g->march_colnext, sizeof(int) * (size_t)p.ntb));
+        g->march_colnext_cap = p.ntb;
+    }
     if (g->march_tiles_cap < p.ntiles) {
         cudaFree(g->march_progress);
         g->march_progress = nullptr;
@@ -235,6 +250,7 @@ void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc)
     p.progress = g->march_progress; p.epoch = ++g->march_epoch; p.ctrl = g->ctrl;
     if (sharded(g)) march_fill_slab(p, g, g->phi_f);
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
+    p.col_next = march_colnext_for_sweep(g, p.ntb);
     static const int occ_env32 = getenv("LSF_OCC32_RUN") ? atoi(getenv("LSF_OCC32_RUN")) : 0;   // experiments: fewer resident CTAs
     const int occ = occ_env32 > 0 ? occ_env32 : (sharded(g) ? 2 : LSF_OCC32);                   // z-slabs: see launch_reinit_sweep_march
     const int ncta = p.ntiles < occ * G.num_sms ? p.ntiles : occ * G.num_sms;
@@ -408,6 +424,7 @@ void launch_reinit_sweep_march(Grid *g, int raster, const CellConst &cc)
     }
 #endif
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
+    p.col_next = march_colnext_for_sweep(g, p.ntb);
     // resident CTAs per SM at RUN time: a sweep over few tiles is bound by the dependence chain between tiles, not by throughput,
     // and then fewer CTAs per SM (each progressing faster) finish sooner -- measured at 512^3: 2 CTAs/SM 22.1, 3 CTAs/SM 19.0 Gcell/s
     static const int occ_env = getenv("LSF_OCC_RUN") ? atoi(getenv("LSF_OCC_RUN")) : 0;

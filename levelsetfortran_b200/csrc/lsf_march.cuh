@@ -99,6 +99,13 @@ LSF_DEV void p_st_release_sys(long long *p, long long v)
 }
 LSF_DEV void p_st_peer(double *p, double v) { __stcg(p, v); }
 LSF_DEV void p_st_peer(float *p, float v) { __stcg(p, v); }
+LSF_DEV int p_ld_relaxed_i32(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+LSF_DEV bool p_cas_i32(int *p, int expect, int desired) { return atomicCAS(p, expect, desired) == expect; }
 LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 // split-phase CTA barrier (mbarrier in shared memory): every warp arrives once per phase (one elected lane after a
 // __syncwarp, release), a waiter spins on the phase parity (acquire).  Between arrive and wait a thread may do anything
@@ -258,6 +265,8 @@ struct MarchParamsT {
     double *partial;               // per tile: sum over its cells of (new-old)^2
     unsigned *ticket;
     const int *order;              // ticket -> J | (K << 16)
+    int *col_next;                 // [ntb] dynamic tile scheduler (march_pick): next tile row K of every tile column, zero before the
+                                   // sweep; null: static tickets in `order`
     long long *progress;           // per tile (J + ntb*K)
     long long epoch;               // progress values are epoch*2^32 + step + BIAS
     Ctrl *ctrl;
@@ -353,6 +362,7 @@ inline void march_orient(MarchParamsT<T> &p, int nx, int ny, int nz, long long s
     p.ntiles = p.ntb * p.ntc;
     p.tend = (nx - 1) - 1 + (CFG::TB - 1) + (CFG::TC - 1) + M_H;
     p.slack = 0;
+    p.col_next = nullptr;
 }
 
 // ticket order: fronts m*J + K ascending (m = 1: anti-diagonals of the tile grid).  Topological for
@@ -842,6 +852,43 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     p_sync();
 }
 
+// Dynamic tile scheduler (one lane per CTA).  A static ticket order hands a CTA a tile whether or not that tile can start, and
+// a CTA holding a tile whose predecessors are not far enough ahead just spins -- which is what makes a steep ticket order (needed
+// on z-slabs so that the sweep reaches the downstream rank quickly) expensive.  Here every tile column J keeps the index of its
+// next unstarted tile, col_next[J]; a free CTA takes the READY tile of the lowest column -- ready: both predecessors (and, on the
+// first tile row of a z-slab, the upstream rank) have published the progress the tile's first chunk needs -- by a compare-and-swap
+// on the column's counter.  Lowest column first is column-major priority: the last tile row, which the downstream rank waits for,
+// completes as early as the dependences allow, and no CTA ever holds a tile that cannot run.  Deadlock-free: a tile is only taken
+// when its predecessors are running or done.  Returns J | (K << 16), or -1 when every column is finished.
+template <class CFG, bool MG, class T>
+LSF_DEV int march_pick(const MarchParamsT<T> &p, int &jlo)
+{
+    constexpr int TB = CFG::TB, TC = CFG::TC;
+    const long long ebase = p.epoch << 32;
+    const long long need_b = ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + p.slack);
+    const long long need_c = ebase + M_BIAS + (M_CHUNK - 1 + TC + (CFG::VEC - 1) + p.slack);
+    long long spins = 0;
+    for (;;) {
+        bool all_done = true;
+        for (int J = jlo; J < p.ntb; ++J) {
+            const int K = p_ld_relaxed_i32(p.col_next + J);
+            if (K >= p.ntc) { if (all_done) jlo = J + 1; continue; }
+            all_done = false;
+            if (J > 0 && p_ld_relaxed(p.progress + ((J - 1) + p.ntb * K)) < need_b) continue;
+            bool ready = true;
+            if (K > 0) ready = p_ld_relaxed(p.progress + (J + p.ntb * (K - 1))) >= need_c;
+            else if (MG && p.in_progress) ready = p_ld_relaxed_sys(p.in_progress + J) >= need_c;
+            if (ready && p_cas_i32(p.col_next + J, K, K + 1)) return J | (K << 16);
+        }
+        if (all_done) return -1;
+        p_sleep();
+        if (((++spins) & 1023) == 0) {
+            if (*(volatile int *)&p.ctrl->status == M_ERR_TIMEOUT) return -1;
+            if (spins > M_SPIN_LIMIT) { *(volatile int *)&p.ctrl->status = M_ERR_TIMEOUT; return -1; }
+        }
+    }
+}
+
 // Persistent CTA: take tickets until the tile list is exhausted.
 template <class AR, bool FA, bool FB, bool FC, class CFG, bool MG = true, bool OV = false>
 LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> &sm, const int tid)
@@ -859,13 +906,14 @@ LSF_DEV void march_cta(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG> 
         }
         p_sync();
     }
+    int jlo = 0;                     // first tile column that still has unstarted tiles (march_pick)
     for (;;) {
-        if (tid == 0) sm.tile = (int)p_ticket(p.ticket);
+        if (tid == 0) sm.tile = p.col_next ? march_pick<CFG, MG>(p, jlo) : (int)p_ticket(p.ticket);
         p_sync();
         const int tk = sm.tile;
         p_sync();
-        if (tk >= p.ntiles) break;
-        const int jk = p.order[tk];
+        if (p.col_next ? tk < 0 : tk >= p.ntiles) break;
+        const int jk = p.col_next ? tk : p.order[tk];
         march_tile<AR, FA, FB, FC, CFG, MG, OV>(p, sm, tid, jk & 0xffff, jk >> 16, bar_phase);
     }
 }

@@ -23,6 +23,11 @@ inline long long p_ld_relaxed(const long long *p) { return __atomic_load_n(p, __
 inline void p_fence_acquire() { __atomic_thread_fence(__ATOMIC_ACQ_REL); }
 inline void p_st_release(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void p_sleep() { sched_yield(); }
+inline int p_ld_relaxed_i32(const int *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline bool p_cas_i32(int *p, int expect, int desired)
+{
+    return __atomic_compare_exchange_n(p, &expect, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+}
 // test hook: stall a CTA close to the end of its tile, so that ranks / tiles that are allowed to run ahead
 // really do (widens the hazard windows the flag protocol has to close)
 extern int emu_stall_us;

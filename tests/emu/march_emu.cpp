@@ -14,6 +14,20 @@
 #include "../../levelsetfortran_b200/csrc/lsf_mm_list.cuh"
 
 namespace lsf { thread_local EmuCta *emu_cta = nullptr; int emu_stall_us = 0; }
+// dynamic tile scheduler (march_pick) instead of static tickets: switched on by the test harness
+static int emu_dynamic = 0;
+extern "C" void emu_set_dynamic(int on) { emu_dynamic = on; }
+#include <deque>
+#include <mutex>
+static std::deque<std::vector<int>> emu_colnext_store;
+static std::mutex emu_colnext_mu;
+static int *emu_colnext(int ntb)
+{
+    if (!emu_dynamic) return nullptr;
+    std::lock_guard<std::mutex> lk(emu_colnext_mu);
+    emu_colnext_store.emplace_back((size_t)ntb, 0);
+    return emu_colnext_store.back().data();
+}
 extern "C" void emu_set_stall(int us) { lsf::emu_stall_us = us; }
 using namespace lsf;
 
@@ -50,6 +64,7 @@ extern "C" double emu_march_sweep(double *phi, const double *phiS, int nx, int n
     Ctrl ctrl = {0, 0, 0, 0, 0};
     p.partial = partial.data(); p.order = order.data(); p.progress = progress.data();
     p.ticket = &ticket; p.ctrl = &ctrl; p.epoch = 1;
+    p.col_next = emu_colnext(p.ntb);
     if (ncta > p.ntiles) ncta = p.ntiles;
     std::vector<Smem> sm(ncta);
     std::vector<EmuCta> ctas(ncta);
@@ -110,6 +125,7 @@ extern "C" double emu_march_sweep_slabs(double *phi, const double *phiS, int nx,
         march_fill_order(p.ntb, p.ntc, order[r].data(), order_m);
         p.partial = partial[r].data(); p.order = order[r].data(); p.progress = progress[r].data();
         p.ticket = &ticket[r]; p.ctrl = &ctrl[r]; p.epoch = 1;
+        p.col_next = emu_colnext(p.ntb);
         const int up = p.fc ? r + 1 : r - 1, down = p.fc ? r - 1 : r + 1;
         if (up >= 0 && up < nranks) p.in_progress = sync[r].in_progress;
         if (down >= 0 && down < nranks) {
@@ -193,6 +209,7 @@ static void *rank_main(void *v)
         Ctrl ctrl = {0, 0, 0, 0, 0};
         p.partial = partial.data(); p.order = order.data(); p.progress = progress.data();
         p.ticket = &ticket; p.ctrl = &ctrl; p.epoch = n + 1;
+        p.col_next = emu_colnext(p.ntb);
         const int up = p.fc ? r + 1 : r - 1, down = p.fc ? r - 1 : r + 1;
         const int side_up = p.fc ? 1 : 0, side_down = p.fc ? 0 : 1;      // which of MY sides that neighbour is on
         if (up >= 0 && up < nranks) {
@@ -489,6 +506,7 @@ extern "C" double emu_march_sweep_f32(float *phi, const float *phiS, int nx, int
     Ctrl ctrl = {0, 0, 0, 0, 0};
     p.partial = partial.data(); p.order = order.data(); p.progress = progress.data();
     p.ticket = &ticket; p.ctrl = &ctrl; p.epoch = 1;
+    p.col_next = emu_colnext(p.ntb);
     if (ncta > p.ntiles) ncta = p.ntiles;
     constexpr int NT = CFGF::THREADS;
     std::vector<SmemF> sm(ncta);
@@ -618,6 +636,7 @@ extern "C" double emu_march_sweep_slabs_f32(float *phi, const float *phiS, int n
         march_fill_order(p.ntb, p.ntc, order[r].data(), order_m);
         p.partial = partial[r].data(); p.order = order[r].data(); p.progress = progress[r].data();
         p.ticket = &ticket[r]; p.ctrl = &ctrl[r]; p.epoch = 1;
+        p.col_next = emu_colnext(p.ntb);
         const int up = p.fc ? r + 1 : r - 1, down = p.fc ? r - 1 : r + 1;
         if (up >= 0 && up < nranks) p.in_progress = sync[r].in_progress;
         if (down >= 0 && down < nranks) {

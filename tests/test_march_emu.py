@@ -30,6 +30,7 @@ def emu(request):
                            "-std=c++17", "-Wno-unknown-pragmas", f"-DLSF_ROWS={request.param}", "-o", so,
                            os.path.join(EMU_DIR, "march_emu.cpp")])
     L = C.CDLL(so)
+    L.emu_set_dynamic(1)          # the production scheduler: tiles picked dynamically (march_pick), not from a static ticket order
     L.emu_march_sweep.restype = C.c_double
     L.emu_march_sweep.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
     L.emu_march_sweep_slabs.restype = C.c_double
