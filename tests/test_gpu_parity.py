@@ -390,3 +390,44 @@ def test_one_sweep_vs_oracle_128(S, oracle):
     _mode(S, False, False)
     S.reinit(c, None, None, 127, 127, 127, 0, DX, 0.0014)
     assert np.abs(a - c).max() < 1e-14
+
+
+def test_grid_checksum_matches_numpy_and_is_partition_independent(S):
+    """lsf_grid_checksum: sum of bits(phi(q))*(2q+1) mod 2^64 and xor of the bit patterns over the grid's points -- the digest
+    bench.py prints for N = 1, 2, 4, 8 to show that the sharded fields are bit-identical."""
+    shape = (23, 17, 19)
+    phi = synth_field(shape, seed=31)
+    G = S.DeviceGrid(shape[0] - 1, shape[1] - 1, shape[2] - 1)
+    G.upload(phi)
+    s, x = G.checksum()
+    G.close()
+    bits = phi.reshape(-1, order="F").view(np.uint64)
+    q = np.arange(bits.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        want_s = int((bits * (np.uint64(2) * q + np.uint64(1))).sum(dtype=np.uint64))
+    want_x = int(np.bitwise_xor.reduce(bits))
+    assert (s, x) == (want_s, want_x)
+    # the slabs of any cut along k add / xor up to the same digest (what the ranks of a sharded grid compute)
+    sxy = shape[0] * shape[1]
+    parts = [(0, 7), (7, 12), (12, 19)]
+    with np.errstate(over="ignore"):
+        tot = sum(int((bits[a * sxy:b * sxy] * (np.uint64(2) * q[a * sxy:b * sxy] + np.uint64(1))).sum(dtype=np.uint64)) for a, b in parts)
+    assert tot % (1 << 64) == want_s
+
+
+def test_host_register_roundtrip(S, lsf):
+    """lsf_host_register / lsf_host_unregister: page-locking a caller-owned array does not change results"""
+    import ctypes as C
+    from levelsetfortran_b200 import _lib
+    shape = (20, 18, 16)
+    a = synth_field(shape, seed=8)
+    b = a.copy(order="F")
+    _lib.check(_lib.lib().lsf_host_register(a.ctypes.data, a.nbytes))
+    try:
+        S.set_arith(True)
+        S.reinit(a, None, None, 19, 17, 15, 5, DX, 0.0014)
+    finally:
+        _lib.check(_lib.lib().lsf_host_unregister(a.ctypes.data))
+    S.reinit(b, None, None, 19, 17, 15, 5, DX, 0.0014)
+    S.set_arith(None)
+    assert np.array_equal(a, b)
