@@ -202,7 +202,8 @@ def workload_config(n, world, f32, ntri=None):
     return {"workload": f"BASELINE config {'4' if world == 1 else '5'}: synthetic torus+cube STL on ONE {n}x{n}x{n * world} "
                         f"{'fp32-mode' if f32 else 'fp64'} grid ({n}^3 points per GPU), reinit-only, one step = {SWEEPS_PER_STEP} "
                         "Gauss-Seidel raster sweeps (+BC+RMS each)",
-            "global_grid": [n, n, n * world], "grid_per_gpu": [n, n, n], "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX}
+            "global_grid": [n, n, n * world], "grid_per_gpu": [n, n, n], "sweeps_per_step": SWEEPS_PER_STEP, "dx": DX,
+            "timed_region": "the K steps are 8K consecutive sweeps of one reinit call"}
 
 
 def run_reference(args):
@@ -288,25 +289,25 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        rc, n_exit, hist = G.reinit(SWEEPS_PER_STEP - 1, DX, h, tol=0.0)     # tol 0: never EXITs early
-        assert rc == 0 and n_exit == SWEEPS_PER_STEP - 1, (rc, n_exit)
+    def steps(k):
+        """k steps = k raster cycles = 8k consecutive sweeps of ONE reinit call (the reference's reinit runs thousands of
+        sweeps per call, subs.f90:735; on z-slabs every call boundary drains the Gauss-Seidel pipeline once)"""
+        rc, n_exit, hist = G.reinit(SWEEPS_PER_STEP * k - 1, DX, h, tol=0.0)     # tol 0: never EXITs early
+        assert rc == 0 and n_exit == SWEEPS_PER_STEP * k - 1, (rc, n_exit)
         return hist
 
-    for _ in range(args.warmup):
-        step()
+    def step():
+        return steps(1)
+
+    if args.warmup > 0:
+        steps(args.warmup)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     wall0 = time.perf_counter()
-    dev_ms = sweep_ms = 0.0
-    n_sweeps = launches = 0
-    hist = None
-    for _ in range(args.steps):
-        hist = step()
-        ms, nl = _lib.last_timing()
-        sm, ns = _lib.last_sweep_timing()
-        dev_ms += ms; launches += nl; sweep_ms += sm; n_sweeps += ns
+    hist = steps(args.steps)
+    dev_ms, launches = _lib.last_timing()
+    sweep_ms, n_sweeps = _lib.last_sweep_timing()
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop()

@@ -113,11 +113,12 @@ int march_ntiles(const Grid *g)
 // Dynamic tile scheduler (march_pick, lsf_march.cuh) unless LSF_STATIC_TICKETS=1: the per-column counters are zeroed before the sweep.
 static int *march_colnext_for_sweep(Grid *g, int ntb)
 {
-    // default: z-slabs only.  On one GPU the anti-diagonal static order is as good or better (1024^3: 31.2 static / 30.2 dynamic;
-    // 512^3: 22.1 / 20.7; round 2, session 8) -- lowest-column priority starts every tile right at the heels of its predecessors.
-    static const int env = getenv("LSF_STATIC_TICKETS") ? atoi(getenv("LSF_STATIC_TICKETS")) : -1;
-    const bool stat = env >= 0 ? env != 0 : !sharded(g);
-    if (stat) return nullptr;
+    // Opt-in (LSF_STATIC_TICKETS=0).  Measured, round 2: one GPU 1024^3 31.2 static / 30.2 dynamic, 512^3 22.1 / 20.7 (fp32 512^3:
+    // 17.9 / 22.1); two z-slabs 53.5 (static, tilt 4) / 53.0 (dynamic): lowest-column priority starts every tile right at the heels
+    // of its predecessors, which costs what the steep static order costs, and the lag at the END of a sweep is a full column chain
+    // either way.  Correct (emulation + 72 GPU tests + the 2-GPU parity worker ran with it), not faster: the static order stays.
+    static const int env = getenv("LSF_STATIC_TICKETS") ? atoi(getenv("LSF_STATIC_TICKETS")) : 1;
+    if (env != 0) return nullptr;
     cudaMemsetAsync(g->march_colnext, 0, sizeof(int) * (size_t)ntb, G.stream);
     return g->march_colnext;
 }
