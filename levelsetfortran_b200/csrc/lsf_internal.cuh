@@ -116,6 +116,10 @@ void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_s
                       const int32_t *d_surfElem, int nElem, double *d_cen,
                       int im, int ip, int jm, int jp, int km, int kp);
 
+// lsf_sign_bvh.cu
+bool launch_sign_search_bvh(Grid *g, const double xLo[3], double dx, const double *d_surfX, int nNode, const int32_t *d_surfElem,
+                            int nElem, const double *d_cen, int im, int jm, int km, int ni, int nj, int nk);
+
 inline long long global_cells(const Grid *g) { return (long long)g->dm.nx * g->dm.ny * g->sg.NZ; }
 inline bool sharded(const Grid *g) { return g->sg.nranks > 1; }
 

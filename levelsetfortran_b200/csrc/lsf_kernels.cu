@@ -629,6 +629,10 @@ void launch_sign_init(Grid *g, const double xLo[3], double dx, const double *d_s
     const int ni = ip - im + 1, nj = jp - jm + 1, nk = kp - km + 1;
     const long long npts = (long long)ni * nj * nk;
     const bool brute = getenv("LSF_SIGN_BRUTE") != nullptr;            // cross-check: the un-culled kernel
+    const bool tiled = getenv("LSF_SIGN_TILED") != nullptr;            // cross-check: round-1 kernel (exact culling, linear scans)
+    if (!brute && !tiled && nElem > 64 &&
+        launch_sign_search_bvh(g, xLo, dx, d_surfX, nNode, d_surfElem, nElem, d_cen, im, jm, km, ni, nj, nk))
+        return;                                                        // production: tree walks instead of the two linear scans
     const long long nbi = (ni + SB_I - 1) / SB_I, nbj = (nj + SB_J - 1) / SB_J, nbk = (nk + SB_K - 1) / SB_K;
     if (brute || nbi * nbj * nbk > 0x7fffffffLL)
         k_sign_search<<<(unsigned)((npts + SIGN_TILE - 1) / SIGN_TILE), SIGN_TILE, 0, G.stream>>>(
