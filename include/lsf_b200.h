@@ -156,8 +156,9 @@ int lsf_stl_dedup(const float *tri, int ntri, float *nodes, int32_t *surfElem, i
 int lsf_grid_create(lsf_grid **g, int nx, int ny, int nz);
 /* fp32 mode: phi is stored as float on the device; the same lsf_grid_* calls apply (upload / download convert
  * from / to the caller's REAL(8) arrays).  reinit runs natively in fp32; sign search and min/max flow -- a
- * negligible share of a run -- execute the fp64 kernels on a transient fp64 copy and round the result.
- * Not available: lsf_grid_download_phiN; on sharded fp32 grids (lsf_sgrid_create_f32) also min/max and node projection. */
+ * negligible share of a run -- execute the fp64 kernels on a transient fp64 copy and round the result (node projection reads
+ * that copy).  On a sharded fp32 grid (lsf_sgrid_create_f32) the transient copy is a sharded fp64 grid that the ranks create
+ * and connect among themselves inside the call (16 B per point while it lives).  Not available: lsf_grid_download_phiN. */
 int lsf_grid_create_f32(lsf_grid **g, int nx, int ny, int nz);
 int lsf_grid_is_f32(lsf_grid *g);
 int lsf_grid_destroy(lsf_grid *g);
@@ -188,7 +189,9 @@ int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol,
  * stage) and RMS / EXIT / NaN tests (per step).  fp64, single GPU.  n_exit: 0-based index of the last executed step. */
 int lsf_grid_reinit_rk3(lsf_grid *g, int steps, double dx, double dt, double tol, int *n_exit, double *rms_hist);
 /* lsf_advect_nodes on the resident phi; phiSB is the band the reference holds at that point: that of the field the
- * last narrowBand call saw (phi, or the previous iterate after a tolerance EXIT of lsf_grid_minmax). */
+ * last narrowBand call saw (phi, or the previous iterate after a tolerance EXIT of lsf_grid_minmax).  On a sharded grid every
+ * rank passes the SAME (whole) node list and receives the same result: each rank projects all nodes, gathering phi from the
+ * slabs of whichever ranks a node crosses (peer loads over NVLink); xLo is the origin of the GLOBAL grid. */
 int lsf_grid_advect_nodes(lsf_grid *g, const double xLo[3], double dx, double *surfXX, int nSurfNode,
                           double *phiSurf, double *gradPhiSurf, int iter, long long *n_moves);
 
@@ -196,7 +199,7 @@ int lsf_grid_advect_nodes(lsf_grid *g, const double xLo[3], double dx, double *s
  * The reference is serial ("Parallel version is in the works", README.md:17).  Here phi(0:nx,0:ny,0:nz) is
  * cut along k -- the slowest index, so a slab is a contiguous range of the reference array -- into one
  * slab per process/GPU.  A sharded grid is used through the same lsf_grid_* calls as a whole one
- * (sign_init, reinit, narrowband, fill, upload, download): all ranks make the same calls in the same order
+ * (sign_init, reinit, narrowband, minmax, advect_nodes, fill, upload, download): all ranks make the same calls in the same order
  * (SPMD), host arrays hold the rank's OWNED planes k0..k1-1 only, n_exit / rms_hist are identical on all
  * ranks, and the result is bit-identical to the single-GPU one (the in-place Gauss-Seidel sweeps run as a
  * software pipeline along k: peer stores over NVLink from inside the sweep kernels, no collective on the
@@ -204,8 +207,7 @@ int lsf_grid_advect_nodes(lsf_grid *g, const double xLo[3], double dx, double *s
  * handles (MPI_Allgather / torch.distributed.all_gather) and every rank attaches. */
 int lsf_slab_range(int nz, int nranks, int rank, int *k0, int *k1);   /* owned planes [k0, k1) of rank */
 int lsf_sgrid_create(lsf_grid **g, int nx, int ny, int nz, int rank, int nranks);   /* nz: GLOBAL extent */
-int lsf_sgrid_create_f32(lsf_grid **g, int nx, int ny, int nz, int rank, int nranks);   /* the same slab in the optional fp32 mode:
-                                            fill, upload, download, sign_init, reinit, narrowband (no min/max, no node projection) */
+int lsf_sgrid_create_f32(lsf_grid **g, int nx, int ny, int nz, int rank, int nranks);   /* the same slab in the optional fp32 mode */
 int lsf_sgrid_ipc_handle(lsf_grid *g, void *handle /* LSF_IPC_HANDLE_BYTES */);
 int lsf_sgrid_attach(lsf_grid *g, const void *handles /* nranks * LSF_IPC_HANDLE_BYTES, rank order */);
 int lsf_sgrid_sync_ghosts(lsf_grid *g);   /* refresh the ghost planes after writing phi through lsf_grid_device_ptr */

@@ -899,7 +899,7 @@ int lsf_grid_narrowband(lsf_grid *g, double dx, int32_t *phiNB_host, int32_t *ph
 int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol, int *n_exit, double *rms_hist)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
-    if (g->f32 && sharded(g)) return set_error(LSF_ERR_ARG, "minmax: not available on a sharded fp32 grid");
+    { const int rc0 = slab_check_attached(g); if (rc0) return rc0; }
     if (g->f32) {                                                       // fp64 flow on a transient shadow, rounded to fp32
         lsf_grid *sh = nullptr;
         int rc = f32_shadow_open(g, &sh);

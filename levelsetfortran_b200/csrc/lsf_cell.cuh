@@ -17,6 +17,7 @@
 // The header is also compiled by g++ (tests/emu) so the schedule logic can be checked on a CPU.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define LSF_HD __host__ __device__ __forceinline__
@@ -163,7 +164,9 @@ struct FastArith {
 #endif
     }
     static LSF_HD double rsq(double x) { return rsqrt(x); }
+    static LSF_HD double flip_if(double x, bool f) { return __hiloint2double(__double2hiint(x) ^ (f ? (int)0x80000000 : 0), __double2loint(x)); }
 #else
+    static LSF_HD double flip_if(double x, bool f) { return f ? -x : x; }
     static LSF_HD double pos_part(double x) { return x > 0. ? x : 0.0; }
     static LSF_HD double neg_part(double x) { return x < 0. ? x : 0.0; }
     static LSF_HD double dabs(double x) { return fabs(x); }
@@ -179,6 +182,52 @@ struct FastArith {
         return __hiloint2double(hi, __double2loint(x));
     }
 #endif
+
+    // ---- max |e| for the WENO epsilon (subs.f90:533: eps = 1e-6 max(e^2) + 1e-99) ---------------------------------
+    // eps only regularises the weights: an error of relative size d in max|e| moves a weight by at most ~d and the
+    // one-sided derivative by d times a third difference.  LSF_EPS_MODE 0 takes the exact maximum (64-bit integer
+    // compares on the bit patterns: ISETP + ISETP.EX + 2 SEL per max, plus one LOP3 per |e|); 1 compares 32-bit keys
+    // made of exponent + 21 mantissa bits (one funnel shift per value, one VIMNMX per max: the maximum is off by
+    // < 2^-22 relative); 2 compares the values rounded to float (one conversion per value, one FMNMX per max: < 2^-24).
+    // Measured deviation from EXACT arithmetic: tools/fast_accuracy.cpp (cube40, 2155 sweeps) and bench.py `parity`.
+#ifndef LSF_EPS_MODE
+#define LSF_EPS_MODE 1
+#endif
+#if defined(__CUDA_ARCH__)
+    static LSF_HD unsigned ekey(double x) { return __funnelshift_l((unsigned)__double2loint(x), (unsigned)__double2hiint(x), 1); }
+    static LSF_HD double eunkey(unsigned k) { return __hiloint2double((int)(k >> 1), (int)((k << 31) | 0x40000000u)); }   // midpoint of the key's interval
+    static LSF_HD unsigned umax2(unsigned a, unsigned b) { return max(a, b); }
+    static LSF_HD float efl(double x) { return __double2float_rn(fabs(x)); }
+#else
+    static LSF_HD unsigned ekey(double x) { unsigned long long b; memcpy(&b, &x, 8); return (unsigned)((b << 1) >> 32); }
+    static LSF_HD double eunkey(unsigned k) { const unsigned long long b = ((unsigned long long)k << 31) | 0x40000000ull; double x; memcpy(&x, &b, 8); return x; }
+    static LSF_HD unsigned umax2(unsigned a, unsigned b) { return a > b ? a : b; }
+    static LSF_HD float efl(double x) { return (float)fabs(x); }
+#endif
+    // mp = max(|e1|..|e5|) (|e1|..|e4| if YQ: subs.f90:576), mm = max(|e0|..|e4|)
+    template <bool YQ>
+    static LSF_HD void eps_max(double e0, double e1, double e2, double e3, double e4, double e5, double &mp, double &mm)
+    {
+#if LSF_EPS_MODE == 1
+        const unsigned mc = umax2(umax2(ekey(e1), ekey(e2)), umax2(ekey(e3), ekey(e4)));
+        mp = eunkey(YQ ? mc : umax2(mc, ekey(e5)));
+        mm = eunkey(umax2(mc, ekey(e0)));
+#elif LSF_EPS_MODE == 2
+        const float mc = fmaxf(fmaxf(efl(e1), efl(e2)), fmaxf(efl(e3), efl(e4)));
+        mp = (double)(YQ ? mc : fmaxf(mc, efl(e5)));
+        mm = (double)fmaxf(mc, efl(e0));
+#elif !defined(LSF_NO_ABS_INT) && defined(__CUDA_ARCH__)
+        // |e| through an opaque 32-bit AND on the high word (the 64-bit sign mask is turned into a
+        // DADD |x| by the compiler, i.e. back onto the FP64 pipe)
+        const double mc = max_nn(max_nn(dabs_i(e1), dabs_i(e2)), max_nn(dabs_i(e3), dabs_i(e4)));
+        mp = YQ ? mc : max_nn(mc, dabs_i(e5));
+        mm = max_nn(mc, dabs_i(e0));
+#else
+        const double mc = max_nn(max_nn(dabs(e1), dabs(e2)), max_nn(dabs(e3), dabs(e4)));
+        mp = YQ ? mc : max_nn(mc, dabs(e5));
+        mm = max_nn(mc, dabs(e0));
+#endif
+    }
 
     // 1/x for the Jiang-Shu weights: MUFU seed (upper 32 bits of x: relative error <~ 2^-20) + ONE Newton step ->
     // relative error <~ 1e-12.  The weights multiply third differences, so the one-sided derivatives move by
@@ -203,14 +252,15 @@ struct FastArith {
 
     // One side of one direction.  E_k = (eps + IS_k)/3 (a common factor cancels in the weights).  With q_k = E_k^2,
     // n0 = q1 q2, x = q0 q2, P = q0 q1 and D = n0 + 6 x + 3 P the Jiang-Shu weights are w0 = n0/D, w2 = 3P/D, and the
-    // WENO correction  2 w0 A + (w2 - 1/2) s  equals  r (2 n0 A + 3 P s) - s/2,  r = 1/D.  Returns r*(n0*A4 + P*s6),
-    // i.e. TWICE the correction plus s (A4 = 4A, s6 = 6s): the caller adds it to cen -/+ s.
-    static LSF_HD double side(double E0, double E1, double E2, double A4, double s6)
+    // WENO correction  2 w0 A + (w2 - 1/2) s  equals  r (2 n0 A + 3 P s) - s/2,  r = 1/D.  Returns r*(n0*A + P*s15),
+    // s15 = 1.5 s: HALF the correction plus s/4; the caller multiplies by 4 inside its final FMA (12 dx times the
+    // one-sided derivative = cen -/+ s +/- 4 * side).
+    static LSF_HD double side(double E0, double E1, double E2, double A, double s15)
     {
         const double q0 = E0 * E0, q1 = E1 * E1, q2 = E2 * E2;
         const double n0 = q1 * q2, x = q0 * q2, P = q0 * q1;
         const double D = fma(6.0, x, fma(3.0, P, n0));
-        return rcp(D) * fma(n0, A4, P * s6);
+        return rcp(D) * fma(n0, A, P * s15);
     }
 
     // dminus / dplus are returned UNSCALED: 12 dx times the one-sided derivatives (godunov applies 1/(12 dx) once,
@@ -223,33 +273,24 @@ struct FastArith {
         const double e3 = v[4] - v[3], e4 = v[5] - v[4], e5 = v[6] - v[5];
         const double am = e1 - e0, bm = e2 - e1, c = e3 - e2, bp = e4 - e3, ap = e5 - e4;
         const double tpa = ap - bp, tpb = bp - c, tmc = c - bm, tma = am - bm;
-#if !defined(LSF_NO_ABS_INT) && defined(__CUDA_ARCH__)
-        // |e| through an opaque 32-bit AND on the high word (the 64-bit sign mask is turned into a
-        // DADD |x| by the compiler, i.e. back onto the FP64 pipe)
-        const double mc = max_nn(max_nn(dabs_i(e1), dabs_i(e2)), max_nn(dabs_i(e3), dabs_i(e4)));
-        const double mp = YQ ? mc : max_nn(mc, dabs_i(e5));
-        const double mm = max_nn(mc, dabs_i(e0));
-#else
-        const double mc = max_nn(max_nn(dabs(e1), dabs(e2)), max_nn(dabs(e3), dabs(e4)));
-        const double mp = YQ ? mc : max_nn(mc, dabs(e5));
-        const double mm = max_nn(mc, dabs(e0));
-#endif
+        double mp, mm;
+        eps_max<YQ>(e0, e1, e2, e3, e4, e5, mp, mm);
         // everything below is (eps + IS)/3: eps/3 = (1e-6/3) max e^2 + tiny, IS/3 = (13/3) u^2 + v^2
         constexpr double k13 = 13.0 / 3.0, keps = 1.0e-6 / 3.0, tiny = 1.0e-60;
         const double epsp = fma(keps * mp, mp, tiny);
         const double epsm = fma(keps * mm, mm, tiny);
-        const double s13b = (k13 * tpb) * tpb, s13c = (k13 * tmc) * tmc;
+        const double kb = k13 * tpb, kc = k13 * tmc;
         double t;
         t = fma(-3.0, bp, ap); const double E0p = fma(k13 * tpa, tpa, fma(t, t, epsp));
-        t = bp + c;            const double E1p = fma(t, t, s13b + epsp);
-        t = fma(3.0, c, -bm);  const double E2p = fma(t, t, s13c + epsp);
+        t = bp + c;            const double E1p = fma(t, t, fma(kb, tpb, epsp));
+        t = fma(3.0, c, -bm);  const double E2p = fma(t, t, fma(kc, tmc, epsp));
         t = fma(-3.0, bm, am); const double E0m = fma(k13 * tma, tma, fma(t, t, epsm));
-        t = bm + c;            const double E1m = fma(t, t, s13c + epsm);
-        t = fma(3.0, c, -bp);  const double E2m = fma(t, t, s13b + epsm);
-        const double s = tpb - tmc, s6 = 6.0 * s;
+        t = bm + c;            const double E1m = fma(t, t, fma(kc, tmc, epsm));
+        t = fma(3.0, c, -bp);  const double E2m = fma(t, t, fma(kb, tpb, epsm));
+        const double s = tpb - tmc, s15 = 1.5 * s;
         const double cen = fma(7.0, e2 + e3, -(e1 + e4));
-        dplus = (cen - s) + side(E0p, E1p, E2p, 4.0 * (tpa - tpb), s6);
-        dminus = (cen + s) - side(E0m, E1m, E2m, 4.0 * (tma + tmc), s6);
+        dplus = fma(4.0, side(E0p, E1p, E2p, tpa - tpb, s15), cen - s);
+        dminus = fma(-4.0, side(E0m, E1m, E2m, tma + tmc, s15), cen + s);
     }
 
     static LSF_HD void lo_dir(double vm, double vc, double vp, const CellConst &cc, double &dminus, double &dplus)
@@ -265,9 +306,18 @@ struct FastArith {
     {
         // upwind pair per axis: phi>0 -> (max(a,0), min(b,0)) else (max(b,0), min(a,0))
         const bool pos = phic > 0.;
+#if !defined(LSF_GODUNOV_SELECT)
+        // phi <= 0 takes (max(b,0), min(a,0)); their squares are those of (min(-b,0), max(-a,0)): flip the signs of
+        // a..f instead of swapping each pair (one XOR on the high word per value instead of two selects); the squares
+        // and their maximum are bit for bit the same
+        const double ax = flip_if(a, !pos), bx = flip_if(b, !pos);
+        const double ay = flip_if(c, !pos), by = flip_if(d, !pos);
+        const double az = flip_if(e, !pos), bz = flip_if(f, !pos);
+#else
         const double ax = pos ? a : b, bx = pos ? b : a;
         const double ay = pos ? c : d, by = pos ? d : c;
         const double az = pos ? e : f, bz = pos ? f : e;
+#endif
         const double x1 = pos_part(ax), x2 = neg_part(bx);
         const double y1 = pos_part(ay), y2 = neg_part(by);
         const double z1 = pos_part(az), z2 = neg_part(bz);

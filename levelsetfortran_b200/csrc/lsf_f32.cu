@@ -257,12 +257,14 @@ int f32_sign_init(Grid *g, const double xLo[3], double dx, const double *d_surfX
     return LSF_OK;
 }
 
-// transient fp64 shadow of an fp32 grid: phi widened on creation, rounded back by f32_shadow_close
+// transient fp64 shadow of an fp32 grid: phi widened on creation, rounded back by f32_shadow_close.  On z-slabs the shadow
+// is a sharded fp64 grid of the same geometry that all ranks create and connect together (lsf_slab.cu: sgrid_shadow_f64), so
+// every multi-GPU stage of the fp64 path -- min/max flow with its ghost-plane exchange, node projection -- runs on it unchanged.
 int f32_shadow_open(Grid *g, lsf_grid **shadow)
 {
-    int rc = lsf_grid_create(shadow, g->dm.nx, g->dm.ny, g->dm.nz);
+    int rc = sharded(g) ? sgrid_shadow_f64(g, shadow) : lsf_grid_create(shadow, g->dm.nx, g->dm.ny, g->dm.nz);
     if (rc) return rc;
-    convert_f2d(g->phi_f, (*shadow)->phi, g->np);
+    convert_f2d(g->phi_f, (*shadow)->phi, g->np);          // ghost planes included: they hold the neighbours' current values
     return LSF_OK;
 }
 
@@ -270,9 +272,10 @@ int f32_shadow_close(Grid *g, lsf_grid *shadow, bool write_back)
 {
     if (write_back) convert_d2f(shadow->phi, g->phi_f, g->np);
     cudaError_t e = cudaStreamSynchronize(G.stream);
-    lsf_grid_destroy(shadow);
+    int rc = LSF_OK;
+    if (sharded(g)) rc = sgrid_shadow_release(g, shadow); else lsf_grid_destroy(shadow);
     if (e != cudaSuccess) return set_error(LSF_ERR_CUDA, "f32 shadow: %s", cudaGetErrorString(e));
-    return LSF_OK;
+    return rc;
 }
 
 }  // namespace lsf

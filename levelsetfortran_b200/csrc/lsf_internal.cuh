@@ -32,6 +32,7 @@ struct lsf_grid {
     bool attached;
     long long phase;              // number of ghost-plane exchanges so far (lockstep on all ranks)
     long long sum_seq;            // number of cross-rank reductions so far
+    long long box_round;          // number of host-side mailbox rendezvous so far (lockstep on all ranks)
     unsigned int *exch_counter;
     // active-list min/max flow (lsf_mm_list.cu)
     long long *mml_list;          // linear indices of the cells that can still change, ascending
@@ -132,6 +133,15 @@ void slab_exchange_raw(Grid *g, bool in_loop, char *buf, size_t esize, bool hand
 void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol, int n);
 long long slab_publish_sum(Grid *g, int npart);  // this rank's sum of partials -> every rank (fire and forget); returns its sequence number
 void slab_decide(Grid *g, long long seq_first, int count, int n_first, int hist_off, double tol);   // EXIT / NaN tests of `count` iterations
+// host-side rendezvous of all ranks through the SlabSync mailboxes: every rank contributes `bytes` (<= SLAB_BOX_BYTES, may be
+// 0) and, if `all` is given, receives the ranks' contributions at all + SLAB_BOX_BYTES * rank.  Doubles as a host-level barrier.
+int slab_host_exchange(Grid *g, const void *mine, size_t bytes, void *all);
+// all ranks' streams meet here (device-side; the host does not wait)
+void slab_device_barrier(Grid *g);
+// view of a field of the global grid; `mine` = this rank's local array of that field (phi or phiN)
+SlabView slab_view(const Grid *g, const double *mine);
+int sgrid_shadow_f64(Grid *g, lsf_grid **shadow);      // sharded fp64 twin of a sharded (fp32) grid, attached; collective
+int sgrid_shadow_release(Grid *g, lsf_grid *shadow);   // collective
 template <class T> inline T *peer_ptr(const Grid *g, int rank, T *mine)
 {
     return (T *)((char *)g->peer_base[rank] + ((char *)mine - (char *)g->shared_base));

@@ -15,8 +15,10 @@ namespace lsf {
 #define LSF_TC 16
 #endif
 #ifndef LSF_OCC
-#define LSF_OCC 3      // resident CTAs per SM the kernels are COMPILED for (register budget 65536 / (OCC * THREADS)): FastArith fits 80
-                       // registers without spills; with the single-copy ring 3 CTAs use 105 KB of shared memory and leave the L1 its size
+#define LSF_OCC 2      // resident CTAs per SM the kernels are COMPILED for (register budget 65536 / (OCC * THREADS) = 128).  Round 2, session
+                       // 11: with ~125 registers the compiler keeps the ring / row addresses and the thread index in registers instead of
+                       // rematerialising them every step (steady loop 651 instead of 681 instructions); 2 and 3 resident CTAs deliver the
+                       // same rate at 1024^3 and 2 are faster below (512^3: 23.7 vs 22.2 Gcell/s).  3 = the 80-register build of sessions 3-10
 #endif
 typedef MarchCfg<LSF_TB, LSF_TC> CFG;
 #ifndef LSF_OCC_EXACT

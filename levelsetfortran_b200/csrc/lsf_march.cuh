@@ -173,6 +173,9 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
 #ifndef LSF_SPLIT_BAR
 #define LSF_SPLIT_BAR 1         // 1 (default): split step barrier -- a thread ARRIVES after its deposits, computes the x direction of its NEXT
 #endif                          //    cell from a register window of its own row, and only then WAITS for the other threads' deposits
+#ifndef LSF_STEADY
+#define LSF_STEADY 1            // 1 (default): second copy of the step body for the steps of interior tiles in which every range test holds
+#endif
 // LSF_EXP_NOSTG / LSF_EXP_NOSYNC: no global stores / no CTA barrier per step (timing experiments, results wrong)
 
 namespace lsf {
@@ -203,6 +206,9 @@ LSF_DEV double bc_add(double v, double dx) { return ExactArith::add(v, dx); }
 LSF_DEV float bc_add(float v, float dx) { return v + dx; }
 LSF_DEV int m_imax(int a, int b) { return a > b ? a : b; }
 LSF_DEV int m_imin(int a, int b) { return a < b ? a : b; }
+
+struct StepGeneric { static constexpr bool value = false; };
+struct StepSteady { static constexpr bool value = true; };
 
 constexpr int M_H = 3;                       // stencil half-width
 constexpr int M_NSLOT = 8;                   // hyperplane slots in the ring (each stored twice)
@@ -597,7 +603,23 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     // the end of step t-1 between the arrive and the wait of that step's barrier
     real xw[7] = {0, 0, 0, 0, 0, 0, 0};
     real xa = 0, xb = 0;
-    for (int t = -M_LOOK; t <= p.tend; ++t) {
+    // Steady state.  On a tile whose rows and halo rows all exist and lie inside the high-order window in b and c (all but the
+    // outermost ring of tiles), every range test of a step -- look-ahead load, cell active, high-order branch, halo row in range,
+    // next cell's x direction -- holds for every thread during steps T0 .. T1-1 (92 % of the steps at nx = 1024).  The step body
+    // is compiled a second time for that range (ST = true) with the tests folded away: straight-line code, no low-order branch.
+    //   a = 1+t-sig, sig in [M_H, TB+TC-2+M_H]:  a >= lo_a for all rows  <=>  t >= lo_a + TB + TC;  a+1 <= hi_a  <=>  t <= hi_a + 1
+    //   (hi_a <= nx-4 covers a+LOOK <= nx, lo_a >= 4 covers the halo rows, whose sig is at most TB+TC+4)
+    int T0 = 0, T1 = 0;
+    if (LSF_STEADY && R == 1 && !OV && CFG::VEC == 1) {
+        const int b0 = 1 + J * TB, c0 = p.c_lo + K * TC;
+        const bool interior = (b0 >= p.lo_b) && (b0 + TB - 1 <= p.hi_b) && (b0 - M_H >= 0) && (b0 + TB - 1 + M_H <= p.ny) &&
+                              (c0 >= p.lo_c) && (c0 + TC - 1 <= p.hi_c) && (c0 + TC - 1 <= p.c_hi) && (c0 - M_H >= 0) &&
+                              (c0 + TC - 1 + M_H <= p.c_max) && (p.lo_a >= 4) && (p.hi_a <= p.nx - 4);
+        if (interior) { T0 = p.lo_a + TB + TC; T1 = p.hi_a + 2; }
+        if (T1 < T0) T1 = T0;
+    }
+    auto body = [&](const int t, auto steady_tag) {
+        constexpr bool ST = decltype(steady_tag)::value;
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
         // (SPLIT && LSF_FOLD_FLAGS: folded into the previous step's barrier instead, see below)
         if (!(SPLIT && LSF_FOLD_FLAGS) && t >= 0 && (t % M_CHUNK) == 0) {
@@ -633,7 +655,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         for (int r = 0; r < R; ++r) {
             const int a = 1 + t - sig[r];
             const int a4 = a + M_LOOK;
-            ldLook[r] = rowValid[r] && (a4 >= 0) && (a4 <= p.nx);
+            ldLook[r] = ST ? true : (rowValid[r] && (a4 >= 0) && (a4 <= p.nx));
             la[r] = 0;
 #if !(LSF_EXP_NOLDG_MASK & 1)
             if (ldLook[r]) {
@@ -642,7 +664,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
                 else la[r] = (LSF_LD_CACHED & 1) ? p_ldca(pOut[r] + M_LOOK * SA) : p_ldcg(pOut[r] + M_LOOK * SA);
             }
 #endif
-            active[r] = compValid[r] && (a >= 1) && (a <= p.nx - 1);
+            active[r] = ST ? true : (compValid[r] && (a >= 1) && (a <= p.nx - 1));
             ps[r] = 0;
 #if !(LSF_EXP_NOLDG_MASK & 2)
             if (active[r]) {
@@ -652,7 +674,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 #else
             if (active[r]) ps[r] = (real)0.5;
 #endif
-            hi[r] = hiBC[r] && (a >= p.lo_a) && (a <= p.hi_a);
+            hi[r] = ST ? true : (hiBC[r] && (a >= p.lo_a) && (a <= p.hi_a));
         }
         bool hdep[CFG::HR];
         real hv[CFG::HR];
@@ -664,7 +686,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
                 hh[r] = hlow[r] ? t : t + M_LOOK;
                 const int ah = 1 + hh[r] - hsig[r];
 #if !(LSF_EXP_NOLDG_MASK & 4)
-                if (hh[r] >= 0 && ah >= 0 && ah <= p.nx) {
+                if (ST || (hh[r] >= 0 && ah >= 0 && ah <= p.nx)) {
                     if constexpr (VEC > 1) hv[r] = rdHalo[r].get(hp[r]);
                     else if (OV) hv[r] = p_ldcg(hp[r] + ((ah == 0 || ah == p.nx) ? p.shell_rd_delta : hShell[r]));
                     else hv[r] = ((LSF_LD_CACHED & 4) && !hlow[r]) ? p_ldca(hp[r]) : p_ldcg(hp[r]);
@@ -760,11 +782,11 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             const real c0 = active[0] ? pn[0] : xw[3];
             xw[0] = xw[1]; xw[1] = xw[2]; xw[2] = c0; xw[3] = xw[4]; xw[4] = xw[5]; xw[5] = xw[6]; xw[6] = la[0];
             const int an = 2 + t - sig[0];
-            if (compValid[0] && (an >= 1) && (an <= p.nx - 1)) {
+            if (ST || (compValid[0] && (an >= 1) && (an <= p.nx - 1))) {
                 real vxn[7];
 #pragma unroll
                 for (int m = -3; m <= 3; ++m) vxn[FA ? 3 - m : 3 + m] = xw[3 + m];
-                reinit_dir_x<AR>(vxn, hiBC[0] && (an >= p.lo_a) && (an <= p.hi_a), p.cc, xa, xb);
+                reinit_dir_x<AR>(vxn, ST ? true : (hiBC[0] && (an >= p.lo_a) && (an <= p.hi_a)), p.cc, xa, xb);
             }
             p_bar_wait(&sm.bar, bar_phase++);      // every thread's deposits of step t are visible
         } else p_sync();
@@ -772,6 +794,15 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         if (pub && tid == TID_PUB) {
             p_fence(); p_st_release(mine, ebase + M_BIAS + t);
             if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + t); }
+        }
+    };
+    {
+        int t = -M_LOOK;
+        for (int pass = 0; pass < 2; ++pass) {           // ramp-in, steady state, ramp-out (one call site per body variant)
+            const int tstop = (pass == 0) ? T0 : p.tend + 1;
+            for (; t < tstop; ++t) body(t, StepGeneric());
+            if (pass == 0)
+                for (; t < T1; ++t) body(t, StepSteady());
         }
     }
     // ---- overlapped sweeps: the boundary block for the points this tile's cells are the source of ------------

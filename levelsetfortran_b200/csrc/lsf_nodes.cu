@@ -10,8 +10,10 @@
 
 namespace lsf {
 
+// PV: `const double *` (the grid lives on this GPU) or SlabView (z-slabs: gathers from the peers' slabs over NVLink)
+template <class PV>
 __global__ void __launch_bounds__(128)
-k_advect_nodes(NodeConst c, const double *__restrict__ phi, const double *__restrict__ sbsrc, double *__restrict__ X, int nNode,
+k_advect_nodes(NodeConst c, const PV phi, const PV sbsrc, double *__restrict__ X, int nNode,
                double *__restrict__ phiSurf, double *__restrict__ gradPhiSurf, int iter, int *__restrict__ status,
                unsigned long long *__restrict__ moves)
 {
@@ -41,7 +43,7 @@ int advect_nodes_core(Grid *g, const double *d_phi, const double *d_sbsrc, const
 {
     if (nNode < 1 || iter < 0 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "advect_nodes: bad nSurfNode/iter/dx");
     NodeConst c;
-    c.sx = g->dm.sx; c.sxy = g->dm.sxy; c.nx = g->dm.nx; c.ny = g->dm.ny; c.nz = g->dm.nz;
+    c.sx = g->dm.sx; c.sxy = g->dm.sxy; c.nx = g->dm.nx; c.ny = g->dm.ny; c.nz = sharded(g) ? g->sg.NZ : g->dm.nz;
     c.xLo[0] = xLo[0]; c.xLo[1] = xLo[1]; c.xLo[2] = xLo[2];
     c.dx = dx; c.bSB = 8.1 * dx;
     double *d_X = nullptr, *d_ps = nullptr, *d_gs = nullptr;
@@ -61,7 +63,17 @@ int advect_nodes_core(Grid *g, const double *d_phi, const double *d_sbsrc, const
     }
     G.n_launch = 0;
     cudaEventRecord(G.ev0, G.stream);
-    k_advect_nodes<<<(nNode + 127) / 128, 128, 0, G.stream>>>(c, d_phi, d_sbsrc, d_X, nNode, d_ps, d_gs, iter, d_st, d_mv);
+    if (sharded(g)) {
+        // Every rank projects ALL nodes (they are few next to the grid and the mesh is replicated like the triangles of the sign
+        // search), reading phi wherever a node goes through the peer-mapped slabs: identical results on all ranks.  The field
+        // must be final on every rank before anyone reads it and must stay untouched until everyone has finished reading.
+        slab_device_barrier(g);
+        k_advect_nodes<SlabView><<<(nNode + 127) / 128, 128, 0, G.stream>>>(c, slab_view(g, d_phi), slab_view(g, d_sbsrc), d_X, nNode, d_ps,
+                                                                            d_gs, iter, d_st, d_mv);
+        slab_device_barrier(g);
+    } else {
+        k_advect_nodes<const double *><<<(nNode + 127) / 128, 128, 0, G.stream>>>(c, d_phi, d_sbsrc, d_X, nNode, d_ps, d_gs, iter, d_st, d_mv);
+    }
     G.n_launch++;
     cudaEventRecord(G.ev1, G.stream);
     int st = 0;
@@ -96,7 +108,7 @@ int lsf_grid_advect_nodes(lsf_grid *g, const double xLo[3], double dx, double *s
                           double *phiSurf, double *gradPhiSurf, int iter, long long *n_moves)
 {
     if (!g || !xLo || !surfXX || !phiSurf || !gradPhiSurf) return set_error(LSF_ERR_ARG, "null argument");
-    if (sharded(g)) return set_error(LSF_ERR_ARG, "advect_nodes: not available on a sharded grid (download and use lsf_advect_nodes)");
+    { const int rc0 = slab_check_attached(g); if (rc0) return rc0; }
     if (g->f32) {                                                       // fp64 evaluation on a transient widened copy of phi
         lsf_grid *sh = nullptr;
         int rc = f32_shadow_open(g, &sh);

@@ -27,8 +27,9 @@ struct NodeConst {
 constexpr int NODE_OK = 0, NODE_OFF_GRID = 1, NODE_BAND_ON_BOUNDARY = 2;
 
 // firstDeriv order 8 at point q along one axis (stride st); YTYPO: subs.f90:346 reads j+1 where j+2 is meant
-template <bool YTYPO>
-LSF_HD double node_d8(const double *phi, long long q, long long st, double dx)
+// PV: anything indexable by the global linear index -- `const double *` on one GPU, lsf::SlabView on a sharded grid
+template <bool YTYPO, class PV>
+LSF_HD double node_d8(const PV &phi, long long q, long long st, double dx)
 {
     typedef ExactArith X;
     const double aa1 = 1. / 280., aa2 = -4. / 105., aa3 = 1. / 5., aa4 = -4. / 5.;
@@ -46,7 +47,8 @@ LSF_HD double node_d8(const double *phi, long long q, long long st, double dx)
 
 // gradPhi(i,j,k,1:3) as the reference holds it when setPhiSurf runs: the order-8 derivative on the stencil
 // band (band of `sbsrc`: the field the last narrowBand call saw), 0 elsewhere.
-LSF_HD int node_grad(const NodeConst &c, const double *phi, const double *sbsrc, int i, int j, int k, double g[3])
+template <class PV>
+LSF_HD int node_grad(const NodeConst &c, const PV &phi, const PV &sbsrc, int i, int j, int k, double g[3])
 {
     const long long q = i + c.sx * j + c.sxy * k;
     g[0] = g[1] = g[2] = 0.;
@@ -59,7 +61,8 @@ LSF_HD int node_grad(const NodeConst &c, const double *phi, const double *sbsrc,
 }
 
 // setPhiSurf for one node, subs.f90:1078-1166
-LSF_HD int node_interp(const NodeConst &c, const double *phi, const double *sbsrc, const double x[3], double &phiSurf, double gs[3])
+template <class PV>
+LSF_HD int node_interp(const NodeConst &c, const PV &phi, const PV &sbsrc, const double x[3], double &phiSurf, double gs[3])
 {
     typedef ExactArith X;
     const double fi = floor(X::div(X::sub(x[0], c.xLo[0]), c.dx));
@@ -112,7 +115,8 @@ LSF_HD int node_interp(const NodeConst &c, const double *phi, const double *sbsr
 }
 
 // The reference's loop for one node (set3d.f90:483-501): x in/out, returns the status and the number of moves.
-LSF_HD int node_project(const NodeConst &c, const double *phi, const double *sbsrc, double x[3], double &phiSurf, double gs[3],
+template <class PV>
+LSF_HD int node_project(const NodeConst &c, const PV &phi, const PV &sbsrc, double x[3], double &phiSurf, double gs[3],
                         int iter, int &moves)
 {
     typedef ExactArith X;

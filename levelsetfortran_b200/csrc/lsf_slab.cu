@@ -229,6 +229,76 @@ void launch_finalize_slab(Grid *g, int npart, int hist_off, double tol, int n)
     slab_decide(g, seq, 1, n, hist_off, tol);
 }
 
+// =====================================================================================
+// Device-side barrier over all ranks (through the reduction slots: a contribution without a sum)
+// =====================================================================================
+__global__ void k_slab_barrier(PeerSyncs peers, SlabSync *self, Ctrl *ctrl, int rank, int nranks, long long seq)
+{
+    const int slot = (int)(seq % SLAB_SUM_SLOTS);
+    if (threadIdx.x < nranks) {
+        p_fence_sys();
+        p_st_release_sys(&peers.s[threadIdx.x]->sum_seq[slot][rank], seq);
+        wait_ge<true>(&self->sum_seq[slot][threadIdx.x], seq, ctrl);
+    }
+}
+
+void slab_device_barrier(Grid *g)
+{
+    if (!sharded(g)) return;
+    const long long seq = ++g->sum_seq;
+    k_slab_barrier<<<1, 32, 0, G.stream>>>(peer_syncs(g), g->sync, g->ctrl, g->sg.rank, g->sg.nranks, seq);
+    G.n_launch++;
+}
+
+SlabView slab_view(const Grid *g, const double *mine)
+{
+    SlabView v;
+    memset(&v, 0, sizeof(v));
+    v.nranks = g->sg.nranks;
+    v.sxy = g->dm.sxy;
+    for (int r = 0; r < g->sg.nranks; ++r) {
+        SlabGeom o;
+        slab_geom(g->sg.NZ, g->sg.nranks, r, o);
+        v.base[r] = sharded(g) ? peer_ptr(g, r, mine) : mine;
+        v.shift[r] = (long long)o.kbase * g->dm.sxy;
+        v.kend[r] = o.k1;
+    }
+    return v;
+}
+
+// =====================================================================================
+// Host-side rendezvous through the mailboxes of the SlabSync blocks (plain cudaMemcpy into the peer-mapped
+// allocations): the library has no communicator of its own, and a collective call that has to hand something to
+// the other ranks after creation time -- the IPC handle of a transient shadow grid -- uses the memory the host
+// program connected once, at lsf_sgrid_attach.
+// =====================================================================================
+int slab_host_exchange(Grid *g, const void *mine, size_t bytes, void *all)
+{
+    if (!sharded(g)) { if (all && mine) memcpy(all, mine, bytes); return LSF_OK; }
+    if (bytes > (size_t)SLAB_BOX_BYTES) return set_error(LSF_ERR_ARG, "slab_host_exchange: %zu bytes do not fit a mailbox", bytes);
+    LSF_CUDA(cudaStreamSynchronize(G.stream));
+    const long long seq = ++g->box_round;
+    const int me = g->sg.rank, P = g->sg.nranks;
+    for (int r = 0; r < P; ++r) {
+        SlabSync *q = (SlabSync *)g->peer_base[r];
+        if (bytes) LSF_CUDA(cudaMemcpy(q->box[me], mine, bytes, cudaMemcpyDefault));
+    }
+    for (int r = 0; r < P; ++r) {                      // the payload is in place everywhere this call put it: now the flags
+        SlabSync *q = (SlabSync *)g->peer_base[r];
+        LSF_CUDA(cudaMemcpy(&q->box_seq[me], &seq, sizeof(seq), cudaMemcpyDefault));
+    }
+    long long seen[SLAB_MAX_RANKS];
+    for (long long spins = 0;; ++spins) {
+        LSF_CUDA(cudaMemcpy(seen, g->sync->box_seq, sizeof(long long) * P, cudaMemcpyDeviceToHost));
+        bool ok = true;
+        for (int r = 0; r < P; ++r) ok = ok && seen[r] >= seq;
+        if (ok) break;
+        if (spins > 3000000) return set_error(LSF_ERR_TIMEOUT, "slab_host_exchange: a rank did not arrive at rendezvous %lld", seq);
+    }
+    if (all) LSF_CUDA(cudaMemcpy(all, g->sync->box, (size_t)SLAB_BOX_BYTES * (size_t)P, cudaMemcpyDeviceToHost));
+    return LSF_OK;
+}
+
 }  // namespace lsf
 
 using namespace lsf;
@@ -352,3 +422,47 @@ int lsf_sgrid_sync_ghosts(lsf_grid *g)
 }
 
 }  // extern "C"
+
+namespace lsf {
+
+// A sharded fp64 grid with the geometry of g, created and attached by all ranks together: the IPC handles travel through g's
+// mailboxes.  A rank may overwrite a mailbox only after every rank has read the previous content: the rendezvous that
+// follows every use (here: the second exchange) guarantees it.
+int sgrid_shadow_f64(Grid *g, lsf_grid **shadow)
+{
+    *shadow = nullptr;
+    lsf_grid *sh = nullptr;
+    int rc = lsf_sgrid_create(&sh, g->dm.nx, g->dm.ny, g->sg.NZ, g->sg.rank, g->sg.nranks);
+    static_assert(LSF_IPC_HANDLE_BYTES < SLAB_BOX_BYTES, "handle + status byte must fit a mailbox");
+    unsigned char mine[SLAB_BOX_BYTES], all[SLAB_BOX_BYTES * SLAB_MAX_RANKS], handles[LSF_IPC_HANDLE_BYTES * SLAB_MAX_RANKS];
+    memset(mine, 0, sizeof(mine));
+    if (!rc) rc = lsf_sgrid_ipc_handle(sh, mine);
+    mine[LSF_IPC_HANDLE_BYTES] = rc ? 1 : 0;                 // a rank that failed tells the others instead of leaving them waiting
+    int rc2 = slab_host_exchange(g, mine, LSF_IPC_HANDLE_BYTES + 1, all);
+    if (!rc2) rc2 = slab_host_exchange(g, nullptr, 0, nullptr);     // everyone has read the boxes
+    bool peer_failed = false;
+    for (int r = 0; r < g->sg.nranks && !rc2; ++r) {
+        peer_failed = peer_failed || all[SLAB_BOX_BYTES * r + LSF_IPC_HANDLE_BYTES];
+        memcpy(handles + LSF_IPC_HANDLE_BYTES * r, all + SLAB_BOX_BYTES * r, LSF_IPC_HANDLE_BYTES);
+    }
+    if (!rc && !rc2 && peer_failed) rc = set_error(LSF_ERR_CUDA, "shadow grid: another rank could not allocate its slab");
+    if (!rc && !rc2) rc = lsf_sgrid_attach(sh, handles);
+    if (rc || rc2) { lsf_grid_destroy(sh); return rc ? rc : rc2; }
+    *shadow = sh;
+    return LSF_OK;
+}
+
+// Every rank has stopped using the peers' slabs (stream drained + rendezvous), unmaps them, and only after a second rendezvous
+// frees its own: memory exported through CUDA IPC must outlive every mapping of it.
+int sgrid_shadow_release(Grid *g, lsf_grid *sh)
+{
+    if (!sh) return LSF_OK;
+    int rc = slab_host_exchange(g, nullptr, 0, nullptr);
+    for (int r = 0; r < sh->sg.nranks; ++r)
+        if (r != sh->sg.rank && sh->peer_base[r]) { cudaIpcCloseMemHandle(sh->peer_base[r]); sh->peer_base[r] = nullptr; }
+    const int rc2 = slab_host_exchange(g, nullptr, 0, nullptr);
+    lsf_grid_destroy(sh);
+    return rc ? rc : rc2;
+}
+
+}  // namespace lsf

@@ -26,6 +26,7 @@ constexpr int SLAB_GHOST = 3;
 constexpr int SLAB_MAX_RANKS = 16;
 constexpr int SLAB_MIN_PLANES = 8;      // owned planes per rank (>= 2*ghost, keeps every exchange nearest-neighbour)
 constexpr int SLAB_MAX_NTB = 4096;
+constexpr int SLAB_BOX_BYTES = 128;    // host-side mailbox per source rank (SlabSync::box)
 constexpr int SLAB_SUM_SLOTS = 16;      // reductions may be published this many sequence numbers ahead of their consumption
 
 struct SlabGeom {
@@ -69,6 +70,31 @@ struct SlabSync {
     int rank_flag[SLAB_SUM_SLOTS][SLAB_MAX_RANKS];       // flags travelling with the sums (bit 0 guard, bit 1 band-on-boundary, bit 2 timeout, bit 3 other error)
     long long in_progress[SLAB_MAX_NTB];     // streaming-halo progress of the upstream rank's last tile row
     long long edge_done[2][SLAB_MAX_NTB];    // [side][J]: epoch of the last sweep in which that neighbour's tile J adjacent to this rank completed
+    // host-side mailbox (lsf_slab.cu: slab_host_exchange): rank r copies up to SLAB_BOX_BYTES into box[r] of every rank and then raises
+    // seq[r]; used for the rendezvous of collective calls that need one (IPC handles of a transient shadow grid, open / close barriers)
+    long long box_seq[SLAB_MAX_RANKS];
+    unsigned char box[SLAB_MAX_RANKS][SLAB_BOX_BYTES];
+};
+
+// Read-only view of a field of the GLOBAL grid phi(0:nx,0:ny,0:NZ) whose planes are spread over the ranks' slabs: element q
+// (global linear index) lives on the rank owning plane q / sxy, at the same (i,j) in that rank's local array.  Used by kernels
+// that gather a few values anywhere in the grid (surface-node projection): loads from a peer's slab travel over NVLink.
+struct SlabView {
+    const double *base[SLAB_MAX_RANKS];      // the ranks' local arrays (peer-mapped)
+    long long shift[SLAB_MAX_RANKS];         // kbase * sxy: global index of the first element of the local array
+    int kend[SLAB_MAX_RANKS];                // first global plane NOT owned by the rank
+    int nranks;
+    long long sxy;
+#if defined(__CUDACC__)
+    __host__ __device__
+#endif
+    double operator[](long long q) const
+    {
+        const int k = (int)(q / sxy);
+        int r = 0;
+        while (r < nranks - 1 && k >= kend[r]) ++r;
+        return base[r][q - shift[r]];
+    }
 };
 
 }  // namespace lsf

@@ -274,7 +274,7 @@ class ShardedGrid(DeviceGrid):
         self.rank = dist.get_rank() if rank is None else int(rank)
         self.nranks = dist.get_world_size() if nranks is None else int(nranks)
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
-        self.f32 = bool(f32)          # optional fp32 mode: fill / upload / download / signSearch / reinit / narrowBand
+        self.f32 = bool(f32)          # optional fp32 mode (same calls)
         self.k0, self.k1 = slab_range(self.nz, self.nranks, self.rank)
         self._h = C.c_void_p()
         create = lib().lsf_sgrid_create_f32 if self.f32 else lib().lsf_sgrid_create

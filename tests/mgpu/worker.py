@@ -83,8 +83,10 @@ def main():
         G.signSearch(g["xLo"], DX, X, E, g["box"])
         sign = G.download()
         G.reinit(15, DX, 0.1 * g["dxx"], tol=0.0)
-        return sign, G.download()
-    sign_ref, phi_ref = whole32(shape, run_whole32b)
+        phi = G.download()
+        rc, n, hist = G.minMaxFlow(13, DX, 0.01 * g["dxx"], tol=0.0)
+        return sign, phi, G.download(), n, hist, G.advectNodes(g["xLo"], DX, X, iter=50)
+    sign_ref, phi_ref, mm32_ref, mm32_n, mm32_hist, nodes32_ref = whole32(shape, run_whole32b)
     SG = ShardedGrid(g["nx"], g["ny"], g["nz"], f32=True)
     SG.fill(1.0)
     SG.signSearch(g["xLo"], DX, X, E, g["box"])
@@ -92,10 +94,22 @@ def main():
     SG.reinit(15, DX, 0.1 * g["dxx"], tol=0.0)
     phi = SG.download()
     nb, sb = SG.narrowBand(DX)
+    # min/max flow and node projection on the sharded fp32 grid: the transient fp64 shadow is itself a sharded grid that the
+    # ranks connect through the slab mailboxes; results must equal the single-GPU fp32 grid's bit for bit
+    rc, n32, hist32 = SG.minMaxFlow(13, DX, 0.01 * g["dxx"], tol=0.0)
+    mm32 = SG.download()
+    nodes32 = SG.advectNodes(g["xLo"], DX, X, iter=50)
+    rc, n32b, _ = SG.minMaxFlow(3, DX, 0.01 * g["dxx"], tol=0.0)          # a second shadow on the same grid (mailbox rounds advance)
     SG.close()
     assert np.array_equal(sign, sign_ref[:, :, SG.k0:SG.k1]) and np.array_equal(np.signbit(sign), np.signbit(sign_ref[:, :, SG.k0:SG.k1]))
     assert np.array_equal(phi, phi_ref[:, :, SG.k0:SG.k1])
     assert np.array_equal(nb, (np.abs(phi) < 4.1 * DX).astype(np.int32))
+    assert n32 == mm32_n and n32b == 2 and np.array_equal(mm32, mm32_ref[:, :, SG.k0:SG.k1]), \
+        f"rank {rank}: sharded fp32 min/max differs, max {np.abs(mm32 - mm32_ref[:, :, SG.k0:SG.k1]).max():.3e}"
+    assert np.allclose(hist32, mm32_hist, rtol=1e-12, atol=0)
+    for a, b, what in zip(nodes32, nodes32_ref, ("surfXX", "phiSurf", "gradPhiSurf", "n_moves")):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), f"rank {rank}: sharded fp32 node projection: {what} differs"
+    assert nodes32[3] > 0, "the node projection moved nothing: the check is vacuous"
     checks += 1
     if only == "f32":
         dist.barrier()
@@ -151,8 +165,8 @@ def main():
         rc, n, hist = G.reinit(15, DX, 0.1 * g["dxx"], tol=0.0)
         phi = G.download()
         rc, n, hist = G.minMaxFlow(13, DX, 0.01 * g["dxx"], tol=0.0)
-        return sign, phi, G.download(), n, hist
-    sign_ref, phi_ref, mm_ref, mm_n, mm_hist = whole(shape, run_whole2)
+        return sign, phi, G.download(), n, hist, G.advectNodes(g["xLo"], DX, X, iter=50)
+    sign_ref, phi_ref, mm_ref, mm_n, mm_hist, nodes_ref = whole(shape, run_whole2)
     SG = ShardedGrid(g["nx"], g["ny"], g["nz"])
     SG.fill(1.0)
     SG.signSearch(g["xLo"], DX, X, E, g["box"])
@@ -169,6 +183,11 @@ def main():
     assert n2 == mm_n and np.array_equal(mm, mm_ref[:, :, SG.k0:SG.k1]), \
         f"rank {rank}: sharded min/max differs, max {np.abs(mm - mm_ref[:, :, SG.k0:SG.k1]).max():.3e}"
     assert np.allclose(hist2, mm_hist, rtol=1e-12, atol=0) and (nb == 1).any()
+    # node projection (set3d.f90:465-501) on the slabs: every rank projects all nodes, gathering phi from the peers' slabs
+    nodes = SG.advectNodes(g["xLo"], DX, X, iter=50)
+    for a, b, what in zip(nodes, nodes_ref, ("surfXX", "phiSurf", "gradPhiSurf", "n_moves")):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), f"rank {rank}: sharded node projection: {what} differs"
+    assert nodes[3] > 0, "the node projection moved nothing: the check is vacuous"
     SG.close()
     checks += 1
 

@@ -47,7 +47,10 @@ def emu(request):
     return L
 
 
-@pytest.mark.parametrize("shape,ncta", [((22, 21, 23), 1), ((24, 36, 22), 4), ((40, 38, 36), 9), ((12, 50, 20), 6)])
+# the last two shapes have tiles that lie inside the high-order window with all halo rows present, and enough steps along x
+# for the steady-state copy of the step body (lsf_march.cuh, ST = true) to run: (60,40,39) on one tile, (47,56,55) on four
+@pytest.mark.parametrize("shape,ncta", [((22, 21, 23), 1), ((24, 36, 22), 4), ((40, 38, 36), 9), ((12, 50, 20), 6),
+                                        ((60, 40, 39), 4), ((47, 56, 55), 5)])
 def test_march_schedule_is_an_exact_reordering(emu, oracle, shape, ncta):
     p0 = synth_field(shape, seed=1)
     pS = p0.copy(order="F")
@@ -66,7 +69,7 @@ def test_march_schedule_is_an_exact_reordering(emu, oracle, shape, ncta):
 
 
 @pytest.mark.parametrize("shape,nranks,ncta,m", [((22, 21, 40), 2, 2, 1), ((20, 36, 51), 3, 3, 2), ((14, 70, 33), 4, 2, 3),
-                                                 ((12, 20, 64), 8, 1, 1)])
+                                                 ((12, 20, 64), 8, 1, 1), ((50, 40, 80), 2, 3, 2)])
 def test_march_slab_pipeline_is_an_exact_reordering(emu, oracle, shape, nranks, ncta, m):
     """z-slab sharding (lsf_slab.cuh): `nranks` slabs sweep concurrently, each on its own local array with
     ghost planes, coupled only through the streaming halo (peer stores + in_progress flags).  The gathered
