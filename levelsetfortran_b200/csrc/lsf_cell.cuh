@@ -163,7 +163,19 @@ struct FastArith {
         return __longlong_as_double(ia > ib ? ia : ib);
 #endif
     }
-    static LSF_HD double rsq(double x) { return rsqrt(x); }
+    // 1/sqrt(x) and sqrt(x) without the library's special-case path (a CALL that 15 % of the warps of the bench grid took:
+    // far from the surface phi is constant and the sum of squares under the root is exactly 0): MUFU seed (relative error
+    // < 2^-20) + one third-order step  y1 = y0 + y0 e (1/2 + 3/8 e),  e = 1 - x y0^2  ->  relative error ~ e^3, below 1 ulp.
+    // x = 0 gives y0 = +inf and a NaN from 0 * inf: exactly what update() needs (0 * rsqrt(0) = NaN is the reference's 0/0,
+    // subs.f90:169); fsqrt returns 0 for zero and denormal arguments.
+    static LSF_HD double rsq(double x)
+    {
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+        const double e = fma(-x, y0 * y0, 1.0);
+        return fma(fma(0.375, e, 0.5), y0 * e, y0);
+    }
+    static LSF_HD double fsqrt(double x) { return __double2hiint(x) < 0x00100000 ? 0.0 : x * rsq(x); }
     static LSF_HD double flip_if(double x, bool f) { return __hiloint2double(__double2hiint(x) ^ (f ? (int)0x80000000 : 0), __double2loint(x)); }
 #else
     static LSF_HD double flip_if(double x, bool f) { return f ? -x : x; }
@@ -172,6 +184,7 @@ struct FastArith {
     static LSF_HD double dabs(double x) { return fabs(x); }
     static LSF_HD double max_nn(double a, double b) { return a > b ? a : b; }
     static LSF_HD double rsq(double x) { return 1.0 / sqrt(x); }
+    static LSF_HD double fsqrt(double x) { return sqrt(x); }
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -324,7 +337,7 @@ struct FastArith {
         const double u0 = max_nn(x1 * x1, x2 * x2), u1 = max_nn(y1 * y1, y2 * y2), u2 = max_nn(z1 * z1, z2 * z2);
         const double k2 = cc.k12 * cc.k12;
         g[0] = k2 * u0; g[1] = k2 * u1; g[2] = k2 * u2;      // only stored by the WG plane kernel; dead code elsewhere
-        return cc.k12 * sqrt((u0 + u1) + u2);
+        return cc.k12 * fsqrt((u0 + u1) + u2);
     }
 
     // `sens` flags an ill-conditioned update: d(sgn (1-gM))/d(gM) contains  k1 * dx^2 / (2 D)  with
@@ -368,21 +381,23 @@ struct F32Arith {
     static LSF_HD float rsq(float x) { return 1.0f / sqrtf(x); }
     static LSF_HD float sqr(float x) { return sqrtf(x); }
 #endif
-    static LSF_HD void weights(float E0, float E1, float E2, float &w0x2, float &w2mh)
+    // One side of one direction, FastArith's fused form: r (n0 A + P s15) = half the WENO correction plus s/4, with the three
+    // E_k normalised by their sum first (see above: keeps the products of squares inside the fp32 range)
+    static LSF_HD float side(float E0, float E1, float E2, float A, float s15)
     {
         const float rs = rcp((E0 + E1) + E2);
         const float n0e = E0 * rs, n1e = E1 * rs, n2e = E2 * rs;
         const float q0 = n0e * n0e, q1 = n1e * n1e, q2 = n2e * n2e;
-        const float n0 = q1 * q2, x = q0 * q2, y3 = 3.0f * (q0 * q1);
-        const float D = fmaf(6.0f, x, y3 + n0);
-        const float r = rcp(D);
-        w0x2 = (n0 + n0) * r;
-        w2mh = fmaf(y3, r, -0.5f);
+        const float n0 = q1 * q2, x = q0 * q2, P = q0 * q1;
+        const float D = fmaf(6.0f, x, fmaf(3.0f, P, n0));
+        return rcp(D) * fmaf(n0, A, P * s15);
     }
 
+    // dminus / dplus are returned UNSCALED like FastArith's: 12 dx times the one-sided derivatives (godunov applies 1/(12 dx) once)
     template <bool YQ>
     static LSF_HD void weno_dir(const float v[7], const CellConstT<float> &cc, float &dminus, float &dplus)
     {
+        (void)cc;
         const float e0 = v[1] - v[0], e1 = v[2] - v[1], e2 = v[3] - v[2];
         const float e3 = v[4] - v[3], e4 = v[5] - v[4], e5 = v[6] - v[5];
         const float am = e1 - e0, bm = e2 - e1, c = e3 - e2, bp = e4 - e3, ap = e5 - e4;
@@ -390,44 +405,43 @@ struct F32Arith {
         const float mc = fmaxf(fmaxf(fabsf(e1), fabsf(e2)), fmaxf(fabsf(e3), fabsf(e4)));
         const float mp = YQ ? mc : fmaxf(mc, fabsf(e5));          // subs.f90:576: p5 == 0 in y
         const float mm = fmaxf(mc, fabsf(e0));
-        const float tiny = 1.0e-30f;
-        const float epsp = fmaf(1.0e-6f * mp, mp, tiny);
-        const float epsm = fmaf(1.0e-6f * mm, mm, tiny);
-        const float s13b = (13.0f * tpb) * tpb, s13c = (13.0f * tmc) * tmc;
+        // everything below is (eps + IS)/3 (the common factor cancels in the weights): eps/3 = (1e-6/3) max e^2 + tiny,
+        // IS/3 = (13/3) u^2 + v^2
+        constexpr float k13 = 13.0f / 3.0f, keps = 1.0e-6f / 3.0f, tiny = 1.0e-30f;
+        const float epsp = fmaf(keps * mp, mp, tiny);
+        const float epsm = fmaf(keps * mm, mm, tiny);
+        const float kb = k13 * tpb, kc = k13 * tmc;
         float t;
-        t = fmaf(-3.0f, bp, ap); const float E0p = fmaf(13.0f * tpa, tpa, fmaf(3.0f * t, t, epsp));
-        t = bp + c;              const float E1p = fmaf(3.0f * t, t, s13b + epsp);
-        t = fmaf(3.0f, c, -bm);  const float E2p = fmaf(3.0f * t, t, s13c + epsp);
-        t = fmaf(-3.0f, bm, am); const float E0m = fmaf(13.0f * tma, tma, fmaf(3.0f * t, t, epsm));
-        t = bm + c;              const float E1m = fmaf(3.0f * t, t, s13c + epsm);
-        t = fmaf(3.0f, c, -bp);  const float E2m = fmaf(3.0f * t, t, s13b + epsm);
-        float w0p2, w2ph, w0m2, w2mh;
-        weights(E0p, E1p, E2p, w0p2, w2ph);
-        weights(E0m, E1m, E2m, w0m2, w2mh);
-        const float s = tpb - tmc;
-        const float Yp = fmaf(w0p2, tpa - tpb, w2ph * s);
-        const float Ym = fmaf(w0m2, tma + tmc, w2mh * s);
+        t = fmaf(-3.0f, bp, ap); const float E0p = fmaf(k13 * tpa, tpa, fmaf(t, t, epsp));
+        t = bp + c;              const float E1p = fmaf(t, t, fmaf(kb, tpb, epsp));
+        t = fmaf(3.0f, c, -bm);  const float E2p = fmaf(t, t, fmaf(kc, tmc, epsp));
+        t = fmaf(-3.0f, bm, am); const float E0m = fmaf(k13 * tma, tma, fmaf(t, t, epsm));
+        t = bm + c;              const float E1m = fmaf(t, t, fmaf(kc, tmc, epsm));
+        t = fmaf(3.0f, c, -bp);  const float E2m = fmaf(t, t, fmaf(kb, tpb, epsm));
+        const float s = tpb - tmc, s15 = 1.5f * s;
         const float cen = fmaf(7.0f, e2 + e3, -(e1 + e4));
-        dminus = cc.k12 * fmaf(-2.0f, Ym, cen);
-        dplus = cc.k12 * fmaf(2.0f, Yp, cen);
+        dplus = fmaf(4.0f, side(E0p, E1p, E2p, tpa - tpb, s15), cen - s);
+        dminus = fmaf(-4.0f, side(E0m, E1m, E2m, tma + tmc, s15), cen + s);
     }
 
     static LSF_HD void lo_dir(float vm, float vc, float vp, const CellConstT<float> &cc, float &dminus, float &dplus)
     {
-        dminus = (vc - vm) * cc.inv_dx;
-        dplus = (vp - vc) * cc.inv_dx;
+        (void)cc;
+        dminus = 12.0f * (vc - vm);          // unscaled like weno_dir
+        dplus = 12.0f * (vp - vc);
     }
 
-    static LSF_HD float godunov(float phic, float a, float b, float c, float d, float e, float f, float g[3], const CellConstT<float> &)
+    // a..f: 12 dx times the one-sided derivatives; returns gM = |grad phi| (subs.f90:702)
+    static LSF_HD float godunov(float phic, float a, float b, float c, float d, float e, float f, float g[3], const CellConstT<float> &cc)
     {
         const bool pos = phic > 0.f;
         const float x1 = fmaxf(pos ? a : b, 0.f), x2 = fminf(pos ? b : a, 0.f);
         const float y1 = fmaxf(pos ? c : d, 0.f), y2 = fminf(pos ? d : c, 0.f);
         const float z1 = fmaxf(pos ? e : f, 0.f), z2 = fminf(pos ? f : e, 0.f);
-        g[0] = fmaxf(x1 * x1, x2 * x2);
-        g[1] = fmaxf(y1 * y1, y2 * y2);
-        g[2] = fmaxf(z1 * z1, z2 * z2);
-        return sqr(g[0] + g[1] + g[2]);
+        const float u0 = fmaxf(x1 * x1, x2 * x2), u1 = fmaxf(y1 * y1, y2 * y2), u2 = fmaxf(z1 * z1, z2 * z2);
+        const float k2 = cc.k12 * cc.k12;
+        g[0] = k2 * u0; g[1] = k2 * u1; g[2] = k2 * u2;      // dead code in the fp32 kernels (no gradPhi outputs in this mode)
+        return cc.k12 * sqr((u0 + u1) + u2);
     }
 
     // no conditioning guard in fp32 mode: the 1e-4 contract is far above the amplification FastArith guards against

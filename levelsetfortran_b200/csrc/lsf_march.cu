@@ -41,7 +41,9 @@ typedef void (*MarchKernel)(const MarchParams);
 
 // ---- fp32 mode (F32Arith, float ring): single GPU -------------------------------------------------
 #ifndef LSF_OCC32
-#define LSF_OCC32 4    // resident CTAs per SM: 64 registers per thread, no spills (2, 3 and 4 CTAs measured within 2 %)
+#define LSF_OCC32 3    // resident CTAs per SM the fp32 kernels are compiled for (85 registers).  Session 12, 1024^3 / 512^3 Gcell/s:
+                       // 4 CTAs (64 regs) 45.2 / 21.9, 3 CTAs 45.8 / 25.7, 2 CTAs (128 regs) 44.0 / 29.3 -- below 2048 tiles a sweep
+                       // cannot feed more than 2 CTAs per SM (the dependence chain between tiles binds), so those run with 2
 #endif
 typedef MarchCfg<LSF_TB, LSF_TC, LSF_ROWS, float> CFG32;
 typedef MarchParamsT<float> MarchParamsF;
@@ -258,7 +260,7 @@ void launch_reinit_sweep_march_f32(Grid *g, int raster, const CellConst &cc)
     cudaMemsetAsync(g->march_ticket, 0, sizeof(unsigned), G.stream);
     p.col_next = march_colnext_for_sweep(g, p.ntb);
     static const int occ_env32 = getenv("LSF_OCC32_RUN") ? atoi(getenv("LSF_OCC32_RUN")) : 0;   // experiments: fewer resident CTAs
-    const int occ = occ_env32 > 0 ? occ_env32 : (sharded(g) ? 2 : LSF_OCC32);                   // z-slabs: see launch_reinit_sweep_march
+    const int occ = occ_env32 > 0 ? occ_env32 : ((sharded(g) || p.ntiles < 2048) ? 2 : LSF_OCC32);   // z-slabs: see launch_reinit_sweep_march
     const int ncta = p.ntiles < occ * G.num_sms ? p.ntiles : occ * G.num_sms;
     march_kernel_f32(p.fa, p.fb, p.fc, sharded(g))<<<ncta, CFG32::THREADS, sizeof(MarchSmem<CFG32>), G.stream>>>(p);
     G.n_launch++;

@@ -173,6 +173,12 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
 #ifndef LSF_SPLIT_BAR
 #define LSF_SPLIT_BAR 1         // 1 (default): split step barrier -- a thread ARRIVES after its deposits, computes the x direction of its NEXT
 #endif                          //    cell from a register window of its own row, and only then WAITS for the other threads' deposits
+#ifndef LSF_PREFETCH
+#define LSF_PREFETCH 1          // global loads issued one step ahead and carried in registers (ncu r2b: 12 % / 17 % of fp64 / fp32 warp time waited
+#endif                          //    for phiS at its first use).  Bit 0: phiS, bit 1: look-ahead cell, bit 2: +b/+c halo rows, bit 3: -b/-c halo rows.
+                                //    Session 14, fp64 / fp32 Gcell/s at 1024^3: 0 -> 33.5 / 45.8, 1 -> 33.9 / 49.0, 3 -> 33.6 / 8.5 (!), 7 -> 30.9 / 7.1,
+                                //    15 -> 33.6 / 13.0: a look-ahead or halo load left in flight across the step's stores to the same rows is
+                                //    expensive (fp32 most: 8 cells per sector), so only phiS -- read-only -- is fetched ahead
 #ifndef LSF_STEADY
 #define LSF_STEADY 1            // 1 (default): second copy of the step body for the steps of interior tiles in which every range test holds
 #endif
@@ -210,6 +216,8 @@ LSF_DEV int m_imin(int a, int b) { return a < b ? a : b; }
 struct StepGeneric { static constexpr bool value = false; };
 struct StepSteady { static constexpr bool value = true; };
 
+constexpr int M_PFM = (LSF_PREFETCH & 8) ? 1 : 0;  // extra steps a predecessor must be ahead: -b/-c halo values are fetched one step before their use
+                                              // (progress is published in the same phase, at steps = CHUNK-1+M_PFM mod CHUNK, so the lag stays minimal);
 constexpr int M_H = 3;                       // stencil half-width
 constexpr int M_NSLOT = 8;                   // hyperplane slots in the ring (each stored twice)
 constexpr bool M_DUP = (LSF_RING_DUP != 0);
@@ -573,9 +581,9 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
 
     // start slack (see MarchParamsT::slack): same flags, a larger head start
     if (p.slack > 0) {
-        if (tid == TID_PB && predB) wait_ge<false>(predB, ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + p.slack), p.ctrl);
+        if (tid == TID_PB && predB) wait_ge<false>(predB, ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + M_PFM + p.slack), p.ctrl);
         if (tid == TID_PC && predC) {
-            const long long need = ebase + M_BIAS + (M_CHUNK - 1 + TC + (CFG::VEC - 1) + p.slack);
+            const long long need = ebase + M_BIAS + (M_CHUNK - 1 + TC + (CFG::VEC - 1) + M_PFM + p.slack);
             if (predCpeer) wait_ge<true>(predC, need, p.ctrl); else wait_ge<false>(predC, need, p.ctrl);
         }
         p_sync();
@@ -618,14 +626,44 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         if (interior) { T0 = p.lo_a + TB + TC; T1 = p.hi_a + 2; }
         if (T1 < T0) T1 = T0;
     }
+    // Prefetch (PF).  The values step t needs from global memory -- the look-ahead cell of the own row, phiS of the cell being
+    // updated, one cell of the halo row this thread feeds -- are loaded during step t-1 and carried in registers, so their L2 /
+    // HBM latency overlaps a whole step of arithmetic instead of the few hundred instructions between a load and its use.  All
+    // three are safe a step early: phiS is read-only; look-ahead and +b/+c halo cells are OLD values that their owner overwrites
+    // many steps later; -b/-c halo cells are the predecessors' NEW values, for which every flag test asks for one more step of
+    // progress (M_PFM).  The first flag test of a tile sits at the end of step -1, so the -b/-c cells of step 0 are loaded in
+    // step 0 itself.
+    constexpr bool PF = (LSF_PREFETCH != 0) && R == 1 && CFG::VEC == 1 && !OV;
+    real laN = 0, psN = 0, hvN[CFG::HR];
+#pragma unroll
+    for (int r = 0; r < CFG::HR; ++r) hvN[r] = 0;
+    // loads of step tn; pOut / pSgn point `off` cells before those of step tn, hp at them
+    auto prefetch = [&](const int tn, const int off, auto steady_tag) {
+        constexpr bool ST = decltype(steady_tag)::value;
+        const int a = 1 + tn - sig[0], a4 = a + M_LOOK;
+        laN = 0; psN = 0;
+        if ((LSF_PREFETCH & 2) && (ST || (rowValid[0] && (a4 >= 0) && (a4 <= p.nx)))) laN = p_ldcg(pOut[0] + (M_LOOK + off) * SA);
+        if ((LSF_PREFETCH & 1) && (ST || (compValid[0] && (a >= 1) && (a <= p.nx - 1)))) psN = p_ldcg(pSgn[0] + off * SA);
+#pragma unroll
+        for (int r = 0; r < CFG::HR; ++r) {
+            hvN[r] = 0;
+            if (hvalid[r]) {
+                const int hhn = hlow[r] ? tn : tn + M_LOOK;
+                const int ah = 1 + hhn - hsig[r];
+                if (!(LSF_PREFETCH & (hlow[r] ? 8 : 4))) continue;
+                if (ST || (hhn >= 0 && ah >= 0 && ah <= p.nx && !(hlow[r] && tn == 0))) hvN[r] = p_ldcg(hp[r]);
+            }
+        }
+    };
+    if constexpr (PF) prefetch(-M_LOOK, 0, StepGeneric());
     auto body = [&](const int t, auto steady_tag) {
         constexpr bool ST = decltype(steady_tag)::value;
         // ---- wait for the two predecessor tiles at chunk starts ---------------------------
         // (SPLIT && LSF_FOLD_FLAGS: folded into the previous step's barrier instead, see below)
         if (!(SPLIT && LSF_FOLD_FLAGS) && t >= 0 && (t % M_CHUNK) == 0) {
             // (a vector load of a -b/-c halo row fetches the predecessor's cells of up to VEC-1 later steps)
-            const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + TB + (VEC - 1));
-            const long long need_c = ebase + M_BIAS + (t + M_CHUNK - 1 + TC + (VEC - 1));
+            const long long need_b = ebase + M_BIAS + (t + M_CHUNK - 1 + TB + (VEC - 1) + M_PFM);
+            const long long need_c = ebase + M_BIAS + (t + M_CHUNK - 1 + TC + (VEC - 1) + M_PFM);
 #if defined(LSF_EXP_TIMING)
             long long tw0 = 0;
             if (tid == 0) tw0 = clock64();
@@ -658,7 +696,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             ldLook[r] = ST ? true : (rowValid[r] && (a4 >= 0) && (a4 <= p.nx));
             la[r] = 0;
 #if !(LSF_EXP_NOLDG_MASK & 1)
-            if (ldLook[r]) {
+            if constexpr (PF && (LSF_PREFETCH & 2)) la[r] = laN;
+            else if (ldLook[r]) {
                 if constexpr (VEC > 1) la[r] = rdLook.get(pOut[r] + M_LOOK * SA);
                 else if (OV) la[r] = p_ldcg(pOut[r] + M_LOOK * SA + ((a4 == 0 || a4 == p.nx) ? p.shell_rd_delta : rowShell[r]));
                 else la[r] = (LSF_LD_CACHED & 1) ? p_ldca(pOut[r] + M_LOOK * SA) : p_ldcg(pOut[r] + M_LOOK * SA);
@@ -667,7 +706,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             active[r] = ST ? true : (compValid[r] && (a >= 1) && (a <= p.nx - 1));
             ps[r] = 0;
 #if !(LSF_EXP_NOLDG_MASK & 2)
-            if (active[r]) {
+            if constexpr (PF && (LSF_PREFETCH & 1)) ps[r] = psN;
+            else if (active[r]) {
                 if constexpr (VEC > 1) ps[r] = rdSgn.get(pSgn[r]);
                 else ps[r] = (LSF_LD_CACHED & 2) ? p_ldca(pSgn[r]) : p_ldcg(pSgn[r]);
             }
@@ -687,7 +727,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
                 const int ah = 1 + hh[r] - hsig[r];
 #if !(LSF_EXP_NOLDG_MASK & 4)
                 if (ST || (hh[r] >= 0 && ah >= 0 && ah <= p.nx)) {
-                    if constexpr (VEC > 1) hv[r] = rdHalo[r].get(hp[r]);
+                    if constexpr (PF) hv[r] = (!(LSF_PREFETCH & (hlow[r] ? 8 : 4)) || (hlow[r] && !ST && t == 0)) ? p_ldcg(hp[r]) : hvN[r];
+                    else if constexpr (VEC > 1) hv[r] = rdHalo[r].get(hp[r]);
                     else if (OV) hv[r] = p_ldcg(hp[r] + ((ah == 0 || ah == p.nx) ? p.shell_rd_delta : hShell[r]));
                     else hv[r] = ((LSF_LD_CACHED & 4) && !hlow[r]) ? p_ldca(hp[r]) : p_ldcg(hp[r]);
                     hdep[r] = true;
@@ -698,6 +739,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             }
             hp[r] += SA;
         }
+        if constexpr (PF) prefetch(t + 1, 1, steady_tag);          // the loads of step t+1 (hp has moved on, pOut / pSgn not yet)
         // ---- (2) cell updates ---------------------------------------------------------------
         real pn[R];
         bool sens = false;
@@ -751,7 +793,7 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         // ---- (4) publish progress every CHUNK steps -----------------------------------------
         // (all threads' stores -> CTA barrier -> one thread's gpu-scope release: cumulative, so the
         // whole tile's stores of this chunk are visible to whoever acquires the flag)
-        const bool pub = (t >= 0) && ((t % M_CHUNK) == M_CHUNK - 1);
+        const bool pub = (t >= M_PFM) && (((t - M_PFM) % M_CHUNK) == M_CHUNK - 1);
 #if defined(LSF_EXP_NOSYNC)          // timing experiment only (results are wrong): no CTA barrier per step
         __syncwarp();
 #else
@@ -760,8 +802,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
                 // The predecessor flags of the chunk that starts with step t+1 were read at the top of this step (the L2 round
                 // trip is long over).  The two polling threads settle them BEFORE they arrive: whoever passes this step's
                 // barrier knows the flags hold -- no separate CTA barrier at the chunk start.
-                const long long need_b = ebase + M_BIAS + (t + 1 + M_CHUNK - 1 + TB + (VEC - 1));
-                const long long need_c = ebase + M_BIAS + (t + 1 + M_CHUNK - 1 + TC + (VEC - 1));
+                const long long need_b = ebase + M_BIAS + (t + 1 + M_CHUNK - 1 + TB + (VEC - 1) + M_PFM);
+                const long long need_c = ebase + M_BIAS + (t + 1 + M_CHUNK - 1 + TC + (VEC - 1) + M_PFM);
 #if defined(LSF_EXP_TIMING)
                 long long tw0 = 0;
                 if (tid == 0) tw0 = clock64();
@@ -896,8 +938,8 @@ LSF_DEV int march_pick(const MarchParamsT<T> &p, int &jlo)
 {
     constexpr int TB = CFG::TB, TC = CFG::TC;
     const long long ebase = p.epoch << 32;
-    const long long need_b = ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + p.slack);
-    const long long need_c = ebase + M_BIAS + (M_CHUNK - 1 + TC + (CFG::VEC - 1) + p.slack);
+    const long long need_b = ebase + M_BIAS + (M_CHUNK - 1 + TB + (CFG::VEC - 1) + M_PFM + p.slack);
+    const long long need_c = ebase + M_BIAS + (M_CHUNK - 1 + TC + (CFG::VEC - 1) + M_PFM + p.slack);
     long long spins = 0;
     for (;;) {
         bool all_done = true;
