@@ -170,12 +170,19 @@ struct FastArith {
     // subs.f90:169); fsqrt returns 0 for zero and denormal arguments.
     static LSF_HD double rsq(double x)
     {
+#if defined(LSF_LIB_SQRT)
+        return rsqrt(x);
+#endif
         double y0;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
         const double e = fma(-x, y0 * y0, 1.0);
         return fma(fma(0.375, e, 0.5), y0 * e, y0);
     }
+#if defined(LSF_LIB_SQRT)
+    static LSF_HD double fsqrt(double x) { return sqrt(x); }
+#else
     static LSF_HD double fsqrt(double x) { return __double2hiint(x) < 0x00100000 ? 0.0 : x * rsq(x); }
+#endif
     static LSF_HD double flip_if(double x, bool f) { return __hiloint2double(__double2hiint(x) ^ (f ? (int)0x80000000 : 0), __double2loint(x)); }
 #else
     static LSF_HD double flip_if(double x, bool f) { return f ? -x : x; }

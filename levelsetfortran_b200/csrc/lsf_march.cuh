@@ -41,9 +41,28 @@
 #define LSF_DEV __device__ __forceinline__
 namespace lsf {
 LSF_DEV void p_sync() { __syncthreads(); }
+// The three global loads of a step and the twelve ring gathers are ORDERED accesses (relaxed.gpu loads / volatile shared loads in
+// volatile asm), which the compiler keeps in program order: the global loads issue before the gathers, at the top of the step.
+// With plain loads ptxas sinks each of them to 25-105 instructions before its first use (tools/sass_ldg_distance.py) -- and in one
+// build (z-slab kernels without the library sqrt's CALL) to 7-29, which made a sweep 7x slower.  LSF_ORDERED_LD: 2 = relaxed.gpu
+// (default; session 21: 34.6 fp64 / 49.5 fp32 Gcell/s at 1024^3), 1 = ld.volatile (33.7 / 45.2), 0 = plain ld.cg (33.9 / 49.1)
+#ifndef LSF_ORDERED_LD
+#define LSF_ORDERED_LD 2
+#endif
+#if LSF_ORDERED_LD == 2
+LSF_DEV double p_ldcg(const double *p) { double v; asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+LSF_DEV float p_ldcg(const float *p) { float v; asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
+template <class T> LSF_DEV T p_lds(const T *p) { return *(const volatile T *)p; }
+#elif LSF_ORDERED_LD == 1
+LSF_DEV double p_ldcg(const double *p) { double v; asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+LSF_DEV float p_ldcg(const float *p) { float v; asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
+template <class T> LSF_DEV T p_lds(const T *p) { return *(const volatile T *)p; }
+#else
+template <class T> LSF_DEV T p_lds(const T *p) { return *p; }
 LSF_DEV double p_ldcg(const double *p) { return __ldcg(p); }
-LSF_DEV void p_stcg(double *p, double v) { __stcg(p, v); }
 LSF_DEV float p_ldcg(const float *p) { return __ldcg(p); }
+#endif
+LSF_DEV void p_stcg(double *p, double v) { __stcg(p, v); }
 // L1-allocating load: only for data no other CTA writes while this tile may still hold the line (phiS; OLD values)
 LSF_DEV double p_ldca(const double *p) { return __ldca(p); }
 LSF_DEV float p_ldca(const float *p) { return __ldca(p); }
@@ -110,23 +129,38 @@ LSF_DEV void p_emu_hook(bool) {}   // CPU emulation only (tests/emu/emu_prims.h)
 // split-phase CTA barrier (mbarrier in shared memory): every warp arrives once per phase (one elected lane after a
 // __syncwarp, release), a waiter spins on the phase parity (acquire).  Between arrive and wait a thread may do anything
 // that touches neither the slot ring nor another thread's data.
+// experiments (session 16): LSF_BAR_ALLARRIVE -- every thread arrives (no __syncwarp + elected lane); LSF_BAR_TESTWAIT -- the
+// waiter polls the non-blocking mbarrier.test_wait instead of the potentially suspending try_wait
 LSF_DEV void p_bar_init(unsigned long long *bar, int nthreads)
 {
+#if defined(LSF_BAR_ALLARRIVE)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(nthreads) : "memory");
+#else
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(nthreads / 32) : "memory");
+#endif
 }
 LSF_DEV void p_bar_arrive(unsigned long long *bar)
 {
+#if defined(LSF_BAR_ALLARRIVE)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#else
     __syncwarp();
     if ((threadIdx.x & 31) == 0)
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#endif
 }
 LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
 {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
     unsigned ok;
     do {
+#if defined(LSF_BAR_TESTWAIT)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(phase & 1u) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(phase & 1u) : "memory");
+#endif
     } while (!ok);
 }
 }  // namespace lsf
@@ -179,6 +213,9 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
                                 //    Session 14, fp64 / fp32 Gcell/s at 1024^3: 0 -> 33.5 / 45.8, 1 -> 33.9 / 49.0, 3 -> 33.6 / 8.5 (!), 7 -> 30.9 / 7.1,
                                 //    15 -> 33.6 / 13.0: a look-ahead or halo load left in flight across the step's stores to the same rows is
                                 //    expensive (fp32 most: 8 cells per sector), so only phiS -- read-only -- is fetched ahead
+#ifndef LSF_PREFETCH_MG
+#define LSF_PREFETCH_MG 0       // the same on z-slab kernels (see march_tile)
+#endif
 #ifndef LSF_STEADY
 #define LSF_STEADY 1            // 1 (default): second copy of the step body for the steps of interior tiles in which every range test holds
 #endif
@@ -451,8 +488,8 @@ LSF_DEV typename AR::real march_cell_yz(const typename AR::real *Sown, int t, ty
 #pragma unroll
     for (int m = -3; m <= 3; ++m) {
         if (m != 0) {
-            vy[FB ? 3 - m : 3 + m] = Sown[m * W + w.o[3 + m]];
-            vz[FC ? 3 - m : 3 + m] = Sown[m * RP + w.o[3 + m]];
+            vy[FB ? 3 - m : 3 + m] = p_lds(Sown + m * W + w.o[3 + m]);
+            vz[FC ? 3 - m : 3 + m] = p_lds(Sown + m * RP + w.o[3 + m]);
         }
     }
     vy[3] = phic; vz[3] = phic;
@@ -633,7 +670,10 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     // many steps later; -b/-c halo cells are the predecessors' NEW values, for which every flag test asks for one more step of
     // progress (M_PFM).  The first flag test of a tile sits at the end of step -1, so the -b/-c cells of step 0 are loaded in
     // step 0 itself.
-    constexpr bool PF = (LSF_PREFETCH != 0) && R == 1 && CFG::VEC == 1 && !OV;
+    // (not on z-slabs: there the same one-step-ahead phiS load made every sweep 2.6x slower -- session 15/17, N = 2: 95 ms instead
+    // of 36 ms per sweep kernel with bit-identical results; the tiles of the slab's first and last tile rows, which execute
+    // system-scope fences and peer stores every chunk and pace all other tiles, do not tolerate a load in flight across them)
+    constexpr bool PF = (LSF_PREFETCH != 0) && R == 1 && CFG::VEC == 1 && !OV && (!MG || LSF_PREFETCH_MG);
     real laN = 0, psN = 0, hvN[CFG::HR];
 #pragma unroll
     for (int r = 0; r < CFG::HR; ++r) hvN[r] = 0;
