@@ -181,11 +181,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+NCU_TAG = {False: "r2c_march", True: "r2c_march_f32"}     # committed `ncu --set full` captures of the current sweep kernels
+
+
 def ncu_traffic(grid, f32=False):
     """DRAM bytes (read + write) of ONE sweep-kernel launch from the committed `ncu --set full` capture of this
-    kernel at the same grid size (profiles/r1g_march_<grid>_full.txt; fp32 kernel: r1j_march_f32_<grid>_full.txt),
+    kernel at the same grid size (profiles/r2c_march_<grid>_full.txt; fp32 kernel: r2c_march_f32_<grid>_full.txt),
     or None if there is no capture."""
-    path = os.path.join(ROOT, "profiles", f"r1j_march_f32_{grid}_full.txt" if f32 else f"r1g_march_{grid}_full.txt")
+    path = os.path.join(ROOT, "profiles", f"{NCU_TAG[bool(f32)]}_{grid}_full.txt")
     if not os.path.exists(path):
         return None
     tot = 0.0
@@ -620,7 +623,7 @@ def run_gpu(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(n, f32),
                              "traffic_note": "DRAM read+write bytes of one launch of a whole %d^3 grid, ncu --set full (profiles/%s_%d_full.txt); "
-                                             "algorithmic bytes per launch: %.4g" % (n, "r1j_march_f32" if f32 else "r1g_march", n,
+                                             "algorithmic bytes per launch: %.4g" % (n, NCU_TAG[bool(f32)], n,
                                                                                     bytes_per_update * cells_per_launch),
                              "kernel": ("k_reinit_march_f32" if f32 else "k_reinit_march") if args.sched == "march" else "k_reinit_plane",
                              "launch_ms": launch_ms, "peak_source": peak_src,

@@ -63,6 +63,7 @@ LSF_DEV double p_ldcg(const double *p) { return __ldcg(p); }
 LSF_DEV float p_ldcg(const float *p) { return __ldcg(p); }
 #endif
 LSF_DEV void p_stcg(double *p, double v) { __stcg(p, v); }
+LSF_DEV void p_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // L1-allocating load: only for data no other CTA writes while this tile may still hold the line (phiS; OLD values)
 LSF_DEV double p_ldca(const double *p) { return __ldca(p); }
 LSF_DEV float p_ldca(const float *p) { return __ldca(p); }
@@ -213,6 +214,11 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
                                 //    Session 14, fp64 / fp32 Gcell/s at 1024^3: 0 -> 33.5 / 45.8, 1 -> 33.9 / 49.0, 3 -> 33.6 / 8.5 (!), 7 -> 30.9 / 7.1,
                                 //    15 -> 33.6 / 13.0: a look-ahead or halo load left in flight across the step's stores to the same rows is
                                 //    expensive (fp32 most: 8 cells per sector), so only phiS -- read-only -- is fetched ahead
+#ifndef LSF_L2_AHEAD
+#define LSF_L2_AHEAD 0          // > 0: every 16 steps a thread asks for the 128-byte lines of its own row (phi and phiS) that its look-ahead
+#endif                          //      will reach this many cells later (prefetch.global.L2: no register, no scoreboard).  ncu r2c: 12 % of the
+                                //      warp time waits for the look-ahead load at its deposit -- a first touch that comes from HBM -- yet the
+                                //      prefetch is a loss (session 27, 48 / 96 cells ahead: 33.4 instead of 34.2 Gcell/s fp64, 46.9 vs 49.4 fp32)
 #ifndef LSF_PREFETCH_MG
 #define LSF_PREFETCH_MG 0       // the same on z-slab kernels (see march_tile)
 #endif
@@ -726,6 +732,13 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             if (tid == TID_PC && predC) preC = predCpeer ? p_ld_relaxed_sys(predC) : p_ld_relaxed(predC);
         }
         p_emu_hook(tid == 0 && t == 6);
+        if (LSF_L2_AHEAD > 0 && R == 1 && !OV && (t & 15) == 0) {
+            const int af = 1 + t - sig[0] + M_LOOK + LSF_L2_AHEAD;            // the cell the look-ahead reaches LSF_L2_AHEAD steps from now
+            if (rowValid[0] && af >= 0 && af <= p.nx) {
+                p_prefetch_l2(pOut[0] + (M_LOOK + LSF_L2_AHEAD) * SA);
+                p_prefetch_l2(pSgn[0] + (M_LOOK + LSF_L2_AHEAD) * SA);
+            }
+        }
         // ---- (1) issue the global loads of this step --------------------------------------
         bool ldLook[R], active[R], hi[R];
         real la[R], ps[R];
@@ -780,6 +793,11 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             hp[r] += SA;
         }
         if constexpr (PF) prefetch(t + 1, 1, steady_tag);          // the loads of step t+1 (hp has moved on, pOut / pSgn not yet)
+#if defined(LSF_PIN_LOADS) && !defined(LSF_EMU)
+        // A never-taken branch ends the basic block here: ptxas does not move the loads above past it, so they are issued before
+        // the arithmetic of the step instead of right before their first use (the z-slab kernels' steady loop: 28-72 instructions)
+        if (p.tend < 0) asm volatile("trap;");
+#endif
         // ---- (2) cell updates ---------------------------------------------------------------
         real pn[R];
         bool sens = false;

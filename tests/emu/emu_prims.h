@@ -14,6 +14,7 @@ inline void p_stcg(double *p, double v) { *(volatile double *)p = v; }
 inline float p_ldcg(const float *p) { return *(const volatile float *)p; }
 inline double p_ldca(const double *p) { return *(const volatile double *)p; }
 inline float p_ldca(const float *p) { return *(const volatile float *)p; }
+inline void p_prefetch_l2(const void *) {}
 template <class T> inline T p_lds(const T *p) { return *(const volatile T *)p; }   // ring gather (shared memory on the GPU)
 inline void p_stcg(float *p, float v) { *(volatile float *)p = v; }
 template <int VEC, class T> inline void p_ldcg_vec(const T *p, T *out) { for (int q = 0; q < VEC; ++q) out[q] = *(const volatile T *)(p + q); }

@@ -600,6 +600,48 @@ extern "C" int emu_advect_nodes(const double *phi, const double *sbsrc, int nx, 
     return worst;
 }
 
+// The same on z-slabs: the global field is cut into `nranks` local arrays (owned planes + 3 ghost planes per neighbour, geometry
+// of lsf_slab.cuh) and every value is fetched through a SlabView -- the accessor the z-slab kernel uses on the peers' slabs.
+// Ghost planes are filled with NaN: the view must only ever read a plane from the rank that OWNS it.
+extern "C" int emu_advect_nodes_slabs(const double *phi, const double *sbsrc, int nx, int ny, int NZ, int nranks, const double *xLo,
+                                      double dx, double *X, int nNode, double *phiSurf, double *gradPhiSurf, int iter, long long *moves)
+{
+    NodeConst c;
+    c.sx = nx + 1; c.sxy = c.sx * (ny + 1); c.nx = nx; c.ny = ny; c.nz = NZ;
+    c.xLo[0] = xLo[0]; c.xLo[1] = xLo[1]; c.xLo[2] = xLo[2]; c.dx = dx; c.bSB = 8.1 * dx;
+    std::vector<std::vector<double>> lp(nranks), ls(nranks);
+    SlabView vp, vs;
+    memset(&vp, 0, sizeof(vp)); memset(&vs, 0, sizeof(vs));
+    vp.nranks = vs.nranks = nranks; vp.sxy = vs.sxy = c.sxy;
+    for (int r = 0; r < nranks; ++r) {
+        SlabGeom g;
+        if (!slab_geom(NZ, nranks, r, g)) return -1;
+        const size_t n = (size_t)c.sxy * (g.nzl + 1);
+        lp[r].assign(n, NAN); ls[r].assign(n, NAN);
+        for (int k = g.k0; k < g.k1; ++k) {
+            memcpy(&lp[r][(size_t)(k - g.kbase) * c.sxy], phi + (size_t)k * c.sxy, sizeof(double) * c.sxy);
+            memcpy(&ls[r][(size_t)(k - g.kbase) * c.sxy], sbsrc + (size_t)k * c.sxy, sizeof(double) * c.sxy);
+        }
+        vp.base[r] = lp[r].data(); vs.base[r] = ls[r].data();
+        vp.shift[r] = vs.shift[r] = (long long)g.kbase * c.sxy;
+        vp.kend[r] = vs.kend[r] = g.k1;
+    }
+    int worst = 0;
+    long long nm = 0;
+    for (int n = 0; n < nNode; ++n) {
+        double x[3] = {X[n], X[n + (size_t)nNode], X[n + 2 * (size_t)nNode]}, ps, gs[3];
+        int mv;
+        const int st = node_project(c, vp, vs, x, ps, gs, iter, mv);
+        if (st > worst) worst = st;
+        if (st) continue;
+        X[n] = x[0]; X[n + (size_t)nNode] = x[1]; X[n + 2 * (size_t)nNode] = x[2];
+        phiSurf[n] = ps;
+        for (int q = 0; q < 3; ++q) gradPhiSurf[n + (size_t)q * nNode] = gs[q];
+        nm += mv;
+    }
+    if (moves) *moves = nm;
+    return worst;
+}
 
 // fp32 twin of emu_march_sweep_slabs: one sweep on `nranks` z-slabs running concurrently, coupled only through the
 // streaming-halo protocol (peer stores of float values + in_progress flags).

@@ -108,3 +108,28 @@ def test_out_of_bounds_cases_are_reported(oracle, emu):  # noqa: F811
     node = np.asfortranarray(np.array([[x[2] + 0.02, 0.0, 0.0]]))
     assert oracle.advect_nodes(phi2, sb2, xLo, DX, node, 10)[0] == -3
     assert _twin(emu, phi2, phi2, xLo, node, 10)[0] == 2                 # NODE_BAND_ON_BOUNDARY
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 5])
+def test_projection_through_the_slab_view(oracle, emu, nranks):  # noqa: F811
+    """z-slabs: every value is fetched through lsf::SlabView from the local array of the rank that OWNS its plane (ghost planes
+    poisoned with NaN here).  Nodes near and across the slab boundaries; result bit-identical to the whole-grid code."""
+    rng = np.random.default_rng(7)
+    n = 48
+    x = (np.arange(n) - n / 2.0 + 0.3) * DX
+    Xg, Yg, Zg = np.meshgrid(x, x, x, indexing="ij")
+    phi = np.asfortranarray(np.sqrt(Xg ** 2 + Yg ** 2 + Zg ** 2) - 0.61 + 0.002 * rng.standard_normal((n, n, n)))
+    xLo = np.array([x[0], x[0], x[0]])
+    d = rng.standard_normal((400, 3))
+    P = np.asfortranarray(d / np.linalg.norm(d, axis=1)[:, None] * (0.61 + 0.1 * (rng.random((400, 1)) - 0.3)))
+    rc, XX, ps, gs, mv = _twin(emu, phi, phi, xLo, P)
+    assert rc == 0 and mv > 0
+    emu.emu_advect_nodes_slabs.restype = C.c_int
+    emu.emu_advect_nodes_slabs.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_double, dp, C.c_int, dp, dp, C.c_int,
+                                           C.POINTER(C.c_longlong)]
+    XX2 = P.copy(order="F")
+    ps2, gs2, mv2 = np.zeros(len(P)), np.zeros((len(P), 3), order="F"), C.c_longlong(0)
+    rc2 = emu.emu_advect_nodes_slabs(phi.ctypes.data_as(dp), phi.ctypes.data_as(dp), n - 1, n - 1, n - 1, nranks, xLo.ctypes.data_as(dp), DX,
+                                     XX2.ctypes.data_as(dp), len(P), ps2.ctypes.data_as(dp), gs2.ctypes.data_as(dp), 1000, C.byref(mv2))
+    assert rc2 == 0 and mv2.value == mv
+    assert np.array_equal(XX2, XX) and np.array_equal(ps2, ps) and np.array_equal(gs2, gs)
