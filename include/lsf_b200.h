@@ -107,7 +107,11 @@ int lsf_sign_init(double *phi, int nx, int ny, int nz, const double xLo[3], doub
  * gradPhi (0:nx,0:ny,0:nz,3) / gradPhiMag may be NULL (both are dead downstream,
  * set3d.f90:372-375); when given they receive the last sweep's weno outputs (subs.f90:696-703).
  * n_exit: loop index n at which the routine left; rms_hist[0..iter]: phiErr per sweep
- * (the values the reference prints at subs.f90:923).  Exit tolerance 1.E-5 (subs.f90:915). */
+ * (the values the reference prints at subs.f90:923).  Exit tolerance 1.E-5 (subs.f90:915).
+ * phiErr is a sum over all points: the library adds per-tile partial sums in a fixed order (deterministic run to run), the
+ * reference accumulates serially over i, j, k -- rms_hist agrees to ~1e-15 relative, so even where phi is bit-identical
+ * (LSF_ARITH_EXACT) an RMS that lands within that distance of the tolerance can leave the loop one sweep apart from the
+ * reference (never observed on the reference's inputs: the RMS changes by ~1e-3 relative per sweep there). */
 int lsf_reinit(double *phi, double *gradPhi, double *gradPhiMag, int nx, int ny, int nz,
                int iter, double dx, double h, int *n_exit, double *rms_hist);
 

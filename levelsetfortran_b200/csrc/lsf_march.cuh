@@ -214,6 +214,9 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
                                 //    Session 14, fp64 / fp32 Gcell/s at 1024^3: 0 -> 33.5 / 45.8, 1 -> 33.9 / 49.0, 3 -> 33.6 / 8.5 (!), 7 -> 30.9 / 7.1,
                                 //    15 -> 33.6 / 13.0: a look-ahead or halo load left in flight across the step's stores to the same rows is
                                 //    expensive (fp32 most: 8 cells per sector), so only phiS -- read-only -- is fetched ahead
+#ifndef LSF_PIN_LOADS
+#define LSF_PIN_LOADS 2         // see the step body
+#endif
 #ifndef LSF_L2_AHEAD
 #define LSF_L2_AHEAD 0          // > 0: every 16 steps a thread asks for the 128-byte lines of its own row (phi and phiS) that its look-ahead
 #endif                          //      will reach this many cells later (prefetch.global.L2: no register, no scoreboard).  ncu r2c: 12 % of the
@@ -793,10 +796,12 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
             hp[r] += SA;
         }
         if constexpr (PF) prefetch(t + 1, 1, steady_tag);          // the loads of step t+1 (hp has moved on, pOut / pSgn not yet)
-#if defined(LSF_PIN_LOADS) && !defined(LSF_EMU)
+#if !defined(LSF_EMU)
         // A never-taken branch ends the basic block here: ptxas does not move the loads above past it, so they are issued before
-        // the arithmetic of the step instead of right before their first use (the z-slab kernels' steady loop: 28-72 instructions)
-        if (p.tend < 0) asm volatile("trap;");
+        // the arithmetic of the step instead of right before their first use.  LSF_PIN_LOADS bit 0: single-GPU kernels (session
+        // 25: 33.3 instead of 34.5 Gcell/s -- off), bit 1: z-slab kernels, whose steady loop otherwise has 28-72 instructions
+        // between a load and its use (session 28, N = 2: 60.1 instead of 50.4 Gcell/s fp64, 72.1 instead of 67.5 fp32 -- on)
+        if ((LSF_PIN_LOADS & (MG ? 2 : 1)) && p.tend < 0) asm volatile("trap;");
 #endif
         // ---- (2) cell updates ---------------------------------------------------------------
         real pn[R];
