@@ -45,8 +45,8 @@ SWEEPS_PER_STEP = 8
 METRIC = "WENO5 reinit Gcell-updates/s"
 UNIT = "Gcell-updates/s"
 BYTES_PER_UPDATE = 24.0          # fp64: read phi + read phiS + write phi
-FP64_PER_UPDATE = 274            # executed FP64-pipe instructions per cell update of the FAST sweep kernel (ncu source page of
-                                 # profiles/r2a_march_1024_full.txt: DFMA 104.6 + DMUL 88.1 + DADD 77.1 + DSETP 4.3; round 1: 307)
+FP64_PER_UPDATE = 272            # executed FP64-pipe instructions per cell update of the FAST sweep kernel (ncu source page of the
+                                 # r2c capture, profiles/r2c_march_1024_full.txt: DFMA 102.9 + DMUL 88.4 + DADD 77.1 + DSETP 4.1; round 1: 307)
 FP64_PIPE_PEAK = 148 * 64 * 1.965e9   # lane-ops/s
 
 
