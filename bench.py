@@ -495,6 +495,28 @@ def run_gpu(args):
                              "traffic": ncu_traffic(n, True)},
                 "last_rms": float(hist32[-1]), "last_rms_fp64": float(hist[-1]) if hist is not None else None}
 
+    # ---- companion: K2' throughput mode -- Jacobi WENO5 + TVD-RK3, the north_star's literal scheme, NOT the reference's algorithm
+    # (lsf_grid_reinit_rk3; no reference parity is claimed for it, see DESIGN.md section 4 K2').  Same grid and geometry, single GPU.
+    rk3 = None
+    if world == 1 and not f32 and not args.no_rk3:
+        GR = DeviceGrid(nx, ny, nz)
+        GR.fill(1.0)
+        GR.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
+        GR.reinitRK3(1, DX, h, tol=0.0)
+        barrier()
+        krk = 3
+        rc, ne, hist_rk = GR.reinitRK3(krk, DX, h, tol=0.0)
+        ms_rk, nl_rk = _lib.last_timing()
+        GR.close()
+        ncell = (nx - 1) * (ny - 1) * (nz - 1)
+        gbs = (24.0 + 32.0 + 32.0) * ncell * krk / (ms_rk * 1e-3) / 1e9
+        rk3 = {"metric": "Jacobi WENO5 + TVD-RK3 reinit, Gcell-stage-updates/s (NOT the reference's Gauss-Seidel scheme; separate mode)",
+               "value": 3.0 * ncell * krk / (ms_rk * 1e-3) / 1e9, "unit": "Gcell-stage-updates/s", "rk_steps": krk, "ms_per_rk_step": ms_rk / krk,
+               "launches": nl_rk, "last_rms": float(hist_rk[-1]),
+               "roofline": {"bound": "hbm", "bytes_per_cell_and_step": 88.0, "achieved": gbs, "peak": measured_peak()[0], "unit": "GB/s",
+                            "frac": gbs / measured_peak()[0], "note": "stage 1 reads u, phiS and writes: 24 B; stages 2, 3 also read phi: 32 B each; "
+                            "fp64 WENO5 stays FP64-pipe bound in this mode as well"}}
+
     # ---- companion at N > 1: the fp32-mode variant of config 5 (BASELINE configs[4] "plus fp32-mode variant") ----
     if world > 1 and not f32 and not args.no_f32:
         G32 = ShardedGrid(nx, ny, nz, f32=True)
@@ -518,6 +540,26 @@ def run_gpu(args):
         fp32 = {"metric": METRIC + " (fp32 mode, config 5 weak scaling)", "value": cells_per_step * k32 / (ms32 * 1e-3) / 1e9, "unit": UNIT,
                 "dtype": "f32", "n_gpus": world, "steps": k32, "ms_per_step": ms32 / k32, "last_rms": float(hist32[-1]),
                 "digest": hexd(d32) if d32 else None}
+
+    # ---- companion at N > 1: K2' (Jacobi / TVD-RK3; not the reference's scheme) on the sharded config-5 grid -- a plain halo
+    # problem (3-plane exchange after every stage, no pipeline), the mode whose weak scaling is NOT bound by the Gauss-Seidel order
+    if world > 1 and not f32 and not args.no_rk3:
+        GR = ShardedGrid(nx, ny, nz)
+        GR.fill(1.0)
+        GR.signSearch(g["xLo"], DX, surfX, surfElem, g["box"])
+        GR.reinitRK3(1, DX, h, tol=0.0)
+        barrier()
+        krk = 3
+        rc, ne, hist_rk = GR.reinitRK3(krk, DX, h, tol=0.0)
+        ms_rk, nl_rk = _lib.last_timing()
+        GR.close()
+        trk = torch.tensor([ms_rk], dtype=torch.float64, device="cuda")
+        dist.all_reduce(trk, op=dist.ReduceOp.MAX)
+        ms_rk = float(trk.item())
+        ncell = (nx - 1) * (ny - 1) * (nz - 1)
+        rk3 = {"metric": "Jacobi WENO5 + TVD-RK3 reinit, Gcell-stage-updates/s (NOT the reference's Gauss-Seidel scheme; separate mode), config 5 weak scaling",
+               "value": 3.0 * ncell * krk / (ms_rk * 1e-3) / 1e9, "unit": "Gcell-stage-updates/s", "n_gpus": world, "rk_steps": krk,
+               "ms_per_rk_step": ms_rk / krk, "launches": nl_rk, "last_rms": float(hist_rk[-1])}
 
     # ---- e2e: the host-buffer drop-in call, pinned host memory, H2D + compute + D2H timed ------
     e2e = None
@@ -639,6 +681,7 @@ def run_gpu(args):
                 "config3": config3,
                 "minmax_flow": mm,
                 "fp32_mode": fp32,
+                "rk3_mode": rk3,
                 "node_projection": nodes,
                 "sign_search": {"ms": sign_ms, "points": int(np.prod([g["box"][1] - g["box"][0] + 1, g["box"][3] - g["box"][2] + 1,
                                                                       g["box"][5] - g["box"][4] + 1])),
@@ -667,6 +710,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--f32", action="store_true", help="measure the optional fp32 mode as the main line (single GPU)")
     ap.add_argument("--no-f32", action="store_true", help="skip the fp32-mode companion measurement")
+    ap.add_argument("--no-rk3", action="store_true", help="skip the K2' (Jacobi / TVD-RK3) companion measurement")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -823,19 +823,37 @@ int lsf_grid_reinit(lsf_grid *g, int iter, double dx, double h, double tol, int 
 int lsf_grid_reinit_rk3(lsf_grid *g, int steps, double dx, double dt, double tol, int *n_exit, double *rms_hist)
 {
     if (!g) return set_error(LSF_ERR_ARG, "null grid");
-    if (g->f32 || sharded(g)) return set_error(LSF_ERR_ARG, "reinit_rk3: fp64 single-GPU grids only");
+    if (g->f32) return set_error(LSF_ERR_ARG, "reinit_rk3: fp64 grids only");
     if (steps < 1 || !(dx > 0.)) return set_error(LSF_ERR_ARG, "reinit_rk3: bad steps/dx");
     if (g->dm.nx < 2 || g->dm.ny < 2 || g->dm.nz < 2) return set_error(LSF_ERR_ARG, "reinit_rk3: grid too small");
-    int rc = ensure_hist(g, steps);
+    int rc = slab_check_attached(g);
+    if (rc) return rc;
+    rc = ensure_hist(g, steps);
     if (rc) return rc;
     g->sb_from_phiN = false;
+    const bool mg = sharded(g);
     const size_t bytes = sizeof(double) * (size_t)g->np;
+    // Stage buffers: phi1 = phiN; phi2 is extra.  On z-slabs every stage buffer has to be peer-visible (its ghost planes are
+    // filled by the neighbours after each stage): phi2 is the phi of a transient sharded grid of the same geometry that the
+    // ranks create and connect together (lsf_slab.cu: sgrid_shadow_f64).  A plain halo problem -- no dependence between the cells
+    // of a stage -- so unlike the Gauss-Seidel path there is no pipeline: stage, boundary block, 3-plane exchange, next stage.
     double *phi2 = nullptr, *scratch = nullptr;
+    lsf_grid *sh = nullptr;
     const long long nblk = rk_nblocks(g);
-    LSF_CUDA(cudaMalloc(&phi2, bytes));
-    cudaError_t e = cudaMalloc(&scratch, sizeof(double) * (size_t)nblk);
-    if (e != cudaSuccess) { cudaFree(phi2); return set_error(LSF_ERR_CUDA, "reinit_rk3: %s", cudaGetErrorString(e)); }
+    if (mg) {
+        rc = sgrid_shadow_f64(g, &sh);
+        if (rc) return rc;
+        phi2 = sh->phi;
+    } else {
+        LSF_CUDA(cudaMalloc(&phi2, bytes));
+    }
+    cudaError_t e = cudaMalloc(&scratch, sizeof(double) * (size_t)(nblk + BC_BLOCKS));
+    if (e != cudaSuccess) {
+        if (mg) sgrid_shadow_release(g, sh); else cudaFree(phi2);
+        return set_error(LSF_ERR_CUDA, "reinit_rk3: %s", cudaGetErrorString(e));
+    }
     double *phi1 = g->phiN;
+    slab_exchange(g, false);                                                                     // z-slabs: ghost planes of phi current
     LSF_CUDA(cudaMemcpyAsync(g->phiS, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));       // frozen sign source
     LSF_CUDA(cudaMemcpyAsync(phi1, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));          // boundary points of the stage buffers
     LSF_CUDA(cudaMemcpyAsync(phi2, g->phi, bytes, cudaMemcpyDeviceToDevice, G.stream));
@@ -847,13 +865,16 @@ int lsf_grid_reinit_rk3(lsf_grid *g, int steps, double dx, double dt, double tol
     tm.start();
     Ctrl hc = {0, 0, 0, 0, 0};
     for (int n = 0; n < steps; ++n) {
-        launch_rk_stage(g, g->phi, g->phi, phi1, cc, 0., 1., scratch, nullptr);
-        launch_reinit_bc_buf(g, phi1, dx);
-        launch_rk_stage(g, phi1, g->phi, phi2, cc, 0.75, 0.25, scratch, nullptr);
-        launch_reinit_bc_buf(g, phi2, dx);
-        launch_rk_stage(g, phi2, g->phi, g->phi, cc, 1. / 3., 2. / 3., scratch, g->partial);    // interior part of the RMS -> partial[0]
+        launch_rk_stage(g, g->phi, g->phi, phi1, cc, 0., 1., scratch, nullptr, mg ? g : nullptr);
+        if (mg) { launch_reinit_bc_rms_buf(g, phi1, dx, scratch + nblk); slab_exchange(g, true, phi1); }
+        else launch_reinit_bc_buf(g, phi1, dx);
+        launch_rk_stage(g, phi1, g->phi, phi2, cc, 0.75, 0.25, scratch, nullptr, mg ? g : nullptr);
+        if (mg) { launch_reinit_bc_rms_buf(g, phi2, dx, scratch + nblk); slab_exchange(sh, true, phi2); }
+        else launch_reinit_bc_buf(g, phi2, dx);
+        launch_rk_stage(g, phi2, g->phi, g->phi, cc, 1. / 3., 2. / 3., scratch, g->partial, mg ? sh : nullptr);    // interior part of the RMS -> partial[0]
         launch_reinit_bc_rms(g, dx, 1);                                                          // boundary block + its part -> partial[1..]
-        launch_finalize(g, 1 + BC_BLOCKS, 0, tol);
+        if (mg) { launch_finalize_slab(g, 1 + BC_BLOCKS, 0, tol, n); slab_exchange(g, true); }
+        else launch_finalize(g, 1 + BC_BLOCKS, 0, tol);
         if ((n + 1) % 16 == 0 || n == steps - 1) {
             rc = read_ctrl(g, &hc);
             if (rc) break;
@@ -861,7 +882,9 @@ int lsf_grid_reinit_rk3(lsf_grid *g, int steps, double dx, double dt, double tol
         }
     }
     const int rc_t = tm.stop();                                        // before the (slow, synchronising) cudaFree calls
-    cudaFree(phi2); cudaFree(scratch);
+    if (mg) { slab_exchange(g, false); cudaStreamSynchronize(G.stream); const int rc_s = sgrid_shadow_release(g, sh); if (!rc) rc = rc_s; }
+    else cudaFree(phi2);
+    cudaFree(scratch);
     if (rc) return rc;
     if (rc_t) return rc_t;
     LSF_CUDA(cudaGetLastError());

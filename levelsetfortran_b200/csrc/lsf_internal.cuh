@@ -104,6 +104,7 @@ void launch_reinit_sweep_plane(Grid *g, int raster, const CellConst &cc, double 
 void launch_reinit_bc(Grid *g, double dx);
 void launch_reinit_bc_buf(Grid *g, double *buf, double dx);
 void launch_reinit_bc_rms(Grid *g, double dx, int partial_off);
+void launch_reinit_bc_rms_buf(Grid *g, double *buf, double dx, double *partial);
 void launch_rms(Grid *g, bool copy);
 void launch_finalize(Grid *g, int npart, int hist_off, double tol, const double *partial = nullptr);
 void launch_copy_boundary(Grid *g, double *dst, const double *src);
@@ -171,7 +172,7 @@ int f32_shadow_close(Grid *g, lsf_grid *shadow, bool write_back);
 // lsf_rk.cu -- K2' throughput mode (Jacobi WENO5 + TVD-RK3; not the reference's algorithm)
 long long rk_nblocks(const Grid *g);
 void launch_rk_stage(Grid *g, const double *in, const double *phin, double *out, const CellConst &cc, double a, double b,
-                     double *scratch_partial, double *rms_out);
+                     double *scratch_partial, double *rms_out, Grid *halo_grid = nullptr);
 
 // lsf_mm_march.cu
 int mm_march_prepare(Grid *g);

@@ -170,6 +170,15 @@ k_reinit_bc_rms(double *__restrict__ phi, Dims dm, double dx, double *__restrict
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// the same on any field of the grid's shape (stage buffers of lsf_grid_reinit_rk3 on z-slabs); the RMS part goes to `partial`
+void launch_reinit_bc_rms_buf(Grid *g, double *buf, double dx, double *partial)
+{
+    const SlabGeom &sg = g->sg;
+    k_reinit_bc_rms<<<BC_BLOCKS, 256, 0, G.stream>>>(buf, g->dm, dx, partial, g->ctrl, sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ, sg.k0 == 0,
+                                                     sg.k1 == sg.NZ + 1);
+    G.n_launch++;
+}
+
 void launch_reinit_bc_rms(Grid *g, double dx, int partial_off)
 {
     const SlabGeom &sg = g->sg;

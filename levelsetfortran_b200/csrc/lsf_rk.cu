@@ -19,6 +19,7 @@
 // FP64-pipe bound here as in the sweep kernel (about 260 FP64 instructions per cell, lsf_cell.cuh).
 #include "lsf_internal.cuh"
 #include "lsf_cell.cuh"
+#include "lsf_march.cuh"      // wait_ge (system-scope flag wait)
 
 namespace lsf {
 
@@ -27,13 +28,22 @@ constexpr int RK_TX = 32, RK_TY = 8, RK_ZC = 32;
 template <class AR>
 __global__ void __launch_bounds__(RK_TX *RK_TY, 2)
 k_rk_stage(const double *in, const double *phin, const double *__restrict__ phiS, double *out, Dims dm, CellConst cc,
-           double a, double b, double *__restrict__ partial, const Ctrl *__restrict__ ctrl, int want_rms)
+           double a, double b, double *__restrict__ partial, const Ctrl *__restrict__ ctrl, int want_rms,
+           int kA, int kB, int kbase, int NZ,       // z-slab: local planes kA..kB are updated, local plane k is global plane k + kbase of 0..NZ
+           const long long *halo_seq, long long need0, long long need1, Ctrl *ctrl_w)   // z-slab: `in`'s ghost planes must have arrived
 {
     if (ctrl->done) return;
+    if (halo_seq) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            if (need0) wait_ge<true>(halo_seq + 0, need0, ctrl_w);
+            if (need1) wait_ge<true>(halo_seq + 1, need1, ctrl_w);
+        }
+        __syncthreads();
+    }
     const int i = 1 + blockIdx.x * RK_TX + threadIdx.x;
     const int j = 1 + blockIdx.y * RK_TY + threadIdx.y;
-    const int k0 = 1 + blockIdx.z * RK_ZC;
-    const int k1 = min(k0 + RK_ZC - 1, dm.nz - 1);
+    const int k0 = kA + blockIdx.z * RK_ZC;
+    const int k1 = min(k0 + RK_ZC - 1, kB);
     double acc = 0.;
     if (i <= dm.nx - 1 && j <= dm.ny - 1) {
         const bool hij = (i > 3) && (i < dm.nx - 4) && (j > 3) && (j < dm.ny - 4);      // subs.f90:506
@@ -59,7 +69,7 @@ k_rk_stage(const double *in, const double *phin, const double *__restrict__ phiS
                 vx[2] = __ldg(in + c - 1); vx[3] = q[3]; vx[4] = __ldg(in + c + 1);
                 vy[2] = __ldg(in + c - dm.sx); vy[3] = q[3]; vy[4] = __ldg(in + c + dm.sx);
             }
-            const bool hi = hij && (k > 3) && (k < dm.nz - 4);
+            const bool hi = hij && (k + kbase > 3) && (k + kbase < NZ - 4);
             double g[3], gM;
             bool sens;
             const double e = reinit_cell<AR>(vx, vy, q, __ldg(phiS + c), hi, cc, g, gM, sens);      // u + dt sgn (1 - |grad u|)
@@ -103,21 +113,28 @@ __global__ void k_rk_sum(const double *__restrict__ partial, long long n, double
 
 long long rk_nblocks(const Grid *g)
 {
-    const long long bx = (g->dm.nx - 1 + RK_TX - 1) / RK_TX, by = (g->dm.ny - 1 + RK_TY - 1) / RK_TY, bz = (g->dm.nz - 1 + RK_ZC - 1) / RK_ZC;
+    const long long nk = g->sg.kupd_hi - g->sg.kupd_lo + 1;
+    const long long bx = (g->dm.nx - 1 + RK_TX - 1) / RK_TX, by = (g->dm.ny - 1 + RK_TY - 1) / RK_TY, bz = (nk + RK_ZC - 1) / RK_ZC;
     return bx * by * bz;
 }
 
 // one stage: out = a*phin + b*(in + dt L(in)); with want_rms the sum over the interior of (out - phin)^2 lands in rms_out[0]
+// hg: the sharded grid whose last ghost-plane exchange refreshed `in` (g itself, or the transient grid that owns phi2); null on one GPU
 void launch_rk_stage(Grid *g, const double *in, const double *phin, double *out, const CellConst &cc, double a, double b,
-                     double *scratch_partial, double *rms_out)
+                     double *scratch_partial, double *rms_out, Grid *hg)
 {
-    dim3 grid((g->dm.nx - 1 + RK_TX - 1) / RK_TX, (g->dm.ny - 1 + RK_TY - 1) / RK_TY, (g->dm.nz - 1 + RK_ZC - 1) / RK_ZC);
+    const long long *hs = (hg && sharded(hg)) ? hg->sync->halo_seq : nullptr;
+    const long long n0 = (hs && hg->sg.rank > 0) ? hg->phase : 0, n1 = (hs && hg->sg.rank < hg->sg.nranks - 1) ? hg->phase : 0;
+    const SlabGeom &sg = g->sg;      // one GPU: kupd_lo = 1, kupd_hi = nz-1, kbase = 0, NZ = nz
+    dim3 grid((g->dm.nx - 1 + RK_TX - 1) / RK_TX, (g->dm.ny - 1 + RK_TY - 1) / RK_TY, (sg.kupd_hi - sg.kupd_lo + 1 + RK_ZC - 1) / RK_ZC);
     dim3 block(RK_TX, RK_TY);
     const int want = rms_out != nullptr;
     if (G.arith_run == LSF_ARITH_EXACT)
-        k_rk_stage<ExactArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want);
+        k_rk_stage<ExactArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want,
+                                                             sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ, hs, n0, n1, g->ctrl);
     else
-        k_rk_stage<FastArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want);
+        k_rk_stage<FastArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want,
+                                                            sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ, hs, n0, n1, g->ctrl);
     G.n_launch++;
     if (want) {
         k_rk_sum<<<1, 1024, 0, G.stream>>>(scratch_partial, rk_nblocks(g), rms_out, g->ctrl);
