@@ -23,10 +23,18 @@
 
 namespace lsf {
 
-constexpr int RK_TX = 32, RK_TY = 8, RK_ZC = 32;
+#ifndef LSF_RK_ZC
+#define LSF_RK_ZC 64
+#endif
+constexpr int RK_TX = 32, RK_TY = 8, RK_ZC = LSF_RK_ZC;   // planes a block marches through (its z-queue warm-up re-reads 6 planes)
 
+#ifndef LSF_RK_OCC
+#define LSF_RK_OCC 4            // resident CTAs per SM the stage kernel is compiled for (64 registers, 64 B of spills).  Session 31, Gcell-stage-updates/s at
+                                // 1024^3: 2 CTAs (126 registers) 38.9, 3 (79) 46.3, 4 47.8 -- the kernel waits on its in-plane loads (ncu r2l: long scoreboard
+                                // 3.5 per issue at 16 warps per SM), so more resident warps pay
+#endif
 template <class AR>
-__global__ void __launch_bounds__(RK_TX *RK_TY, 2)
+__global__ void __launch_bounds__(RK_TX *RK_TY, LSF_RK_OCC)
 k_rk_stage(const double *in, const double *phin, const double *__restrict__ phiS, double *out, Dims dm, CellConst cc,
            double a, double b, double *__restrict__ partial, const Ctrl *__restrict__ ctrl, int want_rms,
            int kA, int kB, int kbase, int NZ,       // z-slab: local planes kA..kB are updated, local plane k is global plane k + kbase of 0..NZ
