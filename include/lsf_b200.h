@@ -190,7 +190,9 @@ int lsf_grid_minmax(lsf_grid *g, int iter, double dx, double h1, double tol,
  * RK scaffolding, set3d.f90:28,285-287, is never used): `steps` TVD Runge-Kutta-3 steps of the Jacobi WENO5 reinitialisation
  * equation phi_t = sgn(phi0)(1 - |grad phi|), the scheme BASELINE.json's north_star names.  Differs from lsf_grid_reinit by
  * ~4e-4 and in iteration count; same per-cell arithmetic, high-order window, boundary block (after every
- * stage) and RMS / EXIT / NaN tests (per step).  fp64, single GPU.  n_exit: 0-based index of the last executed step. */
+ * stage) and RMS / EXIT / NaN tests (per step).  fp64; one GPU or z-slabs (there a plain halo problem: the stage buffers'
+ * ghost planes are exchanged after every stage; phi bit-identical to the single-GPU run of the mode).  n_exit: 0-based index of
+ * the last executed step. */
 int lsf_grid_reinit_rk3(lsf_grid *g, int steps, double dx, double dt, double tol, int *n_exit, double *rms_hist);
 /* lsf_advect_nodes on the resident phi; phiSB is the band the reference holds at that point: that of the field the
  * last narrowBand call saw (phi, or the previous iterate after a tolerance EXIT of lsf_grid_minmax).  On a sharded grid every
