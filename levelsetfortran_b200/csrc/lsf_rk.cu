@@ -103,6 +103,121 @@ k_rk_stage(const double *in, const double *phin, const double *__restrict__ phiS
     }
 }
 
+// The same stage with the in-plane neighbours through shared memory (-DLSF_RK_TILE=1; measured alternative, off): per plane every thread deposits the
+// value of its own column (it sits in the z-queue already) into a (TY+6) x (TX+6) tile, the 3-wide ring around the tile is fetched
+// from global memory ONE PLANE AHEAD into two registers per thread, and the 12 x / y stencil values are shared-memory loads --
+// instead of 12 L1 loads per cell whose latency the few resident warps cannot hide (ncu r2l: long scoreboard 3.5 per issue).
+// Two tiles alternate, so one __syncthreads per plane.  Same values, same arithmetic: bit-identical to k_rk_stage.
+// Session 33, 1024^3: 42.3 Gcell-stage-updates/s (4 CTAs/SM; 42.1 at 3) against 47.8 for the L1 version -- the deposits and the
+// barrier per plane cost more than the L1 hits they replace; the L1 version with 4 resident CTAs stays the default.
+template <class AR>
+__global__ void __launch_bounds__(RK_TX *RK_TY, LSF_RK_OCC)
+k_rk_stage_tile(const double *in, const double *phin, const double *__restrict__ phiS, double *out, Dims dm, CellConst cc,
+                double a, double b, double *__restrict__ partial, const Ctrl *__restrict__ ctrl, int want_rms,
+                int kA, int kB, int kbase, int NZ, const long long *halo_seq, long long need0, long long need1, Ctrl *ctrl_w)
+{
+    if (ctrl->done) return;
+    constexpr int SW = RK_TX + 6, SH = RK_TY + 6, NT = RK_TX * RK_TY, NH = SW * SH - NT;   // tile pitch / rows, threads, ring cells
+    constexpr int HPT = (NH + NT - 1) / NT;                                                  // ring cells per thread (2)
+    __shared__ double tile[2][SH][SW];
+    __shared__ double sh[NT];
+    const int t = threadIdx.x + RK_TX * threadIdx.y;
+    if (halo_seq) {
+        if (t == 0) {
+            if (need0) wait_ge<true>(halo_seq + 0, need0, ctrl_w);
+            if (need1) wait_ge<true>(halo_seq + 1, need1, ctrl_w);
+        }
+        __syncthreads();
+    }
+    const int i0 = 1 + blockIdx.x * RK_TX, j0 = 1 + blockIdx.y * RK_TY;
+    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
+    const int k0 = kA + blockIdx.z * RK_ZC;
+    const int k1 = min(k0 + RK_ZC - 1, kB);
+    const bool inArr = (i <= dm.nx) && (j <= dm.ny);                 // the column exists (its values feed the neighbours)
+    const bool comp = (i <= dm.nx - 1) && (j <= dm.ny - 1);          // ... and is updated
+    const bool hij = (i > 3) && (i < dm.nx - 4) && (j > 3) && (j < dm.ny - 4);      // subs.f90:506
+    const long long base = i + dm.sx * j;
+    // ring cells of this thread: index h in 0..NH-1 enumerates the tile's cells that are not one of the NT centres, row-major
+    long long hoff[HPT];
+    int hrow[HPT], hcol[HPT];
+    bool hok[HPT];
+#pragma unroll
+    for (int r = 0; r < HPT; ++r) {
+        const int h = t + r * NT;
+        int row = 0, col = 0;
+        bool ok = h < NH;
+        if (ok) {
+            // rows 0..2 and SH-3..SH-1 are whole ring rows (SW cells each); the middle rows contribute 3 cells left and 3 right
+            if (h < 3 * SW) { row = h / SW; col = h % SW; }
+            else if (h < 3 * SW + RK_TY * 6) { const int q2 = h - 3 * SW; row = 3 + q2 / 6; const int c6 = q2 % 6; col = c6 < 3 ? c6 : RK_TX + c6; }
+            else { const int q2 = h - 3 * SW - RK_TY * 6; row = 3 + RK_TY + q2 / SW; col = q2 % SW; }
+            const int gi = i0 - 3 + col, gj = j0 - 3 + row;
+            ok = gi >= 0 && gi <= dm.nx && gj >= 0 && gj <= dm.ny;
+            hoff[r] = gi + dm.sx * (long long)gj;
+        } else hoff[r] = 0;
+        hrow[r] = row; hcol[r] = col; hok[r] = ok;
+    }
+    double acc = 0.;
+    double q[7];
+#pragma unroll
+    for (int m = -3; m <= 3; ++m) {
+        const int kk = min(max(k0 + m, 0), dm.nz);
+        q[m + 3] = inArr ? __ldg(in + base + dm.sxy * kk) : 0.;
+    }
+    double hv[HPT];
+#pragma unroll
+    for (int r = 0; r < HPT; ++r) hv[r] = hok[r] ? __ldg(in + hoff[r] + dm.sxy * k0) : 0.;
+    for (int k = k0; k <= k1; ++k) {
+        double(*T)[SW] = tile[(k - k0) & 1];
+        T[threadIdx.y + 3][threadIdx.x + 3] = q[3];
+#pragma unroll
+        for (int r = 0; r < HPT; ++r)
+            if (t + r * NT < NH) T[hrow[r]][hcol[r]] = hv[r];
+        __syncthreads();
+        if (k < k1) {                                                 // the ring of the next plane: in flight during this plane's arithmetic
+#pragma unroll
+            for (int r = 0; r < HPT; ++r) hv[r] = hok[r] ? __ldg(in + hoff[r] + dm.sxy * (k + 1)) : 0.;
+        }
+        if (comp) {
+            const long long c = base + dm.sxy * k;
+            double vx[7], vy[7];
+            if (hij) {
+#pragma unroll
+                for (int m = -3; m <= 3; ++m) {
+                    vx[m + 3] = (m == 0) ? q[3] : T[threadIdx.y + 3][threadIdx.x + 3 + m];
+                    vy[m + 3] = (m == 0) ? q[3] : T[threadIdx.y + 3 + m][threadIdx.x + 3];
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 7; ++m) { vx[m] = 0.; vy[m] = 0.; }
+                vx[2] = T[threadIdx.y + 3][threadIdx.x + 2]; vx[3] = q[3]; vx[4] = T[threadIdx.y + 3][threadIdx.x + 4];
+                vy[2] = T[threadIdx.y + 2][threadIdx.x + 3]; vy[3] = q[3]; vy[4] = T[threadIdx.y + 4][threadIdx.x + 3];
+            }
+            const bool hi = hij && (k + kbase > 3) && (k + kbase < NZ - 4);
+            double g[3], gM;
+            bool sens;
+            const double e = reinit_cell<AR>(vx, vy, q, __ldg(phiS + c), hi, cc, g, gM, sens);
+            const double pold = (a != 0. || want_rms) ? phin[c] : 0.;
+            const double o = (a != 0.) ? fma(a, pold, b * e) : e;
+            out[c] = o;
+            if (want_rms) { const double d = o - pold; acc = fma(d, d, acc); }
+        }
+#pragma unroll
+        for (int m = 0; m < 6; ++m) q[m] = q[m + 1];
+        q[6] = inArr ? __ldg(in + base + dm.sxy * min(k + 4, dm.nz)) : 0.;
+    }
+    if (want_rms) {
+        __syncthreads();
+        sh[t] = acc;
+        __syncthreads();
+        for (int w = NT / 2; w > 0; w >>= 1) {
+            if (t < w) sh[t] = sh[t] + sh[t + w];
+            __syncthreads();
+        }
+        if (t == 0) partial[blockIdx.x + gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z)] = sh[0];
+    }
+}
+
 // fixed-order sum of the stage's per-block partials into ONE partial slot (k_finalize then adds the boundary part)
 __global__ void k_rk_sum(const double *__restrict__ partial, long long n, double *__restrict__ out, const Ctrl *__restrict__ ctrl)
 {
@@ -137,7 +252,17 @@ void launch_rk_stage(Grid *g, const double *in, const double *phin, double *out,
     dim3 grid((g->dm.nx - 1 + RK_TX - 1) / RK_TX, (g->dm.ny - 1 + RK_TY - 1) / RK_TY, (sg.kupd_hi - sg.kupd_lo + 1 + RK_ZC - 1) / RK_ZC);
     dim3 block(RK_TX, RK_TY);
     const int want = rms_out != nullptr;
-    if (G.arith_run == LSF_ARITH_EXACT)
+#ifndef LSF_RK_TILE
+#define LSF_RK_TILE 0
+#endif
+    if (LSF_RK_TILE) {
+        if (G.arith_run == LSF_ARITH_EXACT)
+            k_rk_stage_tile<ExactArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want,
+                                                                      sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ, hs, n0, n1, g->ctrl);
+        else
+            k_rk_stage_tile<FastArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want,
+                                                                     sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ, hs, n0, n1, g->ctrl);
+    } else if (G.arith_run == LSF_ARITH_EXACT)
         k_rk_stage<ExactArith><<<grid, block, 0, G.stream>>>(in, phin, g->phiS, out, g->dm, cc, a, b, scratch_partial, g->ctrl, want,
                                                              sg.kupd_lo, sg.kupd_hi, sg.kbase, sg.NZ, hs, n0, n1, g->ctrl);
     else
