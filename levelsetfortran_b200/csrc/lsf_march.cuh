@@ -214,6 +214,10 @@ LSF_DEV void p_bar_wait(unsigned long long *bar, unsigned phase)
                                 //    Session 14, fp64 / fp32 Gcell/s at 1024^3: 0 -> 33.5 / 45.8, 1 -> 33.9 / 49.0, 3 -> 33.6 / 8.5 (!), 7 -> 30.9 / 7.1,
                                 //    15 -> 33.6 / 13.0: a look-ahead or halo load left in flight across the step's stores to the same rows is
                                 //    expensive (fp32 most: 8 cells per sector), so only phiS -- read-only -- is fetched ahead
+#ifndef LSF_PUB_FENCE
+#define LSF_PUB_FENCE 1         // 1: a __threadfence (fence.sc.gpu) before the release store that publishes a tile's progress.  The release store
+#endif                          //    alone is sufficient (all threads' stores -> step barrier -> one thread's gpu-scope release: cumulative); 0 drops the
+                                //    sequentially-consistent fence from the critical path of every chunk
 #ifndef LSF_PIN_LOADS
 #define LSF_PIN_LOADS 2         // see the step body
 #endif
@@ -897,7 +901,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
         } else p_sync();
 #endif
         if (pub && tid == TID_PUB) {
-            p_fence(); p_st_release(mine, ebase + M_BIAS + t);
+            if (LSF_PUB_FENCE) p_fence();
+            p_st_release(mine, ebase + M_BIAS + t);
             if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + t); }
         }
     };
@@ -966,7 +971,8 @@ LSF_DEV void march_tile(const MarchParamsT<typename AR::real> &p, MarchSmem<CFG>
     sm.red[tid] = (double)acc;
     p_sync();
     if (tid == 0) {
-        p_fence(); p_st_release(mine, ebase + M_BIAS + M_FIN);
+        if (LSF_PUB_FENCE) p_fence();
+        p_st_release(mine, ebase + M_BIAS + M_FIN);
         if (minePeer) { p_fence_sys(); p_st_release_sys(minePeer, ebase + M_BIAS + M_FIN); }
         if (MG && K == 0 && p.edge_pub[0]) { p_fence_sys(); p_st_release_sys(p.edge_pub[0] + J, p.epoch); }
         if (MG && K == p.ntc - 1 && p.edge_pub[1]) { p_fence_sys(); p_st_release_sys(p.edge_pub[1] + J, p.epoch); }
