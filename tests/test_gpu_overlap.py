@@ -1,7 +1,6 @@
 """GPU parity of the opt-in overlapped-sweeps schedule of reinit (lsf_set_overlap): same results as
 the one-launch-per-sweep schedule -- bit-identical in EXACT arithmetic, identical exit iteration, including a tolerance
 EXIT and a NaN STOP that fall inside a batch of 8 sweeps."""
-import os
 
 import numpy as np
 import pytest
